@@ -1,0 +1,174 @@
+/*
+ * lvdgs.h -- C ABI of the B200-native (sm_100a) differentiable Gaussian-splatting rasterizer.
+ *
+ * Drop-in boundary for the two native plugins zwk0901/LVD_GS-SLAM calls on every tracking / mapping
+ * iteration (README.md:39-44 of the reference: `pip install submodules/simple-knn`,
+ * `pip install submodules/diff-gaussian-rasterization`; their sources are in the dropped submodules.zip,
+ * /root/reference/.MISSING_LARGE_BLOBS:1).  Each entry point below names the upstream `_C` export it
+ * replaces and the in-tree call site that reaches it.
+ *
+ * Conventions: plain pointers and sizes only; every array pointer is DEVICE memory unless it says "host";
+ * float = IEEE binary32; 4x4 matrices are 16 floats in the reference's transposed layout, i.e. the flat
+ * array is the column-major math matrix (utils/camera_utils.py:106-120).  `stream` is a cudaStream_t passed
+ * as void*.  Functions return 0 on success, non-zero on error (message: lvdgs_last_error()).  No allocation
+ * happens inside the library: growable buffers are obtained through the caller's lvdgs_resize_fn, exactly
+ * like upstream's `resizeFunctional` over torch uint8 tensors.  The only host synchronisation is the one
+ * upstream has too: reading back the instance count R between binning and sorting.
+ */
+#ifndef LVDGS_H
+#define LVDGS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVDGS_TILE 16
+
+/* flags (all off = upstream behaviour) */
+#define LVDGS_FLAG_EXACT_PP 1      /* pose Jacobian keeps the principal-point entries Pr[8], Pr[9] */
+#define LVDGS_FLAG_OPACITY_GRAD 2  /* propagate dL/d(out_opacity) through the blend backward */
+
+/* which buffer a resize callback is asked for */
+#define LVDGS_BUF_GEOM 0
+#define LVDGS_BUF_BINNING 1
+#define LVDGS_BUF_IMG 2
+
+typedef struct lvdgs_raster_params {
+    int32_t P;            /* Gaussians */
+    int32_t sh_degree;    /* active SH degree D (0..3) */
+    int32_t sh_coeffs;    /* coefficients stored per Gaussian M >= (D+1)^2; ignored when colors_precomp != NULL */
+    int32_t width, height;
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    int32_t prefiltered;  /* accepted for signature parity; unused (as upstream) */
+    int32_t debug;        /* 1: synchronise and check for CUDA errors after every kernel */
+    int32_t flags;        /* LVDGS_FLAG_* */
+} lvdgs_raster_params;
+
+/* Must return a device pointer to at least `bytes` bytes, 256-byte aligned, valid until the matching backward
+ * has run.  Called at most once per buffer per forward, from the calling thread. */
+typedef void *(*lvdgs_resize_fn)(void *user, int32_t which, size_t bytes);
+
+/* Byte offsets of the arrays inside the three opaque buffers (for parity tests and debuggers). */
+typedef struct lvdgs_geom_layout {
+    size_t depths;         /* float  [P]    view-space z */
+    size_t means2D;        /* float2 [P]    pixel centre */
+    size_t conic_opacity;  /* float4 [P]    conic xx,xy,yy + opacity */
+    size_t rgbd;           /* float4 [P]    rgb after SH + clamp, w = depth */
+    size_t rect;           /* int16x4 [P]   tile rect min.x,min.y,max.x,max.y */
+    size_t tiles_touched;  /* uint32 [P] */
+    size_t point_offsets;  /* uint32 [P]    inclusive scan of tiles_touched */
+    size_t clamped;        /* uint8  [P]    bit c set: channel c clamped at 0 */
+    size_t total;
+} lvdgs_geom_layout;
+
+typedef struct lvdgs_binning_layout {
+    size_t keys[2];        /* uint64 [R] x2  (tile << 32 | depth bits); double buffer */
+    size_t vals[2];        /* uint32 [R] x2  Gaussian index */
+    size_t sort_ws;        /* onesweep histograms + look-back state */
+    size_t sorted_sel;     /* int32: which of the two key/val buffers holds the sorted result */
+    size_t total;
+} lvdgs_binning_layout;
+
+typedef struct lvdgs_img_layout {
+    size_t final_T;        /* float  [H*W] */
+    size_t n_contrib;      /* uint32 [H*W] */
+    size_t ranges;         /* uint2  [tiles] */
+    size_t total;
+} lvdgs_img_layout;
+
+int lvdgs_version(void);
+const char *lvdgs_last_error(void);
+int lvdgs_set_device(int device);
+/* kernels launched by this library since the last reset (bench.py's gpu_launches) */
+int64_t lvdgs_launch_count(void);
+void lvdgs_reset_launch_count(void);
+
+/*
+ * Per-launch device timing for bench.py's roofline: between begin and end every kernel launch of this library is
+ * followed by a CUDA event on the launching stream.  lvdgs_profile_end synchronises the stream and returns the
+ * number of entries n (or -1): ms[i] = time between the events before and after launch i, names = n
+ * newline-separated kernel names.  Not thread-safe; never enable inside a timed region.
+ */
+int lvdgs_profile_begin(void *stream);
+int lvdgs_profile_end(void *stream, char *names, size_t names_bytes, float *ms, int32_t max_entries);
+
+int lvdgs_get_geom_layout(int32_t P, lvdgs_geom_layout *out);
+int lvdgs_get_binning_layout(int64_t R, lvdgs_binning_layout *out);
+int lvdgs_get_img_layout(int32_t width, int32_t height, lvdgs_img_layout *out);
+
+/*
+ * Replaces `_C.rasterize_gaussians` (upstream rasterize_points.cu: RasterizeGaussiansCUDA), reached from
+ * gaussian_renderer.render at utils/slam_frontend.py:1493, utils/slam_backend.py:98,184,277,407,
+ * utils/eval_utils_0806.py:215 and render_with_custom_resolution at utils/init_pose.py:145.
+ *   means3D [P,3]; opacities [P]; exactly one of {shs [P,M,3], colors_precomp [P,3]};
+ *   exactly one of {scales [P,3] + rotations [P,4], cov3D_precomp [P,6]}; background [3]; campos [3].
+ * Outputs: out_color [3,H,W], radii [P] int32, out_depth [H,W], out_opacity [H,W], n_touched [P] int32,
+ *   *num_rendered (host) = R, the number of (tile, Gaussian) instances.
+ */
+int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *background, const float *means3D,
+                            const float *colors_precomp, const float *opacities, const float *scales,
+                            const float *rotations, const float *cov3D_precomp, const float *viewmatrix,
+                            const float *projmatrix, const float *projmatrix_raw, const float *shs,
+                            const float *campos, lvdgs_resize_fn resize, void *resize_user, float *out_color,
+                            int32_t *radii, float *out_depth, float *out_opacity, int32_t *n_touched,
+                            int64_t *num_rendered, void *stream);
+
+/* Device scratch needed by lvdgs_rasterize_backward for P Gaussians and R instances. */
+size_t lvdgs_backward_scratch_bytes(int32_t P, int64_t R);
+
+/*
+ * Replaces `_C.rasterize_gaussians_backward` (upstream RasterizeGaussiansBackwardCUDA), reached through
+ * loss.backward() at utils/slam_frontend.py:1517 and utils/slam_backend.py:120,306,457.
+ *   dL_dout_color [3,H,W]; dL_dout_depth [H,W] or NULL; dL_dout_opacity [H,W] or NULL (used only with
+ *   LVDGS_FLAG_OPACITY_GRAD; upstream drops it).  geom/binning/img buffers and R are those of the forward.
+ * Outputs (every element written, no pre-zeroing needed): dL_dmeans2D [P,3] (z = 0), dL_dcolors [P,3],
+ *   dL_dopacity [P], dL_dmeans3D [P,3], dL_dcov3D [P,6], dL_dsh [P,M,3] (NULL ok with colors_precomp),
+ *   dL_dscales [P,3], dL_drots [P,4] (NULL ok with cov3D_precomp), dL_dtau [P,6] = (rho, theta) per Gaussian
+ *   (NULL ok), dL_dtau_sum [6] = the sum over Gaussians that upstream forms in Python
+ *   (`grad_tau.view(-1,6).sum(0)`) (NULL ok).
+ */
+int lvdgs_rasterize_backward(const lvdgs_raster_params *prm, const float *background, const float *means3D,
+                             const int32_t *radii, const float *colors_precomp, const float *opacities,
+                             const float *scales, const float *rotations, const float *cov3D_precomp,
+                             const float *viewmatrix, const float *projmatrix, const float *projmatrix_raw,
+                             const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_opacity,
+                             const float *shs, const float *campos, const void *geom_buffer, int64_t R,
+                             const void *binning_buffer, const void *img_buffer, void *scratch,
+                             size_t scratch_bytes, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
+                             float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales,
+                             float *dL_drots, float *dL_dtau, float *dL_dtau_sum, void *stream);
+
+/* Replaces `_C.mark_visible` (GaussianRasterizer.markVisible): present[i] = view-space z > 0.2. */
+int lvdgs_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                       uint8_t *present, void *stream);
+
+/*
+ * Replaces `simple_knn._C.distCUDA2` (reached from GaussianModel.extend_from_pcd_seq, utils/slam_backend.py:75-78):
+ * mean_dists[i] = mean squared distance from points[i] to its 3 nearest neighbours (exact).
+ */
+size_t lvdgs_dist2_workspace_bytes(int32_t P);
+int lvdgs_dist2(int32_t P, const float *points, float *mean_dists, void *workspace, size_t workspace_bytes,
+                void *stream);
+
+/*
+ * The binning sort on its own (stable LSD radix sort of u64 keys with u32 values over key bits
+ * [0, end_bit)), exposed for parity tests and for the comparison against cub::DeviceRadixSort, the
+ * library call upstream makes.  keys/vals: two buffers each of n elements; input in [0];
+ * *selector (host) receives the buffer index that holds the sorted result.
+ */
+size_t lvdgs_sort_workspace_bytes(int64_t n);
+int lvdgs_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1,
+                     int32_t end_bit, void *workspace, size_t workspace_bytes, int32_t *selector, void *stream);
+size_t lvdgs_cub_sort_workspace_bytes(int64_t n, int32_t end_bit);
+int lvdgs_cub_sort_pairs(int64_t n, const uint64_t *keys_in, uint64_t *keys_out, const uint32_t *vals_in,
+                         uint32_t *vals_out, int32_t end_bit, void *workspace, size_t workspace_bytes,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVDGS_H */

@@ -1,0 +1,303 @@
+// api.cu -- the extern "C" entry points declared in include/lvdgs.h: buffer layouts, argument checks and the
+// launch sequence of the forward and backward passes.  No torch types, no allocation, one host sync (R).
+#include "common.cuh"
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace lvdgs {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+thread_local int g_debug_sync = 0;
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-launch profiler: one CUDA event after every launch, on the launching stream ----
+struct ProfEntry { const char *name; cudaEvent_t ev; };
+static std::vector<ProfEntry> g_prof;
+static bool g_prof_on = false;
+
+int profile_mark(const char *name, cudaStream_t s) {
+    if (!g_prof_on) return 0;
+    ProfEntry e{name, nullptr};
+    LVDGS_CHECK(cudaEventCreate(&e.ev));
+    LVDGS_CHECK(cudaEventRecord(e.ev, s));
+    g_prof.push_back(e);
+    return 0;
+}
+
+static void geom_layout(int32_t P, lvdgs_geom_layout &l) {
+    size_t o = 0;
+    const size_t n = (size_t)(P > 0 ? P : 1);
+    l.depths = o; o += align_up(n * sizeof(float));
+    l.means2D = o; o += align_up(n * sizeof(float2));
+    l.conic_opacity = o; o += align_up(n * sizeof(float4));
+    l.rgbd = o; o += align_up(n * sizeof(float4));
+    l.rect = o; o += align_up(n * sizeof(short4));
+    l.tiles_touched = o; o += align_up(n * sizeof(uint32_t));
+    l.point_offsets = o; o += align_up(n * sizeof(uint32_t));
+    l.clamped = o; o += align_up(n * sizeof(uint8_t));
+    l.total = o;
+}
+static void binning_layout(int64_t R, lvdgs_binning_layout &l) {
+    size_t o = 0;
+    const size_t n = (size_t)(R > 0 ? R : 1);
+    for (int k = 0; k < 2; ++k) { l.keys[k] = o; o += align_up(n * sizeof(uint64_t)); }
+    for (int k = 0; k < 2; ++k) { l.vals[k] = o; o += align_up(n * sizeof(uint32_t)); }
+    l.sort_ws = o; o += align_up(sort_workspace_bytes((int64_t)n));
+    l.sorted_sel = o; o += 256;
+    l.total = o;
+}
+static void img_layout(int32_t W, int32_t H, lvdgs_img_layout &l) {
+    size_t o = 0;
+    const size_t n = (size_t)W * (size_t)H;
+    const size_t tiles = (size_t)((W + TILE - 1) / TILE) * (size_t)((H + TILE - 1) / TILE);
+    l.final_T = o; o += align_up(n * sizeof(float));
+    l.n_contrib = o; o += align_up(n * sizeof(uint32_t));
+    l.ranges = o; o += align_up(tiles * sizeof(uint2));
+    l.total = o;
+}
+
+static GeomPtrs geom_ptrs(void *base, int32_t P) {
+    lvdgs_geom_layout l; geom_layout(P, l);
+    char *b = (char *)base;
+    GeomPtrs g;
+    g.depths = (float *)(b + l.depths); g.means2D = (float2 *)(b + l.means2D);
+    g.conic_opacity = (float4 *)(b + l.conic_opacity); g.rgbd = (float4 *)(b + l.rgbd);
+    g.rect = (short4 *)(b + l.rect); g.tiles_touched = (uint32_t *)(b + l.tiles_touched);
+    g.point_offsets = (uint32_t *)(b + l.point_offsets); g.clamped = (uint8_t *)(b + l.clamped);
+    return g;
+}
+static BinPtrs bin_ptrs(void *base, int64_t R) {
+    lvdgs_binning_layout l; binning_layout(R, l);
+    char *b = (char *)base;
+    BinPtrs p;
+    for (int k = 0; k < 2; ++k) { p.keys[k] = (uint64_t *)(b + l.keys[k]); p.vals[k] = (uint32_t *)(b + l.vals[k]); }
+    p.sort_ws = b + l.sort_ws; p.sorted_sel = (int32_t *)(b + l.sorted_sel);
+    return p;
+}
+static ImgPtrs img_ptrs(void *base, int32_t W, int32_t H) {
+    lvdgs_img_layout l; img_layout(W, H, l);
+    char *b = (char *)base;
+    ImgPtrs p;
+    p.final_T = (float *)(b + l.final_T); p.n_contrib = (uint32_t *)(b + l.n_contrib); p.ranges = (uint2 *)(b + l.ranges);
+    return p;
+}
+
+static int check_params(const lvdgs_raster_params *p) {
+    if (!p) { set_error("params is NULL"); return 1; }
+    if (p->P < 0 || p->width <= 0 || p->height <= 0) { set_error("bad sizes P=%d W=%d H=%d", p->P, p->width, p->height); return 1; }
+    if (p->sh_degree < 0 || p->sh_degree > 3) { set_error("sh_degree %d not in 0..3", p->sh_degree); return 1; }
+    if (!(p->tan_fovx > 0.f) || !(p->tan_fovy > 0.f)) { set_error("tan_fov must be positive"); return 1; }
+    const int64_t tiles = (int64_t)((p->width + TILE - 1) / TILE) * ((p->height + TILE - 1) / TILE);
+    if ((p->width + TILE - 1) / TILE > 32767 || (p->height + TILE - 1) / TILE > 32767 || tiles > (1ll << 31)) {
+        set_error("image too large for the tile grid"); return 1;
+    }
+    return 0;
+}
+
+}  // namespace lvdgs
+
+using namespace lvdgs;
+
+extern "C" {
+
+int lvdgs_version(void) { return 100; }
+const char *lvdgs_last_error(void) { return g_err; }
+int lvdgs_set_device(int device) { LVDGS_CHECK(cudaSetDevice(device)); return 0; }
+int64_t lvdgs_launch_count(void) { return g_launches.load(); }
+void lvdgs_reset_launch_count(void) { g_launches.store(0); }
+
+int lvdgs_profile_begin(void *stream) {
+    for (auto &e : g_prof) cudaEventDestroy(e.ev);
+    g_prof.clear();
+    g_prof_on = true;
+    return profile_mark("(begin)", (cudaStream_t)stream);
+}
+
+int lvdgs_profile_end(void *stream, char *names, size_t names_bytes, float *ms, int32_t max_entries) {
+    g_prof_on = false;
+    LVDGS_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    std::string all;
+    int n = 0;
+    for (size_t i = 1; i < g_prof.size() && n < max_entries; ++i, ++n) {
+        float t = 0.f;
+        LVDGS_CHECK(cudaEventElapsedTime(&t, g_prof[i - 1].ev, g_prof[i].ev));
+        ms[n] = t;
+        all += g_prof[i].name;
+        all += '\n';
+    }
+    if (names && names_bytes) {
+        const size_t c = all.size() < names_bytes - 1 ? all.size() : names_bytes - 1;
+        memcpy(names, all.data(), c);
+        names[c] = 0;
+    }
+    for (auto &e : g_prof) cudaEventDestroy(e.ev);
+    g_prof.clear();
+    return n;
+}
+
+int lvdgs_get_geom_layout(int32_t P, lvdgs_geom_layout *out) { if (!out) return 1; geom_layout(P, *out); return 0; }
+int lvdgs_get_binning_layout(int64_t R, lvdgs_binning_layout *out) { if (!out) return 1; binning_layout(R, *out); return 0; }
+int lvdgs_get_img_layout(int32_t W, int32_t H, lvdgs_img_layout *out) { if (!out) return 1; img_layout(W, H, *out); return 0; }
+
+int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *background, const float *means3D,
+                            const float *colors_precomp, const float *opacities, const float *scales,
+                            const float *rotations, const float *cov3D_precomp, const float *viewmatrix,
+                            const float *projmatrix, const float *projmatrix_raw, const float *shs,
+                            const float *campos, lvdgs_resize_fn resize, void *resize_user, float *out_color,
+                            int32_t *radii, float *out_depth, float *out_opacity, int32_t *n_touched,
+                            int64_t *num_rendered, void *stream) {
+    (void)projmatrix_raw;
+    if (check_params(prm)) return 1;
+    const lvdgs_raster_params &p = *prm;
+    if ((shs == nullptr) == (colors_precomp == nullptr)) { set_error("provide exactly one of shs / colors_precomp"); return 1; }
+    const bool has_sr = scales != nullptr && rotations != nullptr;
+    if (has_sr == (cov3D_precomp != nullptr) || ((scales == nullptr) != (rotations == nullptr))) {
+        set_error("provide exactly one of (scales, rotations) / cov3D_precomp"); return 1;
+    }
+    if (shs && p.sh_coeffs < (p.sh_degree + 1) * (p.sh_degree + 1)) { set_error("sh_coeffs %d too small for degree %d", p.sh_coeffs, p.sh_degree); return 1; }
+    if (!resize || !out_color || !out_depth || !out_opacity || !num_rendered || !background || !viewmatrix || !projmatrix || !campos) {
+        set_error("NULL required argument"); return 1;
+    }
+    if (p.P > 0 && (!means3D || !opacities || !radii || !n_touched)) { set_error("NULL per-Gaussian argument"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    g_debug_sync = p.debug;
+    const int W = p.width, H = p.height;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    *num_rendered = 0;
+
+    lvdgs_img_layout il; img_layout(W, H, il);
+    void *img_base = resize(resize_user, LVDGS_BUF_IMG, il.total);
+    if (!img_base) { set_error("resize callback returned NULL (img)"); return 1; }
+    ImgPtrs im = img_ptrs(img_base, W, H);
+
+    int64_t R = 0;
+    GeomPtrs g{};
+    BinPtrs b{};
+    const uint32_t *point_list = nullptr;
+    if (p.P > 0) {
+        lvdgs_geom_layout gl; geom_layout(p.P, gl);
+        void *geom_base = resize(resize_user, LVDGS_BUF_GEOM, gl.total);
+        if (!geom_base) { set_error("resize callback returned NULL (geom)"); return 1; }
+        g = geom_ptrs(geom_base, p.P);
+        if (launch_preprocess_forward(p, means3D, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
+                                      projmatrix, shs, campos, radii, g, s)) return 1;
+        // the scan's block sums (ceil(P/2048) words) borrow n_touched, which is zeroed right after the R read-back
+        if (launch_scan_tiles(p.P, g.tiles_touched, g.point_offsets, reinterpret_cast<uint32_t *>(n_touched), s)) return 1;
+        uint32_t R32 = 0;
+        LVDGS_CHECK(cudaMemcpyAsync(&R32, g.point_offsets + (p.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        LVDGS_CHECK(cudaStreamSynchronize(s));
+        if (profile_mark("(host: R read-back)", s)) return 1;
+        R = R32;
+        LVDGS_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * (size_t)p.P, s));
+    }
+    *num_rendered = R;
+    if (R > 0) {
+        lvdgs_binning_layout bl; binning_layout(R, bl);
+        void *bin_base = resize(resize_user, LVDGS_BUF_BINNING, bl.total);
+        if (!bin_base) { set_error("resize callback returned NULL (binning)"); return 1; }
+        b = bin_ptrs(bin_base, R);
+        if (launch_emit_keys(p.P, W, H, g, radii, b.keys[0], b.vals[0], s)) return 1;
+        const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
+        int sel = 0;
+        if (launch_sort_pairs(R, b.keys[0], b.keys[1], b.vals[0], b.vals[1], end_bit, b.sort_ws,
+                              sort_workspace_bytes(R), &sel, s)) return 1;
+        LVDGS_CHECK(cudaMemcpyAsync(b.sorted_sel, &sel, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        if (launch_tile_ranges(R, gx * gy, b.keys[sel], im.ranges, s)) return 1;
+        point_list = b.vals[sel];
+    } else {
+        LVDGS_CHECK(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)gx * gy, s));
+    }
+    if (launch_blend_forward(W, H, im.ranges, point_list, g, background, out_color, out_depth, out_opacity, im.final_T,
+                             im.n_contrib, n_touched, s)) return 1;
+    return 0;
+}
+
+size_t lvdgs_backward_scratch_bytes(int32_t P, int64_t R) {
+    (void)R;
+    return align_up((size_t)(P > 0 ? P : 1) * ACC_STRIDE * sizeof(float));
+}
+
+int lvdgs_rasterize_backward(const lvdgs_raster_params *prm, const float *background, const float *means3D,
+                             const int32_t *radii, const float *colors_precomp, const float *opacities,
+                             const float *scales, const float *rotations, const float *cov3D_precomp,
+                             const float *viewmatrix, const float *projmatrix, const float *projmatrix_raw,
+                             const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_opacity,
+                             const float *shs, const float *campos, const void *geom_buffer, int64_t R,
+                             const void *binning_buffer, const void *img_buffer, void *scratch,
+                             size_t scratch_bytes, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
+                             float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales,
+                             float *dL_drots, float *dL_dtau, float *dL_dtau_sum, void *stream) {
+    (void)opacities;
+    if (check_params(prm)) return 1;
+    const lvdgs_raster_params &p = *prm;
+    cudaStream_t s = (cudaStream_t)stream;
+    g_debug_sync = p.debug;
+    if (p.P == 0) {
+        if (dL_dtau_sum) LVDGS_CHECK(cudaMemsetAsync(dL_dtau_sum, 0, 6 * sizeof(float), s));
+        return 0;
+    }
+    if (!geom_buffer || !img_buffer || (R > 0 && !binning_buffer) || !scratch || !dL_dout_color) { set_error("NULL buffer"); return 1; }
+    if (scratch_bytes < lvdgs_backward_scratch_bytes(p.P, R)) { set_error("backward scratch too small"); return 1; }
+    if (!dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dmeans3D || !dL_dcov3D) { set_error("NULL gradient output"); return 1; }
+    if (!colors_precomp && !dL_dsh) { set_error("dL_dsh required when shs are used"); return 1; }
+    if (!cov3D_precomp && (!dL_dscales || !dL_drots)) { set_error("dL_dscales / dL_drots required"); return 1; }
+    const int W = p.width, H = p.height;
+    GeomPtrs g = geom_ptrs(const_cast<void *>(geom_buffer), p.P);
+    ImgPtrs im = img_ptrs(const_cast<void *>(img_buffer), W, H);
+    BlendGradPtrs bg{(float *)scratch};
+    LVDGS_CHECK(cudaMemsetAsync(scratch, 0, (size_t)p.P * ACC_STRIDE * sizeof(float), s));
+    if (R > 0) {
+        BinPtrs b = bin_ptrs(const_cast<void *>(binning_buffer), R);
+        const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+        const int passes = (32 + tile_bits((uint32_t)(gx * gy)) + 7) / 8;
+        const int sel = passes & 1;
+        if (launch_blend_backward(p.P, W, H, R, im.ranges, b.vals[sel], g, background, im.final_T, im.n_contrib,
+                                  dL_dout_color, dL_dout_depth, dL_dout_opacity, p.flags, bg, s)) return 1;
+    }
+    if (launch_preprocess_backward(p, means3D, radii, shs, scales, rotations, cov3D_precomp, viewmatrix, projmatrix,
+                                   projmatrix_raw, campos, g, bg, colors_precomp != nullptr, dL_dmeans2D, dL_dcolors,
+                                   dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drots, dL_dtau,
+                                   dL_dtau_sum, s)) return 1;
+    return 0;
+}
+
+int lvdgs_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                       uint8_t *present, void *stream) {
+    (void)projmatrix;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { set_error("mark_visible: bad arguments"); return 1; }
+    g_debug_sync = 0;
+    return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+size_t lvdgs_dist2_workspace_bytes(int32_t P) { return dist2_workspace_bytes(P); }
+int lvdgs_dist2(int32_t P, const float *points, float *mean_dists, void *workspace, size_t workspace_bytes,
+                void *stream) {
+    if (P < 0 || (P > 0 && (!points || !mean_dists))) { set_error("dist2: bad arguments"); return 1; }
+    g_debug_sync = 0;
+    return launch_dist2(P, points, mean_dists, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t lvdgs_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n > 0 ? n : 1); }
+int lvdgs_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1,
+                     int32_t end_bit, void *workspace, size_t workspace_bytes, int32_t *selector, void *stream) {
+    g_debug_sync = 0;
+    int sel = 0;
+    const int rc = launch_sort_pairs(n, keys0, keys1, vals0, vals1, end_bit, workspace, workspace_bytes, &sel,
+                                     (cudaStream_t)stream);
+    if (selector) *selector = sel;
+    return rc;
+}
+
+}  // extern "C"

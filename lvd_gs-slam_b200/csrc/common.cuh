@@ -1,0 +1,121 @@
+// common.cuh -- shared definitions for the sm_100a rasterizer kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/lvdgs.h"
+
+namespace lvdgs {
+
+constexpr int TILE = LVDGS_TILE;
+constexpr int TILE_PIX = TILE * TILE;
+
+// ---- error plumbing (api.cu) ----
+void set_error(const char *fmt, ...);
+void count_launch();
+int profile_mark(const char *name, cudaStream_t s);   // records an event after the launch when profiling is on
+extern thread_local int g_debug_sync;
+
+#define LVDGS_CHECK(expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            lvdgs::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,               \
+                             cudaGetErrorString(_e));                                            \
+            return 1;                                                                            \
+        }                                                                                        \
+    } while (0)
+
+// after every kernel launch: count it, catch launch errors, optionally synchronise (debug)
+#define LVDGS_LAUNCHED(stream, name)                                                             \
+    do {                                                                                         \
+        lvdgs::count_launch();                                                                   \
+        LVDGS_CHECK(cudaGetLastError());                                                         \
+        if (lvdgs::profile_mark(name, stream)) return 1;                                         \
+        if (lvdgs::g_debug_sync) LVDGS_CHECK(cudaStreamSynchronize(stream));                     \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- canonical arithmetic: explicit IEEE ops, never re-contracted by nvcc ----
+__device__ __forceinline__ float dot3c(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
+}
+
+struct CameraConst {   // staged once per block in shared memory
+    float view[16];
+    float proj[16];
+    float campos[3];
+};
+
+// number of key bits that cover tile ids < n (same rule as upstream's getHigherMsb)
+static inline int tile_bits(uint32_t n) {
+    uint32_t msb = sizeof(n) * 4, step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step; else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return (int)msb;
+}
+
+// ---- kernel launchers (one per .cu) ----
+struct GeomPtrs {
+    float *depths; float2 *means2D; float4 *conic_opacity; float4 *rgbd; short4 *rect;
+    uint32_t *tiles_touched; uint32_t *point_offsets; uint8_t *clamped;
+};
+struct BinPtrs {
+    uint64_t *keys[2]; uint32_t *vals[2]; void *sort_ws; int32_t *sorted_sel;
+};
+struct ImgPtrs {
+    float *final_T; uint32_t *n_contrib; uint2 *ranges;
+};
+
+int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D, const float *colors_precomp,
+                              const float *opacities, const float *scales, const float *rotations,
+                              const float *cov3D_precomp, const float *view, const float *proj, const float *shs,
+                              const float *campos, int32_t *radii, const GeomPtrs &g, cudaStream_t s);
+int launch_scan_tiles(int P, const uint32_t *tiles_touched, uint32_t *point_offsets, uint32_t *block_sums,
+                      cudaStream_t s);
+int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, const int32_t *radii, uint64_t *keys, uint32_t *vals,
+                     cudaStream_t s);
+int launch_tile_ranges(int64_t R, int num_tiles, const uint64_t *keys_sorted, uint2 *ranges, cudaStream_t s);
+
+size_t sort_workspace_bytes(int64_t n);
+int launch_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1, int end_bit,
+                      void *ws, size_t ws_bytes, int *selector, cudaStream_t s);
+
+int launch_blend_forward(int W, int H, const uint2 *ranges, const uint32_t *point_list, const GeomPtrs &g,
+                         const float *bg, float *out_color, float *out_depth, float *out_opacity,
+                         float *final_T, uint32_t *n_contrib, int32_t *n_touched, cudaStream_t s);
+
+// Per-Gaussian accumulators produced by the blend backward: one 48-byte row per Gaussian so that a warp can
+// commit its partial sums with three 128-bit vector reductions (red.global.add.v4.f32).
+//   [0] dL_dmean2D.x  [1] dL_dmean2D.y  (NDC units)   [2] dL_dconic.xx  [3] dL_dconic.xy
+//   [4] dL_dconic.yy  [5] dL_dopacity   [6] dL_ddepth [7] -
+//   [8..10] dL_dcolor rgb               [11] -
+constexpr int ACC_STRIDE = 12;
+struct BlendGradPtrs {
+    float *acc;          // [P][ACC_STRIDE], zeroed by the API before the blend backward
+};
+int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, const uint32_t *point_list,
+                          const GeomPtrs &g, const float *bg, const float *final_T, const uint32_t *n_contrib,
+                          const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_opacity,
+                          int flags, const BlendGradPtrs &o, cudaStream_t s);
+
+int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3D, const int32_t *radii,
+                               const float *shs, const float *scales, const float *rotations,
+                               const float *cov3D_precomp, const float *view, const float *proj,
+                               const float *proj_raw, const float *campos, const GeomPtrs &g,
+                               const BlendGradPtrs &bgp, bool colors_are_precomp, float *dL_dmeans2D,
+                               float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D, float *dL_dcov3D,
+                               float *dL_dsh, float *dL_dscales, float *dL_drots, float *dL_dtau,
+                               float *dL_dtau_sum, cudaStream_t s);
+
+int launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t s);
+
+size_t dist2_workspace_bytes(int P);
+int launch_dist2(int P, const float *points, float *mean_dists, void *ws, size_t ws_bytes, cudaStream_t s);
+
+}  // namespace lvdgs

@@ -1,0 +1,459 @@
+// preprocess.cu -- K1 preprocess forward, K2 tile-count scan, K3 key emission, K5 tile ranges, K10 markVisible.
+//
+// Behaviour follows SURVEY.md Appendix A.1 / A.2 (the reference's `preprocessCUDA`, `duplicateWithKeys`,
+// `identifyTileRanges`, `checkFrustum`, reached from utils/slam_frontend.py:1493 and utils/slam_backend.py:184
+// through the missing gaussian_renderer shim).  Design is B200-first:
+//  * the [P,3] AoS inputs are staged through shared memory with fully coalesced loads, quaternions are
+//    one 128-bit load, all intermediate state is SoA with 8/16-byte vector stores;
+//  * every operation on the chain to an integer output is an explicit IEEE intrinsic (canonical arithmetic);
+//  * key emission is block-cooperative: a block owns 256 consecutive Gaussians, and its threads write the
+//    block's contiguous span of (key,value) instances with coalesced stores (binary search in shared memory)
+//    instead of one thread looping over its own tile rectangle.
+#include "common.cuh"
+
+namespace lvdgs {
+
+constexpr int PRE_THREADS = 256;
+
+__device__ __constant__ float SH_C0 = 0.28209479177387814f;
+__device__ __constant__ float SH_C1 = 0.4886025119029199f;
+__device__ __constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                          -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                          0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                          -0.5900435899266435f};
+
+// coalesced load of 256 x 3 floats into shared memory (block-strided), then each thread picks its triple
+__device__ __forceinline__ float3 load3_staged(const float *__restrict__ base, int P, float *smem) {
+    const int blk0 = blockIdx.x * PRE_THREADS;
+    const int n = min(PRE_THREADS, P - blk0) * 3;
+    const float *src = base + (size_t)blk0 * 3;
+    for (int k = threadIdx.x; k < n; k += PRE_THREADS) smem[k] = __ldg(src + k);
+    __syncthreads();
+    float3 v = make_float3(smem[3 * threadIdx.x], smem[3 * threadIdx.x + 1], smem[3 * threadIdx.x + 2]);
+    __syncthreads();
+    return v;
+}
+
+__device__ __forceinline__ void quat_to_R(float4 q, float R[9]) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    R[0] = __fmaf_rn(-2.f, __fmaf_rn(z, z, __fmul_rn(y, y)), 1.f);
+    R[1] = __fmul_rn(2.f, __fmaf_rn(x, y, -__fmul_rn(r, z)));
+    R[2] = __fmul_rn(2.f, __fmaf_rn(x, z, __fmul_rn(r, y)));
+    R[3] = __fmul_rn(2.f, __fmaf_rn(x, y, __fmul_rn(r, z)));
+    R[4] = __fmaf_rn(-2.f, __fmaf_rn(z, z, __fmul_rn(x, x)), 1.f);
+    R[5] = __fmul_rn(2.f, __fmaf_rn(y, z, -__fmul_rn(r, x)));
+    R[6] = __fmul_rn(2.f, __fmaf_rn(x, z, -__fmul_rn(r, y)));
+    R[7] = __fmul_rn(2.f, __fmaf_rn(y, z, __fmul_rn(r, x)));
+    R[8] = __fmaf_rn(-2.f, __fmaf_rn(y, y, __fmul_rn(x, x)), 1.f);
+}
+
+__device__ __forceinline__ void cov3d_from_scale_rot(float3 s, float mod, float4 q, float c[6]) {
+    float R[9];
+    quat_to_R(q, R);
+    const float s0 = __fmul_rn(mod, s.x), s1 = __fmul_rn(mod, s.y), s2 = __fmul_rn(mod, s.z);
+    float A[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        A[a * 3 + 0] = __fmul_rn(R[a * 3 + 0], s0);
+        A[a * 3 + 1] = __fmul_rn(R[a * 3 + 1], s1);
+        A[a * 3 + 2] = __fmul_rn(R[a * 3 + 2], s2);
+    }
+    c[0] = dot3c(A[0], A[0], A[1], A[1], A[2], A[2]);
+    c[1] = dot3c(A[0], A[3], A[1], A[4], A[2], A[5]);
+    c[2] = dot3c(A[0], A[6], A[1], A[7], A[2], A[8]);
+    c[3] = dot3c(A[3], A[3], A[4], A[4], A[5], A[5]);
+    c[4] = dot3c(A[3], A[6], A[4], A[7], A[5], A[8]);
+    c[5] = dot3c(A[6], A[6], A[7], A[7], A[8], A[8]);
+}
+
+// EWA projection (A.1 step 4): returns the dilated 2D covariance (a,b,c)
+__device__ __forceinline__ float3 ewa_cov2d(float tx, float ty, float tz, float fx, float fy, float tanfovx,
+                                            float tanfovy, const float c3[6], const float *view) {
+    const float limx = __fmul_rn(1.3f, tanfovx), limy = __fmul_rn(1.3f, tanfovy);
+    const float txtz = __fdiv_rn(tx, tz), tytz = __fdiv_rn(ty, tz);
+    const float txc = __fmul_rn(fminf(limx, fmaxf(-limx, txtz)), tz);
+    const float tyc = __fmul_rn(fminf(limy, fmaxf(-limy, tytz)), tz);
+    const float tz2 = __fmul_rn(tz, tz);
+    const float J00 = __fdiv_rn(fx, tz);
+    const float J02 = __fdiv_rn(-__fmul_rn(fx, txc), tz2);
+    const float J11 = __fdiv_rn(fy, tz);
+    const float J12 = __fdiv_rn(-__fmul_rn(fy, tyc), tz2);
+    float m0[3], m1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float R0 = view[4 * k + 0], R1 = view[4 * k + 1], R2 = view[4 * k + 2];
+        m0[k] = __fmaf_rn(J02, R2, __fmul_rn(J00, R0));
+        m1[k] = __fmaf_rn(J12, R2, __fmul_rn(J11, R1));
+    }
+    float u0[3], u1[3];
+    u0[0] = dot3c(c3[0], m0[0], c3[1], m0[1], c3[2], m0[2]);
+    u0[1] = dot3c(c3[1], m0[0], c3[3], m0[1], c3[4], m0[2]);
+    u0[2] = dot3c(c3[2], m0[0], c3[4], m0[1], c3[5], m0[2]);
+    u1[0] = dot3c(c3[0], m1[0], c3[1], m1[1], c3[2], m1[2]);
+    u1[1] = dot3c(c3[1], m1[0], c3[3], m1[1], c3[4], m1[2]);
+    u1[2] = dot3c(c3[2], m1[0], c3[4], m1[1], c3[5], m1[2]);
+    float3 cov;
+    cov.x = __fadd_rn(dot3c(m0[0], u0[0], m0[1], u0[1], m0[2], u0[2]), 0.3f);
+    cov.y = dot3c(m0[0], u1[0], m0[1], u1[1], m0[2], u1[2]);
+    cov.z = __fadd_rn(dot3c(m1[0], u1[0], m1[1], u1[1], m1[2], u1[2]), 0.3f);
+    return cov;
+}
+
+__device__ __forceinline__ float3 sh_to_rgb(int deg, int M, const float *__restrict__ sh, float3 p, const float *campos,
+                                            uint8_t &clamped) {
+    float3 res;
+    float r[3];
+    if (deg == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) r[c] = __fmaf_rn(SH_C0, __ldg(sh + c), 0.5f);
+    } else {
+        float3 d = make_float3(__fsub_rn(p.x, campos[0]), __fsub_rn(p.y, campos[1]), __fsub_rn(p.z, campos[2]));
+        const float inv = __fdiv_rn(1.f, __fsqrt_rn(dot3c(d.x, d.x, d.y, d.y, d.z, d.z)));
+        const float x = d.x * inv, y = d.y * inv, z = d.z * inv;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#define SHC(k) __ldg(sh + (k) * 3 + c)
+            float v = SH_C0 * SHC(0);
+            v = v - SH_C1 * y * SHC(1) + SH_C1 * z * SHC(2) - SH_C1 * x * SHC(3);
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                v = v + SH_C2[0] * xy * SHC(4) + SH_C2[1] * yz * SHC(5) + SH_C2[2] * (2.f * zz - xx - yy) * SHC(6) +
+                    SH_C2[3] * xz * SHC(7) + SH_C2[4] * (xx - yy) * SHC(8);
+                if (deg > 2) {
+                    v = v + SH_C3[0] * y * (3.f * xx - yy) * SHC(9) + SH_C3[1] * xy * z * SHC(10) +
+                        SH_C3[2] * y * (4.f * zz - xx - yy) * SHC(11) +
+                        SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * SHC(12) +
+                        SH_C3[4] * x * (4.f * zz - xx - yy) * SHC(13) + SH_C3[5] * z * (xx - yy) * SHC(14) +
+                        SH_C3[6] * x * (xx - 3.f * yy) * SHC(15);
+                }
+            }
+#undef SHC
+            r[c] = v + 0.5f;
+        }
+    }
+    clamped = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        if (r[c] < 0.f) { clamped |= (uint8_t)(1u << c); r[c] = 0.f; }
+    res = make_float3(r[0], r[1], r[2]);
+    return res;
+}
+
+struct PreArgs {
+    int P, D, M, W, H, gx, gy;
+    float tanfovx, tanfovy, fx, fy, mod;
+    const float *means3D, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp, *view, *proj, *shs, *campos;
+    int32_t *radii;
+    GeomPtrs g;
+};
+
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(const PreArgs a) {
+    __shared__ float stage[PRE_THREADS * 3];
+    __shared__ CameraConst cam;
+    if (threadIdx.x < 16) cam.view[threadIdx.x] = __ldg(a.view + threadIdx.x);
+    else if (threadIdx.x < 32) cam.proj[threadIdx.x - 16] = __ldg(a.proj + threadIdx.x - 16);
+    else if (threadIdx.x < 35) cam.campos[threadIdx.x - 32] = __ldg(a.campos + threadIdx.x - 32);
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const float3 p = load3_staged(a.means3D, a.P, stage);      // contains the __syncthreads that publishes `cam`
+    float3 sc = make_float3(0.f, 0.f, 0.f);
+    if (a.scales) sc = load3_staged(a.scales, a.P, stage);
+    float3 sh0 = make_float3(0.f, 0.f, 0.f);
+    const bool staged_color = a.colors_precomp != nullptr || a.M == 1;
+    if (staged_color) sh0 = load3_staged(a.colors_precomp ? a.colors_precomp : a.shs, a.P, stage);
+    if (i >= a.P) return;
+
+    int32_t radius = 0;
+    uint32_t touched = 0;
+    float depth = 0.f;
+    float2 pix = make_float2(0.f, 0.f);
+    float4 con_o = make_float4(0.f, 0.f, 0.f, 0.f);
+    float3 rgb = make_float3(0.f, 0.f, 0.f);
+    short4 rect = make_short4(0, 0, 0, 0);
+    uint8_t clamped = 0;
+
+    const float *V = cam.view, *Pj = cam.proj;
+    const float tx = __fadd_rn(dot3c(V[0], p.x, V[4], p.y, V[8], p.z), V[12]);
+    const float ty = __fadd_rn(dot3c(V[1], p.x, V[5], p.y, V[9], p.z), V[13]);
+    const float tz = __fadd_rn(dot3c(V[2], p.x, V[6], p.y, V[10], p.z), V[14]);
+    if (tz > 0.2f) {
+        const float hx = __fadd_rn(dot3c(Pj[0], p.x, Pj[4], p.y, Pj[8], p.z), Pj[12]);
+        const float hy = __fadd_rn(dot3c(Pj[1], p.x, Pj[5], p.y, Pj[9], p.z), Pj[13]);
+        const float hw = __fadd_rn(dot3c(Pj[3], p.x, Pj[7], p.y, Pj[11], p.z), Pj[15]);
+        const float pw = __fdiv_rn(1.f, __fadd_rn(hw, 0.0000001f));
+        const float px = __fmul_rn(hx, pw), py = __fmul_rn(hy, pw);
+        float c3[6];
+        if (a.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) c3[k] = __ldg(a.cov3D_precomp + (size_t)i * 6 + k);
+        } else {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(a.rotations) + i);
+            cov3d_from_scale_rot(sc, a.mod, q, c3);
+        }
+        const float3 cov = ewa_cov2d(tx, ty, tz, a.fx, a.fy, a.tanfovx, a.tanfovy, c3, V);
+        const float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
+        if (det != 0.f) {
+            const float det_inv = __fdiv_rn(1.f, det);
+            const float mid = __fmul_rn(0.5f, __fadd_rn(cov.x, cov.z));
+            const float sq = __fsqrt_rn(fmaxf(0.1f, __fmaf_rn(mid, mid, -det)));
+            const float lam = fmaxf(__fadd_rn(mid, sq), __fsub_rn(mid, sq));
+            const float rad = ceilf(__fmul_rn(3.f, __fsqrt_rn(lam)));
+            const float pix_x = __fmul_rn(__fmaf_rn(__fadd_rn(px, 1.f), (float)a.W, -1.f), 0.5f);
+            const float pix_y = __fmul_rn(__fmaf_rn(__fadd_rn(py, 1.f), (float)a.H, -1.f), 0.5f);
+            const int irad = (int)rad;
+            const float fr = (float)irad;
+            const int rminx = min(a.gx, max(0, (int)__fdiv_rn(__fsub_rn(pix_x, fr), 16.f)));
+            const int rminy = min(a.gy, max(0, (int)__fdiv_rn(__fsub_rn(pix_y, fr), 16.f)));
+            const int rmaxx = min(a.gx, max(0, (int)__fdiv_rn(__fadd_rn(__fadd_rn(pix_x, fr), 15.f), 16.f)));
+            const int rmaxy = min(a.gy, max(0, (int)__fdiv_rn(__fadd_rn(__fadd_rn(pix_y, fr), 15.f), 16.f)));
+            const int area = (rmaxx - rminx) * (rmaxy - rminy);
+            if (area != 0) {
+                if (a.colors_precomp) rgb = sh0;
+                else if (a.M == 1 && a.D == 0) {
+                    float r[3] = {__fmaf_rn(SH_C0, sh0.x, 0.5f), __fmaf_rn(SH_C0, sh0.y, 0.5f), __fmaf_rn(SH_C0, sh0.z, 0.5f)};
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (r[c] < 0.f) { clamped |= (uint8_t)(1u << c); r[c] = 0.f; }
+                    rgb = make_float3(r[0], r[1], r[2]);
+                } else {
+                    rgb = sh_to_rgb(a.D, a.M, a.shs + (size_t)i * a.M * 3, p, cam.campos, clamped);
+                }
+                depth = tz;
+                radius = irad;
+                pix = make_float2(pix_x, pix_y);
+                con_o = make_float4(__fmul_rn(cov.z, det_inv), __fmul_rn(-cov.y, det_inv), __fmul_rn(cov.x, det_inv),
+                                    __ldg(a.opacities + i));
+                rect = make_short4((short)rminx, (short)rminy, (short)rmaxx, (short)rmaxy);
+                touched = (uint32_t)area;
+            }
+        }
+    }
+    a.radii[i] = radius;
+    a.g.depths[i] = depth;
+    a.g.means2D[i] = pix;
+    a.g.conic_opacity[i] = con_o;
+    a.g.rgbd[i] = make_float4(rgb.x, rgb.y, rgb.z, depth);
+    a.g.rect[i] = rect;
+    a.g.tiles_touched[i] = touched;
+    a.g.clamped[i] = clamped;
+}
+
+int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D, const float *colors_precomp,
+                              const float *opacities, const float *scales, const float *rotations,
+                              const float *cov3D_precomp, const float *view, const float *proj, const float *shs,
+                              const float *campos, int32_t *radii, const GeomPtrs &g, cudaStream_t s) {
+    PreArgs a;
+    a.P = p.P; a.D = p.sh_degree; a.M = p.sh_coeffs; a.W = p.width; a.H = p.height;
+    a.gx = (p.width + TILE - 1) / TILE; a.gy = (p.height + TILE - 1) / TILE;
+    a.tanfovx = p.tan_fovx; a.tanfovy = p.tan_fovy;
+    a.fx = (float)p.width / (2.f * p.tan_fovx); a.fy = (float)p.height / (2.f * p.tan_fovy);
+    a.mod = p.scale_modifier;
+    a.means3D = means3D; a.colors_precomp = colors_precomp; a.opacities = opacities; a.scales = scales;
+    a.rotations = rotations; a.cov3D_precomp = cov3D_precomp; a.view = view; a.proj = proj; a.shs = shs;
+    a.campos = campos; a.radii = radii; a.g = g;
+    preprocess_forward_kernel<<<ceil_div(p.P, PRE_THREADS), PRE_THREADS, 0, s>>>(a);
+    LVDGS_LAUNCHED(s, "preprocess_forward");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2: inclusive scan of tiles_touched.  Three small launches (reduce / scan block sums / rescan+add); the data
+// is 4 B per Gaussian, so this is launch-latency, not bandwidth.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += n;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, total via out param
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_sums, uint32_t &total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t incl = warp_incl_scan(v);
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t ws = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+        ws = warp_incl_scan(ws);
+        warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    const uint32_t base = w ? warp_sums[w - 1] : 0;
+    total = warp_sums[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(int P, const uint32_t *__restrict__ in,
+                                                                   uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t ws[32];
+    const int base = blockIdx.x * SCAN_TILE;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int i = base + k * SCAN_THREADS + threadIdx.x;
+        if (i < P) v += in[i];
+    }
+    uint32_t total;
+    block_excl_scan(v, ws, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(int nb, uint32_t *block_sums) {
+    __shared__ uint32_t ws[32];
+    uint32_t carry = 0;
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < nb ? block_sums[i] : 0;
+        uint32_t total;
+        const uint32_t ex = block_excl_scan(v, ws, total);
+        if (i < nb) block_sums[i] = carry + ex;     // exclusive prefix of the block sums
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int P, const uint32_t *__restrict__ in,
+                                                                  const uint32_t *__restrict__ block_sums,
+                                                                  uint32_t *__restrict__ out) {
+    __shared__ uint32_t ws[32];
+    // thread owns SCAN_ITEMS consecutive elements (blocked arrangement)
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < P) ? in[base + k] : 0;
+        sum += v[k];
+    }
+    uint32_t total;
+    uint32_t run = block_excl_scan(sum, ws, total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        run += v[k];
+        if (base + k < P) out[base + k] = run;
+    }
+}
+
+int launch_scan_tiles(int P, const uint32_t *tiles_touched, uint32_t *point_offsets, uint32_t *block_sums,
+                      cudaStream_t s) {
+    const int nb = ceil_div(P, SCAN_TILE);
+    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(P, tiles_touched, block_sums);
+    LVDGS_LAUNCHED(s, "scan_reduce");
+    scan_block_sums_kernel<<<1, 1024, 0, s>>>(nb, block_sums);
+    LVDGS_LAUNCHED(s, "scan_block_sums");
+    scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>(P, tiles_touched, block_sums, point_offsets);
+    LVDGS_LAUNCHED(s, "scan_apply");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: key emission.  Block b owns Gaussians [256b, 256b+256); its instances are the contiguous span
+// [offsets[256b-1], offsets[256b+255]).  Thread t writes instances t, t+256, ... of that span, locating the
+// owning Gaussian by binary search over the block's offsets in shared memory.  Emission order inside a
+// Gaussian is y-major, x-minor -- the order the reference's per-thread loop produces -- so ties in the
+// stable sort resolve identically.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int EMIT_THREADS = 256;
+
+__global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, const uint32_t *__restrict__ offsets,
+                                                                 const short4 *__restrict__ rects,
+                                                                 const float *__restrict__ depths,
+                                                                 uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    __shared__ uint32_t s_end[EMIT_THREADS];      // inclusive offsets of this block's Gaussians
+    __shared__ short4 s_rect[EMIT_THREADS];
+    __shared__ uint32_t s_depth[EMIT_THREADS];
+    const int g0 = blockIdx.x * EMIT_THREADS;
+    const int i = g0 + threadIdx.x;
+    const uint32_t span_begin = g0 ? offsets[g0 - 1] : 0;
+    if (i < P) {
+        s_end[threadIdx.x] = offsets[i];
+        s_rect[threadIdx.x] = rects[i];
+        s_depth[threadIdx.x] = __float_as_uint(depths[i]);
+    } else {
+        s_end[threadIdx.x] = 0xffffffffu;
+    }
+    __syncthreads();
+    const int last = min(EMIT_THREADS, P - g0) - 1;
+    const uint32_t span_end = s_end[last];
+    for (uint32_t r = span_begin + threadIdx.x; r < span_end; r += EMIT_THREADS) {
+        // smallest j with s_end[j] > r
+        int lo = 0, hi = last;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_end[mid] > r) hi = mid; else lo = mid + 1;
+        }
+        const uint32_t begin = lo ? s_end[lo - 1] : span_begin;
+        const short4 rc = s_rect[lo];
+        const uint32_t local = r - begin;
+        const uint32_t w = (uint32_t)(rc.z - rc.x);
+        const uint32_t yy = local / w, xx = local - yy * w;
+        const uint32_t tile = (uint32_t)(rc.y + (int)yy) * (uint32_t)gx + (uint32_t)(rc.x + (int)xx);
+        keys[r] = ((uint64_t)tile << 32) | s_depth[lo];
+        vals[r] = (uint32_t)(g0 + lo);
+    }
+}
+
+int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, const int32_t *radii, uint64_t *keys, uint32_t *vals,
+                     cudaStream_t s) {
+    (void)radii; (void)H;
+    const int gx = (W + TILE - 1) / TILE;
+    emit_keys_kernel<<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, g.point_offsets, g.rect, g.depths, keys, vals);
+    LVDGS_LAUNCHED(s, "emit_keys");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: tile ranges from the sorted keys.  `ranges` must be zeroed by the caller (untouched tiles stay (0,0)).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t R, const uint64_t *__restrict__ keys,
+                                                          uint2 *__restrict__ ranges) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= R) return;
+    const uint32_t t = (uint32_t)(keys[r] >> 32);
+    if (r == 0) ranges[t].x = 0;
+    else {
+        const uint32_t tp = (uint32_t)(keys[r - 1] >> 32);
+        if (t != tp) { ranges[tp].y = (uint32_t)r; ranges[t].x = (uint32_t)r; }
+    }
+    if (r == R - 1) ranges[t].y = (uint32_t)R;
+}
+
+int launch_tile_ranges(int64_t R, int num_tiles, const uint64_t *keys_sorted, uint2 *ranges, cudaStream_t s) {
+    LVDGS_CHECK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, s));
+    if (R > 0) {
+        tile_ranges_kernel<<<ceil_div(R, 256), 256, 0, s>>>(R, keys_sorted, ranges);
+        LVDGS_LAUNCHED(s, "tile_ranges");
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K10: markVisible
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PRE_THREADS) mark_visible_kernel(int P, const float *__restrict__ means3D,
+                                                                   const float *__restrict__ view,
+                                                                   uint8_t *__restrict__ present) {
+    __shared__ float stage[PRE_THREADS * 3];
+    const float3 p = load3_staged(means3D, P, stage);
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    if (i >= P) return;
+    const float tz = __fadd_rn(dot3c(__ldg(view + 2), p.x, __ldg(view + 6), p.y, __ldg(view + 10), p.z), __ldg(view + 14));
+    present[i] = tz > 0.2f ? 1 : 0;
+}
+
+int launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t s) {
+    if (P <= 0) return 0;
+    mark_visible_kernel<<<ceil_div(P, PRE_THREADS), PRE_THREADS, 0, s>>>(P, means3D, view, present);
+    LVDGS_LAUNCHED(s, "mark_visible");
+    return 0;
+}
+
+}  // namespace lvdgs

@@ -1,0 +1,209 @@
+"""GPU parity: the sm_100a CUDA path, called through the plugin surface / C ABI, against the CPU oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star): radii, tile ranges, sorted keys, n_touched bit-exact;
+image / depth / opacity within 1e-5 abs (depth: 1e-5 relative to max(1,|depth|), it is an un-normalised sum of
+metres); gradients within 1e-3 relative.  Pixels (and the Gaussians they touch) whose discrete blending decisions
+are within 1e-5 relative of a threshold in the oracle are set aside: there the decision legitimately depends on the
+last ulp of exp() (see oracle margin)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from lvdgs import synth
+from gpu_harness import run_cuda, run_oracle, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "vga50k": dict(cam="vga", N=50_000, sh=0, bg=(0.0, 0.0, 0.0)),          # BASELINE configs[0]
+    "kitti30k_bg": dict(cam="kitti", N=30_000, sh=0, bg=(0.3, 0.1, 0.7)),
+    "mast3r_sh3": dict(cam="mast3r_kitti", N=8_000, sh=3, bg=(0.0, 0.0, 0.0)),
+    "ragged_33x17": dict(cam=None, N=700, sh=1, bg=(0.1, 0.2, 0.3)),
+}
+
+
+def make_case(name):
+    c = CASES[name]
+    if c["cam"] is None:
+        cam = synth.Cam(33, 17, 30.0, 31.0, 15.2, 9.1, np.eye(3), np.zeros(3))
+    else:
+        cam = synth.make_camera(c["cam"], k=2 if name == "kitti30k_bg" else None)
+    sc = synth.make_scene(c["N"], cam, seed=11, sh_degree=c["sh"])
+    if name == "kitti30k_bg":   # scene was generated in the identity frame; keep it in front of the moved camera
+        sc["means3D"][:, 2] += 2.0
+    return cam, sc, np.array(c["bg"], np.float32)
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request):
+    cam, sc, bg = make_case(request.param)
+    H, W = cam.image_height, cam.image_width
+    rng = np.random.default_rng(5)
+    gc = (rng.normal(0, 1, (3, H, W))).astype(np.float32)
+    gd = (rng.normal(0, 1, (1, H, W)) * 0.1).astype(np.float32)
+    out, internals, g = run_cuda(sc, cam, bg, grads=(gc, gd, None))
+    fwd, go = run_oracle(sc, cam, bg, grads=(gc, gd, None))
+    return dict(name=request.param, cam=cam, sc=sc, out=out, int=internals, g=g, fwd=fwd, go=go)
+
+
+def test_preprocess_bit_exact(case):
+    i, f = case["int"], case["fwd"]
+    np.testing.assert_array_equal(case["out"]["radii"], f["radii"])
+    np.testing.assert_array_equal(i["rect"], f["rect"])
+    np.testing.assert_array_equal(i["tiles_touched"], f["tiles_touched"])
+    np.testing.assert_array_equal(i["point_offsets"], np.cumsum(f["tiles_touched"], dtype=np.uint64).astype(np.uint32))
+    np.testing.assert_array_equal(i["depths"].view(np.uint32), f["depths"].view(np.uint32))
+    np.testing.assert_array_equal(i["means2D"].view(np.uint32), f["means2D"].view(np.uint32))
+    np.testing.assert_array_equal(i["conic_opacity"].view(np.uint32), f["conic_opacity"].view(np.uint32))
+    np.testing.assert_array_equal(i["clamped"], f["clamped"])
+    np.testing.assert_allclose(i["rgbd"][:, :3], f["rgb"], rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(i["rgbd"][:, 3].view(np.uint32), f["depths"].view(np.uint32))
+
+
+def test_binning_bit_exact(case):
+    i, f = case["int"], case["fwd"]
+    assert i["R"] == f["R"] and f["R"] > 0
+    np.testing.assert_array_equal(i["keys_sorted"], f["keys_sorted"])
+    np.testing.assert_array_equal(i["point_list"], f["point_list"])
+    np.testing.assert_array_equal(i["ranges"], f["ranges"])
+
+
+def test_blend_forward(case):
+    o, i, f = case["out"], case["int"], case["fwd"]
+    ok = f["margin"] > 1e-5
+    frac_bad = 1.0 - ok.mean()
+    assert frac_bad < 2e-3, f"too many knife-edge pixels: {frac_bad}"
+    np.testing.assert_array_equal(i["n_contrib"][ok], f["n_contrib"][ok])
+    assert np.abs(o["color"][:, ok] - f["color"][:, ok]).max() < 1e-5
+    assert np.abs(o["opacity"][0][ok] - f["opacity"][0][ok]).max() < 1e-5
+    d_err = np.abs(o["depth"][0][ok] - f["depth"][0][ok]) / np.maximum(1.0, np.abs(f["depth"][0][ok]))
+    assert d_err.max() < 1e-5
+    assert np.abs(i["final_T"][ok] - f["final_T"][ok]).max() < 1e-5
+    # n_touched: exact for every Gaussian that is not in the list of a tile holding a knife-edge pixel
+    W, H = f["W"], f["H"]
+    gx = (W + 15) // 16
+    bad_tiles = set()
+    ys, xs = np.nonzero(~ok)
+    for y, x in zip(ys, xs):
+        bad_tiles.add((y // 16) * gx + x // 16)
+    tainted = np.zeros(f["P"], bool)
+    for t in bad_tiles:
+        r0, r1 = f["ranges"][t]
+        tainted[f["point_list"][r0:r1]] = True
+    np.testing.assert_array_equal(o["n_touched"][~tainted], f["n_touched"][~tainted])
+    assert tainted.mean() < 0.5
+    # on tainted Gaussians the count may move by at most the number of knife-edge pixels
+    assert np.abs(o["n_touched"].astype(np.int64) - f["n_touched"]).max() <= max(1, int((~ok).sum()))
+
+
+def test_backward(case):
+    g, go, f = case["g"], case["go"], case["fwd"]
+    frac_bad = 1.0 - (f["margin"] > 1e-5).mean()
+    tol = 1e-3 + 20 * frac_bad      # knife-edge pixels perturb the sums slightly; still ~1e-3
+    assert rel_err(g["means2D"][:, :2], go["dL_dmean2D"]) < tol
+    assert np.all(g["means2D"][:, 2] == 0)
+    assert rel_err(g["means3D"], go["dL_dmeans3D"]) < tol
+    assert rel_err(g["opacities"].reshape(-1), go["dL_dopacity"]) < tol
+    assert rel_err(g["scales"], go["dL_dscales"]) < tol
+    assert rel_err(g["rotations"], go["dL_drots"]) < tol
+    assert rel_err(g["shs"], go["dL_dsh"]) < tol
+    assert rel_err(g["rho"], go["grad_rho"]) < tol
+    assert rel_err(g["theta"], go["grad_theta"]) < tol
+
+
+def test_precomputed_color_and_cov(case):
+    if case["name"] != "ragged_33x17":
+        pytest.skip("one small case is enough")
+    cam, sc, f = case["cam"], dict(case["sc"]), case["fwd"]
+    sc["colors_precomp"] = np.random.default_rng(2).uniform(0, 1, (f["P"], 3)).astype(np.float32)
+    bg = np.array([0.1, 0.2, 0.3], np.float32)
+    H, W = cam.image_height, cam.image_width
+    rng = np.random.default_rng(6)
+    gc = rng.normal(0, 1, (3, H, W)).astype(np.float32)
+    gd = rng.normal(0, 1, (1, H, W)).astype(np.float32)
+    cov = f["cov3D"].copy()
+    # Gaussians the oracle culled have cov3D = 0 there; give them a valid covariance anyway
+    cov[f["radii"] == 0] = np.array([1e-2, 0, 0, 1e-2, 0, 1e-2], np.float32)
+    out, internals, g = run_cuda(sc, cam, bg, grads=(gc, gd, None), use_precomp_color=True, use_precomp_cov=cov)
+    fwd, go = run_oracle(sc, cam, bg, grads=(gc, gd, None), use_precomp_color=True, use_precomp_cov=cov)
+    ok = fwd["margin"] > 1e-5
+    np.testing.assert_array_equal(out["radii"], fwd["radii"])
+    assert np.abs(out["color"][:, ok] - fwd["color"][:, ok]).max() < 1e-5
+    assert rel_err(g["colors_precomp"], go["dL_dcolor"]) < 2e-3
+    assert rel_err(g["cov3D"], go["dL_dcov3D"]) < 2e-3
+    assert rel_err(g["means3D"], go["dL_dmeans3D"]) < 2e-3
+    assert g["scales"] is None and g["shs"] is None
+
+
+def test_flags_true_derivatives():
+    """LVDGS_FLAG_EXACT_PP | LVDGS_FLAG_OPACITY_GRAD reproduce the oracle's true-derivative mode (tracking loss sends
+    gradient into the opacity image, utils/slam_utils.py:60)."""
+    import diff_gaussian_rasterization as dgr
+    cam, sc, bg = make_case("ragged_33x17")
+    H, W = cam.image_height, cam.image_width
+    rng = np.random.default_rng(9)
+    gc = rng.normal(0, 1, (3, H, W)).astype(np.float32)
+    go_img = rng.normal(0, 1, (1, H, W)).astype(np.float32)
+    old = dgr.FLAGS
+    try:
+        dgr.FLAGS = 3
+        out, _, g = run_cuda(sc, cam, bg, grads=(gc, None, go_img))
+    finally:
+        dgr.FLAGS = old
+    fwd, go = run_oracle(sc, cam, bg, grads=(gc, None, go_img), flags=3)
+    assert rel_err(g["theta"], go["grad_theta"]) < 2e-3
+    assert rel_err(g["rho"], go["grad_rho"]) < 2e-3
+    assert rel_err(g["opacities"].reshape(-1), go["dL_dopacity"]) < 2e-3
+    _, go0 = run_oracle(sc, cam, bg, grads=(gc, None, go_img), flags=0)
+    assert rel_err(go0["grad_theta"], go["grad_theta"]) > 1e-3    # the flag is not a no-op on this case
+
+
+def test_empty_and_all_culled():
+    import diff_gaussian_rasterization as dgr
+    from gpu_harness import settings_for
+    cam = synth.make_camera("mast3r_kitti")
+    rs = settings_for(cam, (0.2, 0.4, 0.6), 0)
+    rast = dgr.GaussianRasterizer(rs)
+    dev = "cuda"
+    for P in (0, 5):
+        means = torch.zeros(P, 3, device=dev)
+        means[:, 2] = -1.0                      # behind the camera: everything culled, R = 0
+        means.requires_grad_()
+        m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+        color, radii, depth, opacity, n_touched = rast(
+            means3D=means, means2D=m2d, opacities=torch.full((P, 1), 0.5, device=dev), shs=torch.zeros(P, 1, 3, device=dev),
+            scales=torch.full((P, 3), 0.1, device=dev), rotations=torch.tensor([[1.0, 0, 0, 0]], device=dev).repeat(P, 1),
+            theta=torch.zeros(3, device=dev, requires_grad=True), rho=torch.zeros(3, device=dev, requires_grad=True))
+        assert color.shape == (3, cam.image_height, cam.image_width)
+        assert torch.allclose(color[0], torch.full_like(color[0], 0.2)) and torch.allclose(color[2], torch.full_like(color[2], 0.6))
+        assert float(depth.abs().max()) == 0 and float(opacity.abs().max()) == 0
+        assert radii.shape == (P,) and int(radii.sum()) == 0 and int(n_touched.sum()) == 0
+        color.sum().backward()
+        if P:
+            assert float(means.grad.abs().max()) == 0
+
+
+def test_argument_errors():
+    import diff_gaussian_rasterization as dgr
+    from gpu_harness import settings_for
+    cam = synth.make_camera("mast3r_kitti")
+    rast = dgr.GaussianRasterizer(settings_for(cam, (0, 0, 0), 0))
+    z = torch.zeros(4, 3, device="cuda")
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rast(means3D=z, means2D=z, opacities=z[:, :1], scales=z, rotations=torch.zeros(4, 4, device="cuda"))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        rast(means3D=z, means2D=z, opacities=z[:, :1], shs=torch.zeros(4, 1, 3, device="cuda"))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rast(means3D=z.cpu(), means2D=z.cpu(), opacities=z[:, :1].cpu(), shs=torch.zeros(4, 1, 3), scales=z.cpu(),
+             rotations=torch.zeros(4, 4))
+
+
+def test_mark_visible():
+    import diff_gaussian_rasterization as dgr
+    from gpu_harness import settings_for
+    cam = synth.make_camera("kitti", k=3)
+    sc = synth.make_scene(5000, cam, seed=4)
+    rast = dgr.GaussianRasterizer(settings_for(cam, (0, 0, 0), 0))
+    vis = rast.markVisible(torch.tensor(sc["means3D"], device="cuda")).cpu().numpy()
+    np.testing.assert_array_equal(vis, oracle.mark_visible(sc["means3D"], cam.world_view_transform))
+    assert 0 < vis.sum() < len(vis)
