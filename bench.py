@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd render throughput of the B200 rasterizer on BASELINE.json's headline configuration.
+
+Workload (`config.workload` = "kitti_window8_500k"): one STEP = forward + backward of the 8 keyframe views of a
+mapping window (1241x376 each, SURVEY.md section 8d cameras k=0..7) against a replicated map of 500 000 synthetic
+Gaussians, parameter gradients summed over the views (the mapping loss is a sum, utils/slam_backend.py:266,300).
+metric = fwd+bwd render Mpix/s = 8*H*W / step time.  At N GPUs the 8 views are sharded over the ranks
+(8/N each) and the [P,14] parameter-gradient block is SUM-allreduced over NCCL at the end of the step
+(strong scaling: the window is fixed).
+
+  value  : device-resident inputs, lean C-ABI engine (lvdgs.engine.RasterEngine), CUDA-event timed
+  e2e    : the reference-facing plugin surface (diff_gaussian_rasterization.GaussianRasterizer + torch loss),
+           per view H2D of the target image/depth and camera from pinned host memory, D2H of loss + pose gradient
+  roofline / cpu_baseline : see DESIGN.md section 7
+  --impl reference : the oracle (CPU restatement of the reference's algorithm; the reference's CUDA sources are
+           absent) timed on the host cores for the same metric, one view per step
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "lvd_gs-slam_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+METRIC = "fwd+bwd render Mpix/s at 1241x376, 500k Gaussians"
+WORKLOADS = {"kitti_window8_500k": dict(N=500_000, cam="kitti", views=8),
+             "kitti_window8_1m": dict(N=1_000_000, cam="kitti", views=8)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kitti_window8_500k", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_view(sc, cam, gc, gd):
+    """One view of the workload through the CPU oracle (forward + backward).  Returns seconds."""
+    import oracle
+    t0 = time.perf_counter()
+    fwd = oracle.rasterize_forward(sc["means3D"], sc["opacities"], sc["scales"], sc["rotations"], sc["shs"],
+                                   viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
+                                   campos=cam.camera_center, bg=np.zeros(3, np.float32), W=cam.image_width,
+                                   H=cam.image_height, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, want_margin=False)
+    oracle.rasterize_backward(fwd, gc, gd, projmatrix_raw=cam.projection_matrix)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, wl):
+    """Reference arm: the reference's algorithm on the host cores (oracle port; the reference's own CUDA build is
+    impossible here -- its sources are absent), same metric/config, one view of the window per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from lvdgs import synth
+    cams = [synth.make_camera(wl["cam"], k) for k in range(wl["views"])]
+    sc = synth.make_scene(wl["N"], cams[0], seed=0)
+    gc, gd = synth.make_upstream_grads(cams[0])
+    H, W = cams[0].image_height, cams[0].image_width
+    for i in range(args.warmup):
+        cpu_oracle_view(sc, cams[i % len(cams)], gc, gd)
+    t = 0.0
+    for i in range(args.steps):
+        t += cpu_oracle_view(sc, cams[i % len(cams)], gc, gd)
+    ms = 1e3 * t / max(args.steps, 1)
+    val = H * W / (ms * 1e-3) / 1e6
+    cores = oracle.num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "gaussians": wl["N"], "image": [W, H],
+                       "sample": "one keyframe view (fwd+bwd) of the 8-view window per step"},
+            "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                             "sample": "one full 1241x376 view, fwd+bwd, per step (OpenMP over tiles / Gaussians)"},
+            "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    from lvdgs import synth, _native
+    from lvdgs.engine import RasterEngine, ViewCamera
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert wl["views"] % world == 0, "the 8-view window must divide over the ranks"
+    L = _native.lib()
+
+    cams = [synth.make_camera(wl["cam"], k) for k in range(wl["views"])]
+    my_views = list(range(rank, wl["views"], world))          # keyframe k -> rank k mod world
+    sc = synth.make_scene(wl["N"], cams[0], seed=0)            # identical replicated map on every rank
+    H, W, P = cams[0].image_height, cams[0].image_width, wl["N"]
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device=dev).contiguous()
+    means3D, opac, scales, rots, shs = t(sc["means3D"]), t(sc["opacities"]), t(sc["scales"]), t(sc["rotations"]), t(sc["shs"])
+    gc_np, gd_np = synth.make_upstream_grads(cams[0])
+    gc, gd = t(gc_np), t(gd_np)
+    vcs = {k: ViewCamera(cams[k], dev) for k in my_views}
+    eng = RasterEngine(P, W, H, sh_coeffs=1, sh_degree=0, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: device-resident, C-ABI engine ----------------
+    def step_resident():
+        eng.zero_grads()
+        for k in my_views:
+            eng.forward(vcs[k], means3D, opac, scales, rots, shs)
+            eng.backward(vcs[k], means3D, opac, scales, rots, shs, gc, gd, accumulate=True)
+        if world > 1:
+            dist.all_reduce(eng.grad_flat)                      # SUM over keyframe shards (NCCL / NVLink)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.lvdgs_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    launches = int(L.lvdgs_launch_count())
+    ms = e0.elapsed_time(e1) / args.steps
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = wl["views"] * H * W / (ms * 1e-3) / 1e6
+
+    # ---------------- e2e: plugin surface, host buffers ----------------
+    import diff_gaussian_rasterization as dgr
+    params = [x.clone().requires_grad_() for x in (means3D, opac, scales, rots, shs)]
+    rng = np.random.default_rng(2)
+    host = {}
+    for k in my_views:
+        host[k] = dict(img=torch.from_numpy(rng.uniform(0, 1, (3, H, W)).astype(np.float32)).pin_memory(),
+                       dep=torch.from_numpy(rng.uniform(1, 50, (1, H, W)).astype(np.float32)).pin_memory(),
+                       cam=torch.from_numpy(np.concatenate([cams[k].world_view_transform.ravel(), cams[k].full_proj_transform.ravel(),
+                                                            cams[k].projection_matrix.ravel(), cams[k].camera_center.ravel(),
+                                                            np.zeros(1, np.float32)]).astype(np.float32)).pin_memory())
+    res_host = torch.zeros(len(my_views), 8).pin_memory()
+    bgt = torch.zeros(3, device=dev)
+    h2d = sum(v["img"].numel() + v["dep"].numel() + v["cam"].numel() for v in host.values()) * 4
+    d2h = res_host.numel() * 4
+
+    def step_e2e():
+        for p_ in params:
+            p_.grad = None
+        for j, k in enumerate(my_views):
+            hb = host[k]
+            img = hb["img"].to(dev, non_blocking=True); dep = hb["dep"].to(dev, non_blocking=True)
+            cm = hb["cam"].to(dev, non_blocking=True)
+            rs = dgr.GaussianRasterizationSettings(
+                image_height=H, image_width=W, tanfovx=cams[k].tanfovx, tanfovy=cams[k].tanfovy, bg=bgt, scale_modifier=1.0,
+                viewmatrix=cm[0:16].view(4, 4), projmatrix=cm[16:32].view(4, 4), projmatrix_raw=cm[32:48].view(4, 4),
+                sh_degree=0, campos=cm[48:51], prefiltered=False, debug=False)
+            theta = torch.zeros(3, device=dev, requires_grad=True); rho = torch.zeros(3, device=dev, requires_grad=True)
+            m2d = torch.zeros_like(params[0], requires_grad=True)
+            color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(rs)(
+                means3D=params[0], means2D=m2d, opacities=params[1], shs=params[4], scales=params[2], rotations=params[3],
+                theta=theta, rho=rho)
+            # mapping-style loss (utils/slam_utils.py:107-121): 0.9 L1 rgb + 0.1 L1 depth
+            loss = 0.9 * (color - img).abs().mean() + 0.1 * (depth - dep).abs().mean()
+            loss.backward()
+            res_host[j, 0:1].copy_(loss.detach().reshape(1), non_blocking=True)
+            res_host[j, 1:4].copy_(rho.grad, non_blocking=True)
+            res_host[j, 4:7].copy_(theta.grad, non_blocking=True)
+        if world > 1:
+            flat = torch.cat([p_.grad.reshape(-1) for p_ in params])
+            dist.all_reduce(flat)
+        torch.cuda.current_stream().synchronize()               # the step's result is on the host
+
+    for _ in range(max(3, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+    tms = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(tms.item())
+    e2e_val = wl["views"] * H * W / (e2e_ms * 1e-3) / 1e6
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- per-kernel device times + roofline (rank 0, outside the timed regions) ----------------
+    roof, kernels = None, []
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        sm_max = peaks.get("sm_max_mhz", 1965.0)
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        fp32_peak = n_sm * 128 * 2 * sm_max * 1e6 / 1e12        # TFLOP/s at max clock; no measured FP32 peak exists
+        stream = torch.cuda.current_stream().cuda_stream
+        agg, pairs, Rs, vis = {}, 0, 0, 0
+        reps = 3
+        for _ in range(reps):
+            for k in my_views:
+                _native.profile_begin(stream)
+                eng.forward(vcs[k], means3D, opac, scales, rots, shs)
+                eng.backward(vcs[k], means3D, opac, scales, rots, shs, gc, gd, accumulate=True)
+                for name, t_ms in _native.profile_end(stream):
+                    agg.setdefault(name, []).append(t_ms)
+                pairs += eng.pair_count(); Rs += eng.R; vis += int((eng.radii > 0).sum().item())
+        nview = reps * len(my_views)
+        pairs /= nview; Rs /= nview; vis /= nview
+        passes = 6
+        alg = {  # algorithmic work per view (SURVEY.md section 8d / DESIGN.md section 7)
+            "preprocess_forward": ("hbm", 20.0 * (P - vis) + 131.0 * vis),
+            "emit_keys": ("hbm", 12.0 * Rs + 20.0 * P),
+            "sort_histogram": ("hbm", 8.0 * Rs),
+            "sort_onesweep": ("hbm", passes * 24.0 * Rs),
+            "tile_ranges": ("hbm", 8.0 * Rs),
+            "blend_forward": ("fp32", 28.0 * pairs),
+            "blend_backward": ("fp32", 70.0 * pairs),
+            "preprocess_backward": ("hbm", 190.0 * vis + 52.0 * (P - vis)),
+        }
+        for name, v in agg.items():
+            per_view_ms = sum(v) / nview
+            ent = {"kernel": name, "launches_per_view": len(v) / nview, "ms_per_view": per_view_ms}
+            if name in alg and per_view_ms > 0:
+                bound, work = alg[name]
+                if bound == "hbm":
+                    ach = work / (per_view_ms * 1e-3) / 1e9
+                    ent.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak)
+                else:
+                    ach = work / (per_view_ms * 1e-3) / 1e12
+                    ent.update(bound="fp32", achieved=ach, peak=fp32_peak, unit="TFLOP/s", frac=ach / fp32_peak)
+            kernels.append(ent)
+        kernels.sort(key=lambda e: -e["ms_per_view"])
+        dom = next((e for e in kernels if "bound" in e), None)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom["kernel"])
+        except Exception:
+            pass
+        if dom:
+            roof = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                    "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic,
+                    "ms_per_launch": dom["ms_per_view"] / dom["launches_per_view"],
+                    "peak_source": hbm_src if dom["bound"] == "hbm" else
+                    f"computed {n_sm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (no measured FP32 peak in MEASURED_PEAKS.json; "
+                    "tensor cores unused: the blend is FP32 FMA/MUFU issue-bound, not a dense contraction)",
+                    "algorithmic": {"pairs_per_view": pairs, "instances_per_view": Rs, "visible_per_view": vis}}
+
+    # ---------------- cpu baseline (rank 0, N=1): oracle port on the host cores, one view ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        oracle.build()
+        cpu_oracle_view(sc, cams[0], gc_np, gd_np)               # warm (page-in, OpenMP pool)
+        ts = [cpu_oracle_view(sc, cams[k], gc_np, gd_np) for k in (0, 3, 6)]
+        tv = float(np.median(ts))
+        cpu = {"value": H * W / tv / 1e6, "unit": "Mpix/s", "cores": oracle.num_threads(), "kind": "port",
+               "sample": "3 of the 8 views (k=0,3,6), full 1241x376 fwd+bwd each, median; C oracle with OpenMP",
+               "seconds_per_view": tv}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "gaussians": P, "image": [W, H], "views_per_step": wl["views"],
+                           "views_per_rank": len(my_views), "sh_degree": 0,
+                           "l2": "inputs larger than L2: each view streams its own sorted instance list, and the 8 views "
+                                 "of a step rewrite >300 MB of binning state between revisits",
+                           "parallelism": f"keyframes sharded over {world} rank(s), NCCL SUM-allreduce of [P,14] grads" if world > 1 else "1 GPU"},
+                "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "path": "diff_gaussian_rasterization.GaussianRasterizer (autograd) + torch L1 loss"},
+                "gpu_launches": launches, "mapping_iters_per_s": 1e3 / ms, "clocks": clocks, "roofline": roof,
+                "kernels": kernels, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -23,13 +23,23 @@ void set_error(const char *fmt, ...) {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- optional per-launch profiler: one CUDA event after every launch, on the launching stream ----
-struct ProfEntry { const char *name; cudaEvent_t ev; };
+struct ProfEntry { const char *name; cudaEvent_t ev; cudaEvent_t pre; };
 static std::vector<ProfEntry> g_prof;
 static bool g_prof_on = false;
 
+static cudaEvent_t g_prof_pending_pre = nullptr;
+
+int profile_pre(cudaStream_t s) {
+    if (!g_prof_on) return 0;
+    if (!g_prof_pending_pre) LVDGS_CHECK(cudaEventCreate(&g_prof_pending_pre));
+    LVDGS_CHECK(cudaEventRecord(g_prof_pending_pre, s));
+    return 0;
+}
+
 int profile_mark(const char *name, cudaStream_t s) {
     if (!g_prof_on) return 0;
-    ProfEntry e{name, nullptr};
+    ProfEntry e{name, nullptr, g_prof_pending_pre};
+    g_prof_pending_pre = nullptr;
     LVDGS_CHECK(cudaEventCreate(&e.ev));
     LVDGS_CHECK(cudaEventRecord(e.ev, s));
     g_prof.push_back(e);
@@ -119,7 +129,7 @@ int64_t lvdgs_launch_count(void) { return g_launches.load(); }
 void lvdgs_reset_launch_count(void) { g_launches.store(0); }
 
 int lvdgs_profile_begin(void *stream) {
-    for (auto &e : g_prof) cudaEventDestroy(e.ev);
+    for (auto &e : g_prof) { cudaEventDestroy(e.ev); if (e.pre) cudaEventDestroy(e.pre); }
     g_prof.clear();
     g_prof_on = true;
     return profile_mark("(begin)", (cudaStream_t)stream);
@@ -132,7 +142,8 @@ int lvdgs_profile_end(void *stream, char *names, size_t names_bytes, float *ms, 
     int n = 0;
     for (size_t i = 1; i < g_prof.size() && n < max_entries; ++i, ++n) {
         float t = 0.f;
-        LVDGS_CHECK(cudaEventElapsedTime(&t, g_prof[i - 1].ev, g_prof[i].ev));
+        // a launch has its own "pre" event; host-side markers are measured from the previous entry
+        LVDGS_CHECK(cudaEventElapsedTime(&t, g_prof[i].pre ? g_prof[i].pre : g_prof[i - 1].ev, g_prof[i].ev));
         ms[n] = t;
         all += g_prof[i].name;
         all += '\n';
@@ -142,7 +153,7 @@ int lvdgs_profile_end(void *stream, char *names, size_t names_bytes, float *ms, 
         memcpy(names, all.data(), c);
         names[c] = 0;
     }
-    for (auto &e : g_prof) cudaEventDestroy(e.ev);
+    for (auto &e : g_prof) { cudaEventDestroy(e.ev); if (e.pre) cudaEventDestroy(e.pre); }
     g_prof.clear();
     return n;
 }
@@ -161,10 +172,12 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     (void)projmatrix_raw;
     if (check_params(prm)) return 1;
     const lvdgs_raster_params &p = *prm;
-    if ((shs == nullptr) == (colors_precomp == nullptr)) { set_error("provide exactly one of shs / colors_precomp"); return 1; }
-    const bool has_sr = scales != nullptr && rotations != nullptr;
-    if (has_sr == (cov3D_precomp != nullptr) || ((scales == nullptr) != (rotations == nullptr))) {
-        set_error("provide exactly one of (scales, rotations) / cov3D_precomp"); return 1;
+    if (p.P > 0) {
+        if ((shs == nullptr) == (colors_precomp == nullptr)) { set_error("provide exactly one of shs / colors_precomp"); return 1; }
+        const bool has_sr = scales != nullptr && rotations != nullptr;
+        if (has_sr == (cov3D_precomp != nullptr) || ((scales == nullptr) != (rotations == nullptr))) {
+            set_error("provide exactly one of (scales, rotations) / cov3D_precomp"); return 1;
+        }
     }
     if (shs && p.sh_coeffs < (p.sh_degree + 1) * (p.sh_degree + 1)) { set_error("sh_coeffs %d too small for degree %d", p.sh_coeffs, p.sh_degree); return 1; }
     if (!resize || !out_color || !out_depth || !out_opacity || !num_rendered || !background || !viewmatrix || !projmatrix || !campos) {

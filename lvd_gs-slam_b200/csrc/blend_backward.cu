@@ -144,6 +144,7 @@ int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, c
     if (R <= 0) return 0;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const float *dop = (flags & LVDGS_FLAG_OPACITY_GRAD) ? dL_dout_opacity : nullptr;
+    LVDGS_PRE(s);
     blend_backward_kernel<<<dim3(gx, gy), BB_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
                                                                g.rgbd, bg, final_T, n_contrib, dL_dout_color,
                                                                dL_dout_depth, dop, o.acc);

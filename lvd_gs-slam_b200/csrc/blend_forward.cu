@@ -104,6 +104,7 @@ int launch_blend_forward(int W, int H, const uint2 *ranges, const uint32_t *poin
                          const float *bg, float *out_color, float *out_depth, float *out_opacity, float *final_T,
                          uint32_t *n_contrib, int32_t *n_touched, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    LVDGS_PRE(s);
     blend_forward_kernel<<<dim3(gx, gy), BF_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
                                                               g.rgbd, bg, out_color, out_depth, out_opacity, final_T,
                                                               n_contrib, n_touched);

@@ -13,7 +13,8 @@ constexpr int TILE_PIX = TILE * TILE;
 // ---- error plumbing (api.cu) ----
 void set_error(const char *fmt, ...);
 void count_launch();
-int profile_mark(const char *name, cudaStream_t s);   // records an event after the launch when profiling is on
+int profile_mark(const char *name, cudaStream_t s);   // profiling on: event after the launch (or a host-side marker)
+int profile_pre(cudaStream_t s);                      // profiling on: event right before the launch
 extern thread_local int g_debug_sync;
 
 #define LVDGS_CHECK(expr)                                                                        \
@@ -27,6 +28,11 @@ extern thread_local int g_debug_sync;
     } while (0)
 
 // after every kernel launch: count it, catch launch errors, optionally synchronise (debug)
+#define LVDGS_PRE(stream)                                                                        \
+    do {                                                                                         \
+        if (lvdgs::profile_pre(stream)) return 1;                                                \
+    } while (0)
+
 #define LVDGS_LAUNCHED(stream, name)                                                             \
     do {                                                                                         \
         lvdgs::count_launch();                                                                   \

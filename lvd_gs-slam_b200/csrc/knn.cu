@@ -47,6 +47,7 @@ size_t dist2_workspace_bytes(int P) { (void)P; return 256; }
 int launch_dist2(int P, const float *points, float *mean_dists, void *ws, size_t ws_bytes, cudaStream_t s) {
     (void)ws; (void)ws_bytes;
     if (P <= 0) return 0;
+    LVDGS_PRE(s);
     dist2_bruteforce_kernel<<<ceil_div(P, KNN_THREADS), KNN_THREADS, 0, s>>>(P, points, mean_dists);
     LVDGS_LAUNCHED(s, "dist2");
     return 0;

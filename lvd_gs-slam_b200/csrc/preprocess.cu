@@ -251,6 +251,7 @@ int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D
     a.means3D = means3D; a.colors_precomp = colors_precomp; a.opacities = opacities; a.scales = scales;
     a.rotations = rotations; a.cov3D_precomp = cov3D_precomp; a.view = view; a.proj = proj; a.shs = shs;
     a.campos = campos; a.radii = radii; a.g = g;
+    LVDGS_PRE(s);
     preprocess_forward_kernel<<<ceil_div(p.P, PRE_THREADS), PRE_THREADS, 0, s>>>(a);
     LVDGS_LAUNCHED(s, "preprocess_forward");
     return 0;
@@ -345,10 +346,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int P, const u
 int launch_scan_tiles(int P, const uint32_t *tiles_touched, uint32_t *point_offsets, uint32_t *block_sums,
                       cudaStream_t s) {
     const int nb = ceil_div(P, SCAN_TILE);
+    LVDGS_PRE(s);
     scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(P, tiles_touched, block_sums);
     LVDGS_LAUNCHED(s, "scan_reduce");
+    LVDGS_PRE(s);
     scan_block_sums_kernel<<<1, 1024, 0, s>>>(nb, block_sums);
     LVDGS_LAUNCHED(s, "scan_block_sums");
+    LVDGS_PRE(s);
     scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>(P, tiles_touched, block_sums, point_offsets);
     LVDGS_LAUNCHED(s, "scan_apply");
     return 0;
@@ -405,6 +409,7 @@ int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, const int32_t *radi
                      cudaStream_t s) {
     (void)radii; (void)H;
     const int gx = (W + TILE - 1) / TILE;
+    LVDGS_PRE(s);
     emit_keys_kernel<<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, g.point_offsets, g.rect, g.depths, keys, vals);
     LVDGS_LAUNCHED(s, "emit_keys");
     return 0;
@@ -429,6 +434,7 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t R, const uint6
 int launch_tile_ranges(int64_t R, int num_tiles, const uint64_t *keys_sorted, uint2 *ranges, cudaStream_t s) {
     LVDGS_CHECK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, s));
     if (R > 0) {
+        LVDGS_PRE(s);
         tile_ranges_kernel<<<ceil_div(R, 256), 256, 0, s>>>(R, keys_sorted, ranges);
         LVDGS_LAUNCHED(s, "tile_ranges");
     }
@@ -451,6 +457,7 @@ __global__ void __launch_bounds__(PRE_THREADS) mark_visible_kernel(int P, const 
 
 int launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t s) {
     if (P <= 0) return 0;
+    LVDGS_PRE(s);
     mark_visible_kernel<<<ceil_div(P, PRE_THREADS), PRE_THREADS, 0, s>>>(P, means3D, view, present);
     LVDGS_LAUNCHED(s, "mark_visible");
     return 0;

@@ -191,10 +191,11 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
             const uint8_t cl = a.clamped[i];
             const float dRGB[3] = {(cl & 1) ? 0.f : r2.x, (cl & 2) ? 0.f : r2.y, (cl & 4) ? 0.f : r2.z};
             const int ncoef = (a.D + 1) * (a.D + 1);
-            for (int k = ncoef * 3; k < a.M * 3; ++k) dsh[k] = 0.f;
+            const bool accum_sh = (a.flags & LVDGS_FLAG_ACCUMULATE) != 0;
+            if (!accum_sh) for (int k = ncoef * 3; k < a.M * 3; ++k) dsh[k] = 0.f;
             if (a.D == 0) {
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) dsh[ch] = B_SH_C0 * dRGB[ch];
+                for (int ch = 0; ch < 3; ++ch) { if (accum_sh) dsh[ch] += B_SH_C0 * dRGB[ch]; else dsh[ch] = B_SH_C0 * dRGB[ch]; }
             } else {
                 const float3 dorig = make_float3(x - cam.campos[0], y - cam.campos[1], z - cam.campos[2]);
                 const float s2 = dorig.x * dorig.x + dorig.y * dorig.y + dorig.z * dorig.z;
@@ -203,7 +204,8 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
                 float ddir[3] = {0.f, 0.f, 0.f};
                 for (int ch = 0; ch < 3; ++ch) {
 #define SHC(k) sh[(k) * 3 + ch]
-#define DSH(k) dsh[(k) * 3 + ch]
+#define DSH(k) dshv[k]
+                    float dshv[16];
                     const float g = dRGB[ch];
                     float ddx, ddy, ddz;
                     DSH(0) = B_SH_C0 * g;
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
                         }
                     }
                     ddir[0] += ddx * g; ddir[1] += ddy * g; ddir[2] += ddz * g;
+                    for (int k = 0; k < ncoef; ++k) { if (accum_sh) dsh[k * 3 + ch] += dshv[k]; else dsh[k * 3 + ch] = dshv[k]; }
 #undef SHC
 #undef DSH
                 }
@@ -271,20 +274,30 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
             drot[2] = 2.f * (-2.f * qy * Q[0] + qx * Q[1] + r * Q[2] + qx * Q[3] + qz * Q[5] - r * Q[6] + qz * Q[7] - 2.f * qy * Q[8]);
             drot[3] = 2.f * (-2.f * qz * Q[0] - r * Q[1] + qx * Q[2] + r * Q[3] - 2.f * qz * Q[4] + qy * Q[5] + qx * Q[6] + qy * Q[7]);
         }
-    } else if (i < a.P && a.dL_dsh) {
+    } else if (i < a.P && a.dL_dsh && !(a.flags & LVDGS_FLAG_ACCUMULATE)) {
         float *dsh = a.dL_dsh + (size_t)i * a.M * 3;
         for (int k = 0; k < a.M * 3; ++k) dsh[k] = 0.f;
     }
     if (i < a.P) {
+        // parameter gradients are either stored or, with LVDGS_FLAG_ACCUMULATE, added to what the caller's buffers
+        // hold (the mapping loss is a SUM over keyframe views, utils/slam_backend.py:266,300); per-view outputs
+        // (dL_dmeans2D, dL_dtau) are always stored.
+        const bool accum = (a.flags & LVDGS_FLAG_ACCUMULATE) != 0;
+#define PUT(ptr, idx, v) do { if (accum) (ptr)[idx] += (v); else (ptr)[idx] = (v); } while (0)
         const size_t i3 = 3 * (size_t)i;
         a.dL_dmeans2D[i3] = r0.x; a.dL_dmeans2D[i3 + 1] = r0.y; a.dL_dmeans2D[i3 + 2] = 0.f;
-        a.dL_dcolors[i3] = r2.x; a.dL_dcolors[i3 + 1] = r2.y; a.dL_dcolors[i3 + 2] = r2.z;
-        a.dL_dopacity[i] = r1.y;
-        a.dL_dmeans3D[i3] = dmean[0]; a.dL_dmeans3D[i3 + 1] = dmean[1]; a.dL_dmeans3D[i3 + 2] = dmean[2];
+        PUT(a.dL_dcolors, i3, r2.x); PUT(a.dL_dcolors, i3 + 1, r2.y); PUT(a.dL_dcolors, i3 + 2, r2.z);
+        PUT(a.dL_dopacity, i, r1.y);
+        PUT(a.dL_dmeans3D, i3, dmean[0]); PUT(a.dL_dmeans3D, i3 + 1, dmean[1]); PUT(a.dL_dmeans3D, i3 + 2, dmean[2]);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * (size_t)i + k] = dcov[k];
-        if (a.dL_dscales) { a.dL_dscales[i3] = dscale[0]; a.dL_dscales[i3 + 1] = dscale[1]; a.dL_dscales[i3 + 2] = dscale[2]; }
-        if (a.dL_drots) reinterpret_cast<float4 *>(a.dL_drots)[i] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+        for (int k = 0; k < 6; ++k) PUT(a.dL_dcov3D, 6 * (size_t)i + k, dcov[k]);
+        if (a.dL_dscales) { PUT(a.dL_dscales, i3, dscale[0]); PUT(a.dL_dscales, i3 + 1, dscale[1]); PUT(a.dL_dscales, i3 + 2, dscale[2]); }
+        if (a.dL_drots) {
+            float4 *dst = reinterpret_cast<float4 *>(a.dL_drots) + i;
+            float4 v = make_float4(drot[0], drot[1], drot[2], drot[3]);
+            if (accum) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *dst = v;
+        }
         if (a.dL_dtau) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) a.dL_dtau[6 * (size_t)i + k] = tau[k];
@@ -329,6 +342,7 @@ int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3
     a.dL_dcov3D = dL_dcov3D; a.dL_dsh = colors_are_precomp ? nullptr : dL_dsh; a.dL_dscales = dL_dscales;
     a.dL_drots = dL_drots; a.dL_dtau = dL_dtau; a.dL_dtau_sum = dL_dtau_sum;
     if (dL_dtau_sum) LVDGS_CHECK(cudaMemsetAsync(dL_dtau_sum, 0, 6 * sizeof(float), s));
+    LVDGS_PRE(s);
     preprocess_backward_kernel<<<ceil_div(p.P, PB_THREADS), PB_THREADS, 0, s>>>(a);
     LVDGS_LAUNCHED(s, "preprocess_backward");
     return 0;

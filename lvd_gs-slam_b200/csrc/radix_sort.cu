@@ -228,14 +228,17 @@ int launch_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *val
         attr_set = true;
     }
     const int hist_blocks = (int)min((int64_t)148 * 8, (n + RS_THREADS * 8 - 1) / (RS_THREADS * 8));
+    LVDGS_PRE(s);
     rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, s>>>(keys0, n, passes, end_bit, ws);
     LVDGS_LAUNCHED(s, "sort_histogram");
+    LVDGS_PRE(s);
     rs_scan_hist_kernel<<<passes, RS_BINS, 0, s>>>(ws);
     LVDGS_LAUNCHED(s, "sort_scan_hist");
     uint64_t *kin = keys0, *kout = keys1;
     uint32_t *vin = vals0, *vout = vals1;
     for (int p = 0; p < passes; ++p) {
         const int shift = p * 8, nb = min(8, end_bit - shift);
+        LVDGS_PRE(s);
         rs_onesweep_kernel<<<ntiles, RS_THREADS, sizeof(RsSmem), s>>>(kin, kout, vin, vout, n, shift, nb, p, ws,
                                                                       reinterpret_cast<uint32_t *>(lb_base + lb_stride * p));
         LVDGS_LAUNCHED(s, "sort_onesweep");
