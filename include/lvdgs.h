@@ -13,7 +13,8 @@
  * as void*.  Functions return 0 on success, non-zero on error (message: lvdgs_last_error()).  No allocation
  * happens inside the library: growable buffers are obtained through the caller's lvdgs_resize_fn, exactly
  * like upstream's `resizeFunctional` over torch uint8 tensors.  The only host synchronisation is the one
- * upstream has too: reading back the instance count R between binning and sorting.
+ * upstream has too: reading back the instance count R between binning and sorting (hidden behind speculative
+ * launches when the caller passes a capacity hint, see lvdgs_rasterize_forward).
  */
 #ifndef LVDGS_H
 #define LVDGS_H
@@ -50,13 +51,14 @@ typedef struct lvdgs_raster_params {
 } lvdgs_raster_params;
 
 /* Must return a device pointer to at least `bytes` bytes, 256-byte aligned, valid until the matching backward
- * has run.  Called at most once per buffer per forward, from the calling thread. */
+ * has run.  Called once per buffer per forward (twice for LVDGS_BUF_BINNING when a capacity hint was too small),
+ * from the calling thread; the latest pointer per buffer is the live one. */
 typedef void *(*lvdgs_resize_fn)(void *user, int32_t which, size_t bytes);
 
 /* Byte offsets of the arrays inside the three opaque buffers (for parity tests and debuggers). */
 typedef struct lvdgs_geom_layout {
     size_t depths;         /* float  [P]    view-space z */
-    size_t means2D;        /* float2 [P]    pixel centre */
+    size_t means2D;        /* float4 [P]    pixel centre x,y + half extents hx,hy of the alpha>=1/255 ellipse's bounding box */
     size_t conic_opacity;  /* float4 [P]    conic xx,xy,yy + opacity */
     size_t rgbd;           /* float4 [P]    rgb after SH + clamp, w = depth */
     size_t rect;           /* int16x4 [P]   tile rect min.x,min.y,max.x,max.y */
@@ -108,15 +110,21 @@ int lvdgs_get_img_layout(int32_t width, int32_t height, lvdgs_img_layout *out);
  *   means3D [P,3]; opacities [P]; exactly one of {shs [P,M,3], colors_precomp [P,3]};
  *   exactly one of {scales [P,3] + rotations [P,4], cov3D_precomp [P,6]}; background [3]; campos [3].
  * Outputs: out_color [3,H,W], radii [P] int32, out_depth [H,W], out_opacity [H,W], n_touched [P] int32,
- *   *num_rendered (host) = R, the number of (tile, Gaussian) instances.
+ *   *num_rendered (host) = R, the number of (tile, Gaussian) instances; *binning_capacity (host) = the instance
+ *   capacity the binning buffer was laid out for (pass both to the backward).
+ * capacity_hint: 0 = size the binning buffer exactly, after reading R back (upstream's behaviour: the device idles
+ *   while the host reads R and launches the rest).  > 0 = speculative mode: the binning buffer is requested for
+ *   `capacity_hint` instances and the whole remainder of the forward is queued BEFORE the host waits for R; if
+ *   R > capacity_hint the remainder is re-run with an exactly sized buffer (resize is then called a second time
+ *   for LVDGS_BUF_BINNING).  Results are identical in both modes.
  */
 int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *background, const float *means3D,
                             const float *colors_precomp, const float *opacities, const float *scales,
                             const float *rotations, const float *cov3D_precomp, const float *viewmatrix,
                             const float *projmatrix, const float *projmatrix_raw, const float *shs,
-                            const float *campos, lvdgs_resize_fn resize, void *resize_user, float *out_color,
-                            int32_t *radii, float *out_depth, float *out_opacity, int32_t *n_touched,
-                            int64_t *num_rendered, void *stream);
+                            const float *campos, lvdgs_resize_fn resize, void *resize_user, int64_t capacity_hint,
+                            float *out_color, int32_t *radii, float *out_depth, float *out_opacity,
+                            int32_t *n_touched, int64_t *num_rendered, int64_t *binning_capacity, void *stream);
 
 /* Device scratch needed by lvdgs_rasterize_backward for P Gaussians and R instances. */
 size_t lvdgs_backward_scratch_bytes(int32_t P, int64_t R);
@@ -139,7 +147,7 @@ int lvdgs_rasterize_backward(const lvdgs_raster_params *prm, const float *backgr
                              const float *viewmatrix, const float *projmatrix, const float *projmatrix_raw,
                              const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_opacity,
                              const float *shs, const float *campos, const void *geom_buffer, int64_t R,
-                             const void *binning_buffer, const void *img_buffer, void *scratch,
+                             int64_t binning_capacity, const void *binning_buffer, const void *img_buffer, void *scratch,
                              size_t scratch_bytes, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
                              float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales,
                              float *dL_drots, float *dL_dtau, float *dL_dtau_sum, void *stream);

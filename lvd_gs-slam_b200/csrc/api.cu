@@ -50,7 +50,7 @@ static void geom_layout(int32_t P, lvdgs_geom_layout &l) {
     size_t o = 0;
     const size_t n = (size_t)(P > 0 ? P : 1);
     l.depths = o; o += align_up(n * sizeof(float));
-    l.means2D = o; o += align_up(n * sizeof(float2));
+    l.means2D = o; o += align_up(n * sizeof(float4));
     l.conic_opacity = o; o += align_up(n * sizeof(float4));
     l.rgbd = o; o += align_up(n * sizeof(float4));
     l.rect = o; o += align_up(n * sizeof(short4));
@@ -82,7 +82,7 @@ static GeomPtrs geom_ptrs(void *base, int32_t P) {
     lvdgs_geom_layout l; geom_layout(P, l);
     char *b = (char *)base;
     GeomPtrs g;
-    g.depths = (float *)(b + l.depths); g.means2D = (float2 *)(b + l.means2D);
+    g.depths = (float *)(b + l.depths); g.means2D = (float4 *)(b + l.means2D);
     g.conic_opacity = (float4 *)(b + l.conic_opacity); g.rgbd = (float4 *)(b + l.rgbd);
     g.rect = (short4 *)(b + l.rect); g.tiles_touched = (uint32_t *)(b + l.tiles_touched);
     g.point_offsets = (uint32_t *)(b + l.point_offsets); g.clamped = (uint8_t *)(b + l.clamped);
@@ -162,13 +162,37 @@ int lvdgs_get_geom_layout(int32_t P, lvdgs_geom_layout *out) { if (!out) return 
 int lvdgs_get_binning_layout(int64_t R, lvdgs_binning_layout *out) { if (!out) return 1; binning_layout(R, *out); return 0; }
 int lvdgs_get_img_layout(int32_t W, int32_t H, lvdgs_img_layout *out) { if (!out) return 1; img_layout(W, H, *out); return 0; }
 
+// pinned slot + event for the asynchronous read-back of the instance count (one per host thread, created once)
+static thread_local uint32_t *t_pinned_R = nullptr;
+static thread_local cudaEvent_t t_R_event = nullptr;
+
+// everything after the instance count is known on the DEVICE: keys, sort, ranges, blend.  `capacity` sizes the
+// launches and the binning arena; the kernels clamp to min(R, capacity) read from device memory.
+static int launch_bin_and_blend(const lvdgs_raster_params &p, const GeomPtrs &g, const BinPtrs &b, const ImgPtrs &im,
+                                int64_t capacity, const float *background, float *out_color, float *out_depth,
+                                float *out_opacity, int32_t *n_touched, cudaStream_t s) {
+    const int W = p.width, H = p.height;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const uint32_t *R_dev = g.point_offsets + (p.P - 1);
+    LVDGS_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * (size_t)p.P, s));
+    if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], b.vals[0], s)) return 1;
+    const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
+    int sel = 0;
+    if (launch_sort_pairs(capacity, R_dev, b.keys[0], b.keys[1], b.vals[0], b.vals[1], end_bit, b.sort_ws,
+                          sort_workspace_bytes(capacity), &sel, s)) return 1;
+    LVDGS_CHECK(cudaMemcpyAsync(b.sorted_sel, &sel, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (launch_tile_ranges(capacity, R_dev, gx * gy, b.keys[sel], im.ranges, s)) return 1;
+    return launch_blend_forward(W, H, im.ranges, b.vals[sel], g, background, out_color, out_depth, out_opacity,
+                                im.final_T, im.n_contrib, n_touched, s);
+}
+
 int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *background, const float *means3D,
                             const float *colors_precomp, const float *opacities, const float *scales,
                             const float *rotations, const float *cov3D_precomp, const float *viewmatrix,
                             const float *projmatrix, const float *projmatrix_raw, const float *shs,
-                            const float *campos, lvdgs_resize_fn resize, void *resize_user, float *out_color,
-                            int32_t *radii, float *out_depth, float *out_opacity, int32_t *n_touched,
-                            int64_t *num_rendered, void *stream) {
+                            const float *campos, lvdgs_resize_fn resize, void *resize_user, int64_t capacity_hint,
+                            float *out_color, int32_t *radii, float *out_depth, float *out_opacity,
+                            int32_t *n_touched, int64_t *num_rendered, int64_t *binning_capacity, void *stream) {
     (void)projmatrix_raw;
     if (check_params(prm)) return 1;
     const lvdgs_raster_params &p = *prm;
@@ -180,7 +204,8 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
         }
     }
     if (shs && p.sh_coeffs < (p.sh_degree + 1) * (p.sh_degree + 1)) { set_error("sh_coeffs %d too small for degree %d", p.sh_coeffs, p.sh_degree); return 1; }
-    if (!resize || !out_color || !out_depth || !out_opacity || !num_rendered || !background || !viewmatrix || !projmatrix || !campos) {
+    if (!resize || !out_color || !out_depth || !out_opacity || !num_rendered || !binning_capacity || !background ||
+        !viewmatrix || !projmatrix || !campos) {
         set_error("NULL required argument"); return 1;
     }
     if (p.P > 0 && (!means3D || !opacities || !radii || !n_touched)) { set_error("NULL per-Gaussian argument"); return 1; }
@@ -189,51 +214,60 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     const int W = p.width, H = p.height;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     *num_rendered = 0;
+    *binning_capacity = 0;
 
     lvdgs_img_layout il; img_layout(W, H, il);
     void *img_base = resize(resize_user, LVDGS_BUF_IMG, il.total);
     if (!img_base) { set_error("resize callback returned NULL (img)"); return 1; }
     ImgPtrs im = img_ptrs(img_base, W, H);
 
-    int64_t R = 0;
-    GeomPtrs g{};
-    BinPtrs b{};
-    const uint32_t *point_list = nullptr;
-    if (p.P > 0) {
-        lvdgs_geom_layout gl; geom_layout(p.P, gl);
-        void *geom_base = resize(resize_user, LVDGS_BUF_GEOM, gl.total);
-        if (!geom_base) { set_error("resize callback returned NULL (geom)"); return 1; }
-        g = geom_ptrs(geom_base, p.P);
-        if (launch_preprocess_forward(p, means3D, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
-                                      projmatrix, shs, campos, radii, g, s)) return 1;
-        // the scan's block sums (ceil(P/2048) words) borrow n_touched, which is zeroed right after the R read-back
-        if (launch_scan_tiles(p.P, g.tiles_touched, g.point_offsets, reinterpret_cast<uint32_t *>(n_touched), s)) return 1;
-        uint32_t R32 = 0;
-        LVDGS_CHECK(cudaMemcpyAsync(&R32, g.point_offsets + (p.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        LVDGS_CHECK(cudaStreamSynchronize(s));
-        if (profile_mark("(host: R read-back)", s)) return 1;
-        R = R32;
-        LVDGS_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * (size_t)p.P, s));
+    if (p.P == 0) {     // empty map: background only
+        LVDGS_CHECK(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)gx * gy, s));
+        GeomPtrs g{};
+        return launch_blend_forward(W, H, im.ranges, nullptr, g, background, out_color, out_depth, out_opacity, im.final_T,
+                                    im.n_contrib, n_touched, s);
     }
-    *num_rendered = R;
-    if (R > 0) {
-        lvdgs_binning_layout bl; binning_layout(R, bl);
+    if (!t_pinned_R) {
+        LVDGS_CHECK(cudaHostAlloc((void **)&t_pinned_R, 64, cudaHostAllocDefault));
+        LVDGS_CHECK(cudaEventCreateWithFlags(&t_R_event, cudaEventDisableTiming));
+    }
+    lvdgs_geom_layout gl; geom_layout(p.P, gl);
+    void *geom_base = resize(resize_user, LVDGS_BUF_GEOM, gl.total);
+    if (!geom_base) { set_error("resize callback returned NULL (geom)"); return 1; }
+    GeomPtrs g = geom_ptrs(geom_base, p.P);
+    if (launch_preprocess_forward(p, means3D, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
+                                  projmatrix, shs, campos, radii, g, s)) return 1;
+    // the scan's block sums (ceil(P/2048) words) borrow n_touched, which is zeroed before the blend
+    if (launch_scan_tiles(p.P, g.tiles_touched, g.point_offsets, reinterpret_cast<uint32_t *>(n_touched), s)) return 1;
+    LVDGS_CHECK(cudaMemcpyAsync(t_pinned_R, g.point_offsets + (p.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    LVDGS_CHECK(cudaEventRecord(t_R_event, s));
+
+    // Speculative launch: with a capacity hint the whole rest of the forward is queued BEFORE the host waits for R,
+    // so the device never idles across the read-back.  If R turns out larger than the hint, the tail is re-run with
+    // an exactly sized arena (the speculative results are simply overwritten).
+    int64_t capacity = capacity_hint > 0 ? capacity_hint : 0;
+    bool launched = false;
+    if (capacity > 0) {
+        lvdgs_binning_layout bl; binning_layout(capacity, bl);
         void *bin_base = resize(resize_user, LVDGS_BUF_BINNING, bl.total);
         if (!bin_base) { set_error("resize callback returned NULL (binning)"); return 1; }
-        b = bin_ptrs(bin_base, R);
-        if (launch_emit_keys(p.P, W, H, g, radii, b.keys[0], b.vals[0], s)) return 1;
-        const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
-        int sel = 0;
-        if (launch_sort_pairs(R, b.keys[0], b.keys[1], b.vals[0], b.vals[1], end_bit, b.sort_ws,
-                              sort_workspace_bytes(R), &sel, s)) return 1;
-        LVDGS_CHECK(cudaMemcpyAsync(b.sorted_sel, &sel, sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        if (launch_tile_ranges(R, gx * gy, b.keys[sel], im.ranges, s)) return 1;
-        point_list = b.vals[sel];
-    } else {
-        LVDGS_CHECK(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)gx * gy, s));
+        if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, background, out_color, out_depth,
+                                 out_opacity, n_touched, s)) return 1;
+        launched = true;
     }
-    if (launch_blend_forward(W, H, im.ranges, point_list, g, background, out_color, out_depth, out_opacity, im.final_T,
-                             im.n_contrib, n_touched, s)) return 1;
+    LVDGS_CHECK(cudaEventSynchronize(t_R_event));
+    if (profile_mark("(host: R read-back)", s)) return 1;
+    const int64_t R = *t_pinned_R;
+    *num_rendered = R;
+    if (!launched || R > capacity) {
+        capacity = R > 0 ? R : 1;
+        lvdgs_binning_layout bl; binning_layout(capacity, bl);
+        void *bin_base = resize(resize_user, LVDGS_BUF_BINNING, bl.total);
+        if (!bin_base) { set_error("resize callback returned NULL (binning)"); return 1; }
+        if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, background, out_color, out_depth,
+                                 out_opacity, n_touched, s)) return 1;
+    }
+    *binning_capacity = capacity;
     return 0;
 }
 
@@ -248,7 +282,7 @@ int lvdgs_rasterize_backward(const lvdgs_raster_params *prm, const float *backgr
                              const float *viewmatrix, const float *projmatrix, const float *projmatrix_raw,
                              const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_opacity,
                              const float *shs, const float *campos, const void *geom_buffer, int64_t R,
-                             const void *binning_buffer, const void *img_buffer, void *scratch,
+                             int64_t binning_capacity, const void *binning_buffer, const void *img_buffer, void *scratch,
                              size_t scratch_bytes, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
                              float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales,
                              float *dL_drots, float *dL_dtau, float *dL_dtau_sum, void *stream) {
@@ -272,7 +306,7 @@ int lvdgs_rasterize_backward(const lvdgs_raster_params *prm, const float *backgr
     BlendGradPtrs bg{(float *)scratch};
     LVDGS_CHECK(cudaMemsetAsync(scratch, 0, (size_t)p.P * ACC_STRIDE * sizeof(float), s));
     if (R > 0) {
-        BinPtrs b = bin_ptrs(const_cast<void *>(binning_buffer), R);
+        BinPtrs b = bin_ptrs(const_cast<void *>(binning_buffer), binning_capacity);
         const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
         const int passes = (32 + tile_bits((uint32_t)(gx * gy)) + 7) / 8;
         const int sel = passes & 1;
@@ -307,7 +341,7 @@ int lvdgs_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *vals
                      int32_t end_bit, void *workspace, size_t workspace_bytes, int32_t *selector, void *stream) {
     g_debug_sync = 0;
     int sel = 0;
-    const int rc = launch_sort_pairs(n, keys0, keys1, vals0, vals1, end_bit, workspace, workspace_bytes, &sel,
+    const int rc = launch_sort_pairs(n, nullptr, keys0, keys1, vals0, vals1, end_bit, workspace, workspace_bytes, &sel,
                                      (cudaStream_t)stream);
     if (selector) *selector = sel;
     return rc;

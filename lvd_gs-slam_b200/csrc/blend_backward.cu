@@ -1,27 +1,65 @@
 // blend_backward.cu -- K7: back-to-front gradient of the tile blend (reached through
 // loss.backward() at utils/slam_frontend.py:1517 and utils/slam_backend.py:306).
 //
-// The reference issues ten global float atomicAdds per (pixel, Gaussian) pair.  Here a CTA owns one tile and a
-// thread one pixel, the per-pixel recurrences (T, accumulated colour/depth behind the current Gaussian) are
-// those of A.4, but the ten per-Gaussian partial sums are first reduced across the warp with shuffles
-// (skipped entirely when no pixel of the warp was touched by the Gaussian) and committed by one lane into a
-// 48-byte accumulator row per Gaussian.  The traversal starts at the tile's largest n_contrib, not at the end
-// of the tile's list, so the part of the list that every pixel terminated before is never loaded.
+// The reference issues ten global float atomicAdds per (pixel, Gaussian) pair.  Here:
+//  * a CTA of 4 warps owns a 16x16 tile, a warp an 8x8 pixel block, a thread TWO pixels (rows y and y+4), so one
+//    warp-level reduction serves 64 pairs;
+//  * instances are staged 128 at a time through shared memory, rearmost first, together with a per-block mask from
+//    the same conservative {alpha >= 1/255} bounding-box test as the forward: a warp only visits instances that can
+//    reach its block, and the traversal starts at the tile's largest n_contrib instead of the end of the list;
+//  * per pixel the recurrences are those of A.4 (T <- T/(1-alpha); colour/depth accumulated behind the current
+//    Gaussian), evaluated eagerly;
+//  * per (warp, Gaussian) the twelve partial sums (six geometric moments of m = G dL/dalpha, depth, rgb -- see
+//    ACC_STRIDE in common.cuh) are reduced with a transposing butterfly: 16 shuffles in total instead of 5 per value,
+//    after which sixteen lanes each hold one finished slot and commit it with a single warp-wide RED instruction.
 #include "common.cuh"
 
 namespace lvdgs {
 
-constexpr int BB_THREADS = TILE_PIX;
+constexpr int BB_THREADS = 128;
+constexpr int BB_WARPS = BB_THREADS / 32;      // 4 warps = 2 x 2 blocks of 8 x 8 pixels
 
-__device__ __forceinline__ float warp_sum(float v) {
+// After the call v[0] of lane L holds the warp-wide sum of slot ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
+__device__ __forceinline__ void transpose_reduce16(float (&v)[16], int lane) {
+    {
+        const bool up = lane & 16;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
+        for (int i = 0; i < 8; ++i) {
+            const float send = up ? v[i] : v[i + 8];
+            const float keep = up ? v[i + 8] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = up ? v[i] : v[i + 4];
+            const float keep = up ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = up ? v[i] : v[i + 2];
+            const float keep = up ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool up = lane & 2;
+        const float send = up ? v[0] : v[1];
+        const float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     int W, int H, int gx, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
-    const float2 *__restrict__ means2D, const float4 *__restrict__ conic_opacity, const float4 *__restrict__ rgbd,
+    const float4 *__restrict__ means2D, const float4 *__restrict__ conic_opacity, const float4 *__restrict__ rgbd,
     const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
     const float *__restrict__ dL_dout_color, const float *__restrict__ dL_dout_depth,
     const float *__restrict__ dL_dout_opacity, float *__restrict__ acc) {
@@ -29,107 +67,133 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     __shared__ float2 s_xy[BB_THREADS];
     __shared__ float4 s_co[BB_THREADS];
     __shared__ float4 s_cd[BB_THREADS];
-    __shared__ uint32_t s_max[BB_THREADS / 32];
+    __shared__ uint32_t s_mask[BB_WARPS][BB_WARPS];     // [staging warp][pixel block]
+    __shared__ uint32_t s_top[BB_WARPS];
 
     const int tile = blockIdx.y * gx + blockIdx.x;
-    const int lx = threadIdx.x & (TILE - 1), ly = threadIdx.x >> 4;
-    const int px = blockIdx.x * TILE + lx, py = blockIdx.y * TILE + ly;
-    const bool inside = px < W && py < H;
-    const float pfx = (float)px, pfy = (float)py;
-    const int lane = threadIdx.x & 31;
-    const size_t pix = (size_t)py * W + px, HW = (size_t)H * W;
-
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bx = warp & 1, by = warp >> 1;
+    const int px = blockIdx.x * TILE + bx * 8 + (lane & 7);
+    const int py0 = blockIdx.y * TILE + by * 8 + (lane >> 3);
+    const float pfx = (float)px;
+    const float tx0 = (float)(blockIdx.x * TILE), ty0 = (float)(blockIdx.y * TILE);
+    const size_t HW = (size_t)H * W;
     const uint2 range = ranges[tile];
-    const uint32_t last = inside ? n_contrib[pix] : 0u;   // this pixel handles contributor indices < last
-    const float T_final = inside ? final_T[pix] : 0.f;
-    float T = T_final;
-    float dpx0 = 0.f, dpx1 = 0.f, dpx2 = 0.f, dpd = 0.f, bg_dot = 0.f;
-    if (inside) {
-        dpx0 = dL_dout_color[pix]; dpx1 = dL_dout_color[HW + pix]; dpx2 = dL_dout_color[2 * HW + pix];
-        if (dL_dout_depth) dpd = dL_dout_depth[pix];
-        bg_dot = __ldg(bg) * dpx0 + __ldg(bg + 1) * dpx1 + __ldg(bg + 2) * dpx2;
-        if (dL_dout_opacity) bg_dot -= dL_dout_opacity[pix];
-    }
-    // tile-wide max of n_contrib: nothing beyond it contributes to any pixel
-    uint32_t m = last;
+
+    // per-pixel state (q = 0: row py0, q = 1: row py0 + 4)
+    float pfy[2], T[2], Tf[2], dp0[2], dp1[2], dp2[2], dpd[2], bgd[2], B0[2], B1[2], B2[2], Bd[2];
+    uint32_t last[2];
+    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if (lane == 0) s_max[threadIdx.x >> 5] = m;
+    for (int q = 0; q < 2; ++q) {
+        const int py = py0 + 4 * q;
+        const bool inside = px < W && py < H;
+        const size_t pix = (size_t)py * W + px;
+        pfy[q] = (float)py;
+        last[q] = inside ? n_contrib[pix] : 0u;
+        Tf[q] = inside ? final_T[pix] : 0.f;
+        T[q] = Tf[q];
+        dp0[q] = inside ? dL_dout_color[pix] : 0.f;
+        dp1[q] = inside ? dL_dout_color[HW + pix] : 0.f;
+        dp2[q] = inside ? dL_dout_color[2 * HW + pix] : 0.f;
+        dpd[q] = (inside && dL_dout_depth) ? dL_dout_depth[pix] : 0.f;
+        bgd[q] = bg0 * dp0[q] + bg1 * dp1[q] + bg2 * dp2[q];
+        if (inside && dL_dout_opacity) bgd[q] -= dL_dout_opacity[pix];   // d(1 - T_final)/dalpha = +T_final/(1-alpha)
+        B0[q] = B1[q] = B2[q] = Bd[q] = 0.f;
+    }
+    // warp-wide and tile-wide max of n_contrib: nothing at or beyond it contributes
+    uint32_t wtop = max(last[0], last[1]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) wtop = max(wtop, __shfl_xor_sync(0xffffffffu, wtop, d));
+    if (lane == 0) s_top[warp] = wtop;
     __syncthreads();
     uint32_t top = 0;
 #pragma unroll
-    for (int k = 0; k < BB_THREADS / 32; ++k) top = max(top, s_max[k]);
+    for (int k = 0; k < BB_WARPS; ++k) top = max(top, s_top[k]);
     top = min(top, range.y - range.x);
 
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, ad = 0.f;           // accum_rec colour / depth
-    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;
-    const float half_W = 0.5f * (float)W, half_H = 0.5f * (float)H;
+    // slot of the transposing reduction this lane ends up holding, and whether it is a real accumulator slot
+    const int slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const bool commits = !(lane & 1) && slot < 11 && slot != 7;
 
     // entries are visited in decreasing contributor index k = top-1 ... 0
     for (int remaining = (int)top; remaining > 0; remaining -= BB_THREADS) {
         __syncthreads();
         const int nb = min(BB_THREADS, remaining);
+        uint32_t blocks = 0;
         if ((int)threadIdx.x < nb) {
             const uint32_t id = __ldg(point_list + range.x + (uint32_t)(remaining - 1 - (int)threadIdx.x));
+            const float4 m = __ldg(means2D + id);
             s_id[threadIdx.x] = id;
-            s_xy[threadIdx.x] = __ldg(means2D + id);
+            s_xy[threadIdx.x] = make_float2(m.x, m.y);
             s_co[threadIdx.x] = __ldg(conic_opacity + id);
             s_cd[threadIdx.x] = __ldg(rgbd + id);
+            const float rx = m.x - tx0, ry = m.y - ty0;
+            uint32_t xb = 0, yb = 0;
+            if (!(rx + m.z < 0.f) && !(rx - m.z > 7.f)) xb |= 1u;
+            if (!(rx + m.z < 8.f) && !(rx - m.z > 15.f)) xb |= 2u;
+            if (!(ry + m.w < 0.f) && !(ry - m.w > 7.f)) yb |= 1u;
+            if (!(ry + m.w < 8.f) && !(ry - m.w > 15.f)) yb |= 2u;
+            if (yb & 1u) blocks |= xb;
+            if (yb & 2u) blocks |= xb << 2;
+        }
+#pragma unroll
+        for (int r = 0; r < BB_WARPS; ++r) {
+            const uint32_t m = __ballot_sync(0xffffffffu, (blocks >> r) & 1u);
+            if (lane == r) s_mask[warp][r] = m;
         }
         __syncthreads();
-        for (int j = 0; j < nb; ++j) {
-            const uint32_t k = (uint32_t)(remaining - 1 - j);    // contributor index (0-based) of this entry
-            float g_mx = 0.f, g_my = 0.f, g_cxx = 0.f, g_cxy = 0.f, g_cyy = 0.f, g_op = 0.f, g_dd = 0.f,
-                  g_c0 = 0.f, g_c1 = 0.f, g_c2 = 0.f;
-            bool valid = false;
-            if (k < last) {
+        for (int wp = 0; wp < BB_WARPS; ++wp) {
+            uint32_t mask = s_mask[wp][warp];
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int j = wp * 32 + b;
+                const uint32_t k = (uint32_t)(remaining - 1 - j);    // contributor index (0-based) of this entry
+                if (k >= wtop) continue;                             // warp-uniform
                 const float2 xy = s_xy[j];
                 const float4 co = s_co[j];
-                const float dx = xy.x - pfx, dy = xy.y - pfy;
-                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-                if (power <= 0.f) {
-                    const float G = __expf(power);
-                    const float alpha = fminf(0.99f, co.w * G);
-                    if (alpha >= 1.f / 255.f) {
-                        valid = true;
-                        const float4 cd = s_cd[j];
-                        const float one_m = 1.f - alpha;
-                        T = __fdividef(T, one_m);
-                        const float wgt = alpha * T;
-                        float dL_dalpha;
-                        a0 = last_alpha * lc0 + (1.f - last_alpha) * a0; lc0 = cd.x;
-                        a1 = last_alpha * lc1 + (1.f - last_alpha) * a1; lc1 = cd.y;
-                        a2 = last_alpha * lc2 + (1.f - last_alpha) * a2; lc2 = cd.z;
-                        ad = last_alpha * ld + (1.f - last_alpha) * ad; ld = cd.w;
-                        dL_dalpha = (cd.x - a0) * dpx0 + (cd.y - a1) * dpx1 + (cd.z - a2) * dpx2 + (cd.w - ad) * dpd;
-                        g_c0 = wgt * dpx0; g_c1 = wgt * dpx1; g_c2 = wgt * dpx2; g_dd = wgt * dpd;
-                        dL_dalpha *= T;
-                        last_alpha = alpha;
-                        dL_dalpha += __fdividef(-T_final, one_m) * bg_dot;
-                        const float dL_dG = co.w * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * co.x - gdy * co.y;
-                        const float dG_ddely = -gdy * co.z - gdx * co.y;
-                        g_mx = dL_dG * dG_ddelx * half_W;
-                        g_my = dL_dG * dG_ddely * half_H;
-                        g_cxx = -0.5f * gdx * dx * dL_dG;
-                        g_cxy = -0.5f * gdx * dy * dL_dG;
-                        g_cyy = -0.5f * gdy * dy * dL_dG;
-                        g_op = G * dL_dalpha;
+                const float4 cd = s_cd[j];
+                const float dx = xy.x - pfx;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                bool valid = false;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (k < last[q]) {
+                        const float dy = xy.y - pfy[q];
+                        const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                        if (power <= 0.f) {
+                            const float G = __expf(power);
+                            const float alpha = fminf(0.99f, co.w * G);
+                            if (alpha >= 1.f / 255.f) {
+                                valid = true;
+                                const float one_m = 1.f - alpha;
+                                T[q] = __fdividef(T[q], one_m);
+                                const float wgt = alpha * T[q];
+                                float dL_dalpha = (cd.x - B0[q]) * dp0[q] + (cd.y - B1[q]) * dp1[q] +
+                                                  (cd.z - B2[q]) * dp2[q] + (cd.w - Bd[q]) * dpd[q];
+                                dL_dalpha *= T[q];
+                                dL_dalpha += __fdividef(-Tf[q], one_m) * bgd[q];
+                                B0[q] = alpha * cd.x + one_m * B0[q];
+                                B1[q] = alpha * cd.y + one_m * B1[q];
+                                B2[q] = alpha * cd.z + one_m * B2[q];
+                                Bd[q] = alpha * cd.w + one_m * Bd[q];
+                                const float m = G * dL_dalpha;
+                                const float mdx = m * dx, mdy = m * dy;
+                                v[0] += mdx; v[1] += mdy;
+                                v[2] += mdx * dx; v[3] += mdx * dy; v[4] += mdy * dy;
+                                v[5] += m;
+                                v[6] += wgt * dpd[q];
+                                v[8] += wgt * dp0[q]; v[9] += wgt * dp1[q]; v[10] += wgt * dp2[q];
+                            }
+                        }
                     }
                 }
-            }
-            if (__any_sync(0xffffffffu, valid)) {
-                g_mx = warp_sum(g_mx); g_my = warp_sum(g_my);
-                g_cxx = warp_sum(g_cxx); g_cxy = warp_sum(g_cxy); g_cyy = warp_sum(g_cyy);
-                g_op = warp_sum(g_op); g_dd = warp_sum(g_dd);
-                g_c0 = warp_sum(g_c0); g_c1 = warp_sum(g_c1); g_c2 = warp_sum(g_c2);
-                if (lane == 0) {
-                    float *row = acc + (size_t)s_id[j] * ACC_STRIDE;
-                    atomicAdd(row + 0, g_mx); atomicAdd(row + 1, g_my);
-                    atomicAdd(row + 2, g_cxx); atomicAdd(row + 3, g_cxy); atomicAdd(row + 4, g_cyy);
-                    atomicAdd(row + 5, g_op); atomicAdd(row + 6, g_dd);
-                    atomicAdd(row + 8, g_c0); atomicAdd(row + 9, g_c1); atomicAdd(row + 10, g_c2);
+                if (__any_sync(0xffffffffu, valid)) {
+                    transpose_reduce16(v, lane);
+                    if (commits) atomicAdd(acc + (size_t)s_id[j] * ACC_STRIDE + slot, v[0]);
                 }
             }
         }

@@ -2,10 +2,16 @@
 // opacity (1 - T) and n_touched outputs of the pose-aware fork (reached from
 // utils/slam_frontend.py:1493 / utils/slam_backend.py:184 through gaussian_renderer.render).
 //
-// One CTA per tile, one thread per pixel.  The tile's depth-sorted instance list is streamed in batches of 256:
-// each thread gathers one instance's 40 bytes (xy, conic+opacity, rgb+depth -- three aligned vector loads from the
-// SoA geometry arrays, which are L2-resident) into shared memory, then all threads walk the batch with broadcast
-// shared-memory reads.  FP32 FMA/MUFU bound; no tensor cores (there is no dense contraction on this path).
+// One CTA per tile, one thread per pixel, each WARP owns an 8x4-pixel block of the tile.  The tile's depth-sorted
+// instance list is streamed in batches of 256: each thread gathers one instance's 48 bytes (xy + bounding-box half
+// extents, conic + opacity, rgb + depth -- three 128-bit loads from the SoA geometry arrays, which are
+// L2-resident) into shared memory and tests the instance's {alpha >= 1/255} bounding box against the eight pixel
+// blocks; a ballot per block turns the result into eight 32-bit masks per staging warp.  Each warp then walks only
+// the set bits of ITS block's masks, in list order, so an instance that cannot reach a block costs that warp
+// nothing (the reference evaluates the exponent for all 256 pixels and discards it).  The test is conservative, so
+// every (pixel, Gaussian) pair that passes the reference's two skips is still evaluated and the result is
+// unchanged; n_contrib keeps counting list positions.
+// FP32 FMA/MUFU bound; no tensor cores (there is no dense contraction on this path).
 // n_touched is aggregated per warp with a ballot, and only while some pixel of the warp still has T > 0.5
 // (T only decreases, so the test T*(1-alpha) > 0.5 can never fire afterwards).
 #include "common.cuh"
@@ -13,10 +19,11 @@
 namespace lvdgs {
 
 constexpr int BF_THREADS = TILE_PIX;
+constexpr int BF_WARPS = BF_THREADS / 32;      // 8 warps = 2 x 4 blocks of 8 x 4 pixels
 
 __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H, int gx, const uint2 *__restrict__ ranges,
                                                                    const uint32_t *__restrict__ point_list,
-                                                                   const float2 *__restrict__ means2D,
+                                                                   const float4 *__restrict__ means2D,
                                                                    const float4 *__restrict__ conic_opacity,
                                                                    const float4 *__restrict__ rgbd, const float *__restrict__ bg,
                                                                    float *__restrict__ out_color, float *__restrict__ out_depth,
@@ -26,64 +33,88 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
     __shared__ float2 s_xy[BF_THREADS];
     __shared__ float4 s_co[BF_THREADS];
     __shared__ float4 s_cd[BF_THREADS];
+    __shared__ uint32_t s_mask[BF_WARPS][BF_WARPS];     // [staging warp][pixel block]
 
     const int tile = blockIdx.y * gx + blockIdx.x;
-    const int lx = threadIdx.x & (TILE - 1), ly = threadIdx.x >> 4;
-    const int px = blockIdx.x * TILE + lx, py = blockIdx.y * TILE + ly;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bx = warp & 1, by = warp >> 1;                       // this warp's 8x4 block inside the tile
+    const int px = blockIdx.x * TILE + bx * 8 + (lane & 7);
+    const int py = blockIdx.y * TILE + by * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pfx = (float)px, pfy = (float)py;
-    const int lane = threadIdx.x & 31;
+    const float tx0 = (float)(blockIdx.x * TILE), ty0 = (float)(blockIdx.y * TILE);   // tile's first pixel centre
 
     const uint2 range = ranges[tile];
     int todo = (int)(range.y - range.x);
     bool done = !inside;
     float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
-    uint32_t contributor = 0, last_contributor = 0;
+    uint32_t last_contributor = 0;
+    uint32_t batch_first = 0;                                      // list position of the batch's first entry
     bool warp_hi = true;     // some pixel of this warp may still satisfy T(1-alpha) > 0.5
 
-    for (uint32_t base = range.x; todo > 0; base += BF_THREADS, todo -= BF_THREADS) {
+    for (uint32_t base = range.x; todo > 0; base += BF_THREADS, todo -= BF_THREADS, batch_first += BF_THREADS) {
         if (__syncthreads_count(done) == BF_THREADS) break;
+        uint32_t blocks = 0;                                        // bit (by*2+bx): instance may reach that block
         if ((int)threadIdx.x < todo) {
             const uint32_t id = __ldg(point_list + base + threadIdx.x);
+            const float4 m = __ldg(means2D + id);
             s_id[threadIdx.x] = id;
-            s_xy[threadIdx.x] = __ldg(means2D + id);
+            s_xy[threadIdx.x] = make_float2(m.x, m.y);
             s_co[threadIdx.x] = __ldg(conic_opacity + id);
             s_cd[threadIdx.x] = __ldg(rgbd + id);
+            const float rx = m.x - tx0, ry = m.y - ty0;
+            uint32_t xb = 0, yb = 0;
+            // block column bx spans pixel centres [8bx, 8bx+7]; keep it unless the box [rx-hx, rx+hx] misses it
+            if (!(rx + m.z < 0.f) && !(rx - m.z > 7.f)) xb |= 1u;
+            if (!(rx + m.z < 8.f) && !(rx - m.z > 15.f)) xb |= 2u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (!(ry + m.w < 4.f * q) && !(ry - m.w > 4.f * q + 3.f)) yb |= 1u << q;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (yb & (1u << q)) blocks |= xb << (2 * q);
+        }
+#pragma unroll
+        for (int r = 0; r < BF_WARPS; ++r) {
+            const uint32_t m = __ballot_sync(0xffffffffu, (blocks >> r) & 1u);
+            if (lane == r) s_mask[warp][r] = m;
         }
         __syncthreads();
-        const int nb = min(BF_THREADS, todo);
-        for (int j = 0; j < nb; ++j) {
-            if ((j & 7) == 0) {
-                if (__all_sync(0xffffffffu, done)) break;
-                if (warp_hi) warp_hi = __any_sync(0xffffffffu, !done && T > 0.5f);
-            }
-            bool hit = false;
-            if (!done) {
-                contributor++;
-                const float2 xy = s_xy[j];
-                const float4 co = s_co[j];
-                const float dx = xy.x - pfx, dy = xy.y - pfy;
-                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-                if (power <= 0.f) {
-                    const float alpha = fminf(0.99f, co.w * __expf(power));
-                    if (alpha >= 1.f / 255.f) {
-                        const float test_T = T * (1.f - alpha);
-                        if (test_T < 0.0001f) {
-                            done = true;
-                        } else {
-                            const float4 cd = s_cd[j];
-                            const float wgt = alpha * T;
-                            C0 += cd.x * wgt; C1 += cd.y * wgt; C2 += cd.z * wgt; D += cd.w * wgt;
-                            hit = test_T > 0.5f;
-                            T = test_T;
-                            last_contributor = contributor;
+        for (int wp = 0; wp < BF_WARPS; ++wp) {
+            uint32_t m = s_mask[wp][warp];
+            if (__all_sync(0xffffffffu, done)) break;
+            if (warp_hi) warp_hi = __any_sync(0xffffffffu, !done && T > 0.5f);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int j = wp * 32 + b;
+                bool hit = false;
+                if (!done) {
+                    const float2 xy = s_xy[j];
+                    const float4 co = s_co[j];
+                    const float dx = xy.x - pfx, dy = xy.y - pfy;
+                    const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                    if (power <= 0.f) {
+                        const float alpha = fminf(0.99f, co.w * __expf(power));
+                        if (alpha >= 1.f / 255.f) {
+                            const float test_T = T * (1.f - alpha);
+                            if (test_T < 0.0001f) {
+                                done = true;
+                            } else {
+                                const float4 cd = s_cd[j];
+                                const float wgt = alpha * T;
+                                C0 += cd.x * wgt; C1 += cd.y * wgt; C2 += cd.z * wgt; D += cd.w * wgt;
+                                hit = test_T > 0.5f;
+                                T = test_T;
+                                last_contributor = batch_first + (uint32_t)j + 1u;
+                            }
                         }
                     }
                 }
-            }
-            if (warp_hi) {
-                const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                if (b && lane == 0) atomicAdd(n_touched + s_id[j], __popc(b));
+                if (warp_hi) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                    if (bal && lane == 0) atomicAdd(n_touched + s_id[j], __popc(bal));
+                }
             }
         }
     }

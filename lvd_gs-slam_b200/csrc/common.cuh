@@ -68,7 +68,7 @@ static inline int tile_bits(uint32_t n) {
 
 // ---- kernel launchers (one per .cu) ----
 struct GeomPtrs {
-    float *depths; float2 *means2D; float4 *conic_opacity; float4 *rgbd; short4 *rect;
+    float *depths; float4 *means2D; float4 *conic_opacity; float4 *rgbd; short4 *rect;
     uint32_t *tiles_touched; uint32_t *point_offsets; uint8_t *clamped;
 };
 struct BinPtrs {
@@ -84,13 +84,14 @@ int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D
                               const float *campos, int32_t *radii, const GeomPtrs &g, cudaStream_t s);
 int launch_scan_tiles(int P, const uint32_t *tiles_touched, uint32_t *point_offsets, uint32_t *block_sums,
                       cudaStream_t s);
-int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, const int32_t *radii, uint64_t *keys, uint32_t *vals,
+int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, int64_t capacity, uint64_t *keys, uint32_t *vals,
                      cudaStream_t s);
-int launch_tile_ranges(int64_t R, int num_tiles, const uint64_t *keys_sorted, uint2 *ranges, cudaStream_t s);
+int launch_tile_ranges(int64_t capacity, const uint32_t *n_dev, int num_tiles, const uint64_t *keys_sorted, uint2 *ranges,
+                       cudaStream_t s);
 
 size_t sort_workspace_bytes(int64_t n);
-int launch_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1, int end_bit,
-                      void *ws, size_t ws_bytes, int *selector, cudaStream_t s);
+int launch_sort_pairs(int64_t n, const uint32_t *n_dev, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
+                      uint32_t *vals1, int end_bit, void *ws, size_t ws_bytes, int *selector, cudaStream_t s);
 
 int launch_blend_forward(int W, int H, const uint2 *ranges, const uint32_t *point_list, const GeomPtrs &g,
                          const float *bg, float *out_color, float *out_depth, float *out_opacity,
@@ -98,9 +99,12 @@ int launch_blend_forward(int W, int H, const uint2 *ranges, const uint32_t *poin
 
 // Per-Gaussian accumulators produced by the blend backward: one 48-byte row per Gaussian so that a warp can
 // commit its partial sums with three 128-bit vector reductions (red.global.add.v4.f32).
-//   [0] dL_dmean2D.x  [1] dL_dmean2D.y  (NDC units)   [2] dL_dconic.xx  [3] dL_dconic.xy
-//   [4] dL_dconic.yy  [5] dL_dopacity   [6] dL_ddepth [7] -
-//   [8..10] dL_dcolor rgb               [11] -
+// The geometric slots are the moments of m = G * dL/dalpha over the Gaussian's pixels (d = mean2D - pixel):
+//   [0] S_x = sum m dx   [1] S_y = sum m dy   [2] S_xx = sum m dx^2   [3] S_xy = sum m dx dy
+//   [4] S_yy = sum m dy^2   [5] S_0 = sum m (= dL_dopacity)   [6] dL_ddepth   [7] -
+//   [8..10] dL_dcolor rgb   [11] -
+// from which the preprocess backward forms, with (A,B,C,o) = conic_opacity:
+//   dL_dmean2D = -o (A S_x + B S_y, B S_x + C S_y) * (W/2, H/2),  dL_dconic = -o/2 (S_xx, S_xy, S_yy).
 constexpr int ACC_STRIDE = 12;
 struct BlendGradPtrs {
     float *acc;          // [P][ACC_STRIDE], zeroed by the API before the blend backward

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(const P
     int32_t radius = 0;
     uint32_t touched = 0;
     float depth = 0.f;
-    float2 pix = make_float2(0.f, 0.f);
+    float4 pix = make_float4(0.f, 0.f, -1e30f, -1e30f);
     float4 con_o = make_float4(0.f, 0.f, 0.f, 0.f);
     float3 rgb = make_float3(0.f, 0.f, 0.f);
     short4 rect = make_short4(0, 0, 0, 0);
@@ -220,9 +220,17 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(const P
                 }
                 depth = tz;
                 radius = irad;
-                pix = make_float2(pix_x, pix_y);
-                con_o = make_float4(__fmul_rn(cov.z, det_inv), __fmul_rn(-cov.y, det_inv), __fmul_rn(cov.x, det_inv),
-                                    __ldg(a.opacities + i));
+                const float opac = __ldg(a.opacities + i);
+                // Half extents of the axis-aligned box around {alpha >= 1/255} = {d^T conic d <= 2 ln(255 o)}: the blend
+                // kernels use it to drop (pixel block, Gaussian) pairs that upstream would evaluate and then skip.
+                // Conservative (1% + 0.02 slack on the level, so float noise in `power` can never flip a decision);
+                // o <= 1/255 gives a negative level -> extents stay -1e30 and the Gaussian is never evaluated.
+                const float lvl = 2.02f * __logf(255.f * opac) + 0.02f;
+                float hx = -1e30f, hy = -1e30f;
+                if (lvl > 0.f) { hx = sqrtf(lvl * cov.x) * 1.0001f + 0.01f; hy = sqrtf(lvl * cov.z) * 1.0001f + 0.01f; }
+                if (!(opac == opac) || !(lvl == lvl)) { hx = 1e30f; hy = 1e30f; }   // NaN inputs: never cull
+                pix = make_float4(pix_x, pix_y, hx, hy);
+                con_o = make_float4(__fmul_rn(cov.z, det_inv), __fmul_rn(-cov.y, det_inv), __fmul_rn(cov.x, det_inv), opac);
                 rect = make_short4((short)rminx, (short)rminy, (short)rmaxx, (short)rmaxy);
                 touched = (uint32_t)area;
             }
@@ -367,7 +375,7 @@ int launch_scan_tiles(int P, const uint32_t *tiles_touched, uint32_t *point_offs
 // ---------------------------------------------------------------------------------------------------------
 constexpr int EMIT_THREADS = 256;
 
-__global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, const uint32_t *__restrict__ offsets,
+__global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, uint32_t capacity, const uint32_t *__restrict__ offsets,
                                                                  const short4 *__restrict__ rects,
                                                                  const float *__restrict__ depths,
                                                                  uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
@@ -386,7 +394,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
     }
     __syncthreads();
     const int last = min(EMIT_THREADS, P - g0) - 1;
-    const uint32_t span_end = s_end[last];
+    const uint32_t span_end = min(s_end[last], capacity);      // never write past the arena the launch was sized for
     for (uint32_t r = span_begin + threadIdx.x; r < span_end; r += EMIT_THREADS) {
         // smallest j with s_end[j] > r
         int lo = 0, hi = last;
@@ -405,12 +413,12 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
     }
 }
 
-int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, const int32_t *radii, uint64_t *keys, uint32_t *vals,
+int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, int64_t capacity, uint64_t *keys, uint32_t *vals,
                      cudaStream_t s) {
-    (void)radii; (void)H;
+    (void)H;
     const int gx = (W + TILE - 1) / TILE;
     LVDGS_PRE(s);
-    emit_keys_kernel<<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, g.point_offsets, g.rect, g.depths, keys, vals);
+    emit_keys_kernel<<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, (uint32_t)min(capacity, (int64_t)0xffffffffll), g.point_offsets, g.rect, g.depths, keys, vals);
     LVDGS_LAUNCHED(s, "emit_keys");
     return 0;
 }
@@ -418,8 +426,9 @@ int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, const int32_t *radi
 // ---------------------------------------------------------------------------------------------------------
 // K5: tile ranges from the sorted keys.  `ranges` must be zeroed by the caller (untouched tiles stay (0,0)).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t R, const uint64_t *__restrict__ keys,
-                                                          uint2 *__restrict__ ranges) {
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t capacity, const uint32_t *__restrict__ n_dev,
+                                                          const uint64_t *__restrict__ keys, uint2 *__restrict__ ranges) {
+    const int64_t R = n_dev ? min((int64_t)__ldg(n_dev), capacity) : capacity;
     const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (r >= R) return;
     const uint32_t t = (uint32_t)(keys[r] >> 32);
@@ -431,11 +440,13 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t R, const uint6
     if (r == R - 1) ranges[t].y = (uint32_t)R;
 }
 
-int launch_tile_ranges(int64_t R, int num_tiles, const uint64_t *keys_sorted, uint2 *ranges, cudaStream_t s) {
+int launch_tile_ranges(int64_t capacity, const uint32_t *n_dev, int num_tiles, const uint64_t *keys_sorted, uint2 *ranges,
+                       cudaStream_t s) {
+    const int64_t R = capacity;
     LVDGS_CHECK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, s));
     if (R > 0) {
         LVDGS_PRE(s);
-        tile_ranges_kernel<<<ceil_div(R, 256), 256, 0, s>>>(R, keys_sorted, ranges);
+        tile_ranges_kernel<<<ceil_div(R, 256), 256, 0, s>>>(R, n_dev, keys_sorted, ranges);
         LVDGS_LAUNCHED(s, "tile_ranges");
     }
     return 0;

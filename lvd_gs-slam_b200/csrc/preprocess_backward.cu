@@ -24,6 +24,7 @@ struct PbArgs {
     const float *means3D, *shs, *scales, *rotations, *cov3D_precomp, *view, *proj, *proj_raw, *campos;
     const int32_t *radii;
     const uint8_t *clamped;
+    const float4 *conic_opacity;
     const float *acc;
     float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drots,
         *dL_dtau, *dL_dtau_sum;
@@ -57,8 +58,19 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
     const bool live = i < a.P && a.radii[i] > 0;
     if (i < a.P) {
+        // moments of the blend backward -> dL_dmean2D (NDC units), dL_dconic, dL_dopacity (see ACC_STRIDE, common.cuh)
         const float4 *row = reinterpret_cast<const float4 *>(a.acc + (size_t)i * ACC_STRIDE);
-        r0 = row[0]; r1 = row[1]; r2 = row[2];
+        const float4 m0 = row[0], m1 = row[1];
+        r2 = row[2];
+        const float4 co = a.conic_opacity[i];
+        const float o = co.w;
+        r0.x = -0.5f * (float)a.W * o * (co.x * m0.x + co.y * m0.y);
+        r0.y = -0.5f * (float)a.H * o * (co.y * m0.x + co.z * m0.y);
+        r0.z = -0.5f * o * m0.z;       // dL_dconic xx
+        r0.w = -0.5f * o * m0.w;       // dL_dconic xy
+        r1.x = -0.5f * o * m1.x;       // dL_dconic yy
+        r1.y = m1.y;                   // dL_dopacity
+        r1.z = m1.z;                   // dL_ddepth
     }
     if (live) {
         const float x = a.means3D[3 * (size_t)i], y = a.means3D[3 * (size_t)i + 1], z = a.means3D[3 * (size_t)i + 2];
@@ -337,7 +349,7 @@ int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3
     a.mod = p.scale_modifier;
     a.means3D = means3D; a.shs = colors_are_precomp ? nullptr : shs; a.scales = scales; a.rotations = rotations;
     a.cov3D_precomp = cov3D_precomp; a.view = view; a.proj = proj; a.proj_raw = proj_raw; a.campos = campos;
-    a.radii = radii; a.clamped = g.clamped; a.acc = bgp.acc;
+    a.radii = radii; a.clamped = g.clamped; a.conic_opacity = g.conic_opacity; a.acc = bgp.acc;
     a.dL_dmeans2D = dL_dmeans2D; a.dL_dcolors = dL_dcolors; a.dL_dopacity = dL_dopacity; a.dL_dmeans3D = dL_dmeans3D;
     a.dL_dcov3D = dL_dcov3D; a.dL_dsh = colors_are_precomp ? nullptr : dL_dsh; a.dL_dscales = dL_dscales;
     a.dL_drots = dL_drots; a.dL_dtau = dL_dtau; a.dL_dtau_sum = dL_dtau_sum;

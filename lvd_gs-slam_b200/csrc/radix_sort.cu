@@ -38,8 +38,16 @@ __device__ __forceinline__ uint32_t digit_of(uint64_t key, int shift, uint32_t m
 }
 
 // ---- histogram of every digit position in one read of the keys ----
-__global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const uint64_t *__restrict__ keys, int64_t n, int passes,
+// `n_dev` (optional): device-side element count, clamped to the capacity `n` the launch was sized for -- lets the
+// forward launch the sort before the host has read the instance count back.
+__device__ __forceinline__ int64_t rs_count(int64_t n_cap, const uint32_t *n_dev) {
+    return n_dev ? min((int64_t)__ldg(n_dev), n_cap) : n_cap;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const uint64_t *__restrict__ keys, int64_t n_cap,
+                                                                  const uint32_t *__restrict__ n_dev, int passes,
                                                                   int end_bit, SortWs *ws) {
+    const int64_t n = rs_count(n_cap, n_dev);
     __shared__ uint32_t h[RS_MAX_PASSES * RS_BINS];
     for (int k = threadIdx.x; k < passes * RS_BINS; k += RS_THREADS) h[k] = 0;
     __syncthreads();
@@ -108,8 +116,9 @@ struct __align__(16) RsSmem {
 
 __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                                                                  const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
-                                                                 int64_t n, int shift, int nbits, int pass, SortWs *ws,
-                                                                 uint32_t *lookback) {
+                                                                 int64_t n_cap, const uint32_t *__restrict__ n_dev, int shift,
+                                                                 int nbits, int pass, SortWs *ws, uint32_t *lookback) {
+    const int64_t n = rs_count(n_cap, n_dev);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmem &sm = *reinterpret_cast<RsSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -120,6 +129,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
     __syncthreads();
     const uint32_t tile = sm.tile;
     const int64_t tile_base = (int64_t)tile * RS_TILE;
+    if (tile_base >= n) return;          // launch was sized for the capacity; tiles past the real count retire at once
     const int n_valid = (int)min((int64_t)RS_TILE, n - tile_base);
 
     // ---- load (warp-striped: item k of lane l in warp w is element w*512 + k*32 + l of the tile) ----
@@ -209,8 +219,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
     }
 }
 
-int launch_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1, int end_bit,
-                      void *ws_raw, size_t ws_bytes, int *selector, cudaStream_t s) {
+int launch_sort_pairs(int64_t n, const uint32_t *n_dev, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
+                      uint32_t *vals1, int end_bit, void *ws_raw, size_t ws_bytes, int *selector, cudaStream_t s) {
     if (selector) *selector = 0;
     if (n <= 0) return 0;
     if (end_bit < 1 || end_bit > 64) { set_error("sort: end_bit %d out of range", end_bit); return 1; }
@@ -229,7 +239,7 @@ int launch_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *val
     }
     const int hist_blocks = (int)min((int64_t)148 * 8, (n + RS_THREADS * 8 - 1) / (RS_THREADS * 8));
     LVDGS_PRE(s);
-    rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, s>>>(keys0, n, passes, end_bit, ws);
+    rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, s>>>(keys0, n, n_dev, passes, end_bit, ws);
     LVDGS_LAUNCHED(s, "sort_histogram");
     LVDGS_PRE(s);
     rs_scan_hist_kernel<<<passes, RS_BINS, 0, s>>>(ws);
@@ -239,7 +249,7 @@ int launch_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *val
     for (int p = 0; p < passes; ++p) {
         const int shift = p * 8, nb = min(8, end_bit - shift);
         LVDGS_PRE(s);
-        rs_onesweep_kernel<<<ntiles, RS_THREADS, sizeof(RsSmem), s>>>(kin, kout, vin, vout, n, shift, nb, p, ws,
+        rs_onesweep_kernel<<<ntiles, RS_THREADS, sizeof(RsSmem), s>>>(kin, kout, vin, vout, n, n_dev, shift, nb, p, ws,
                                                                       reinterpret_cast<uint32_t *>(lb_base + lb_stride * p));
         LVDGS_LAUNCHED(s, "sort_onesweep");
         uint64_t *tk = kin; kin = kout; kout = tk;

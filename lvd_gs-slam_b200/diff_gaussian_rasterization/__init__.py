@@ -26,6 +26,12 @@ from lvdgs import _native
 # Set LVDGS_FLAGS=1|2 (or assign module attribute FLAGS) to use the true derivatives instead.
 FLAGS = int(os.environ.get("LVDGS_FLAGS", "0"))
 
+# Speculative-launch capacity hints (include/lvdgs.h: lvdgs_rasterize_forward): per device, the next forward sizes its
+# binning buffer for 1.25x the largest instance count seen recently, so the device never idles while the host reads R.
+# LVDGS_SPECULATIVE=0 restores upstream's read-R-then-launch order.
+SPECULATIVE = os.environ.get("LVDGS_SPECULATIVE", "1") != "0"
+_capacity_hint = {}
+
 
 class GaussianRasterizationSettings(NamedTuple):
     image_height: int
@@ -54,21 +60,17 @@ def _prep(t, device=None):
     return t
 
 
-class _Buffers:
-    """The three opaque buffers of the C ABI, grown on request by the library's resize callback."""
+def _make_resizer(device, store):
+    """ctypes resize callback for the three opaque buffers of the C ABI.  `store` (a plain dict: which -> uint8 tensor)
+    is what the autograd ctx keeps alive; the callback object itself is dropped right after the forward call, so no
+    reference cycle delays the release of the buffers (they are tens of MB each)."""
 
-    def __init__(self, device):
-        self.device = device
-        self.t = {}
-        self.cb = _native.RESIZE_FN(self._resize)
-
-    def _resize(self, _user, which, nbytes):
-        buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
-        self.t[int(which)] = buf
+    def _resize(_user, which, nbytes):
+        buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+        store[int(which)] = buf
         return buf.data_ptr()
 
-    def get(self, which):
-        return self.t.get(which)
+    return _native.RESIZE_FN(_resize)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta,
@@ -106,19 +108,26 @@ class _RasterizeGaussians(torch.autograd.Function):
         opac_img = torch.empty(1, H, W, dtype=torch.float32, device=dev)
         radii = torch.empty(P, dtype=torch.int32, device=dev)
         n_touched = torch.empty(P, dtype=torch.int32, device=dev)
-        bufs = _Buffers(dev)
+        bufs = {}
+        resize_cb = _make_resizer(dev, bufs)
         prm = _params(rs, P, M)
         R = C.c_int64(0)
+        cap = C.c_int64(0)
+        hint = _capacity_hint.get(dev.index, 0) if SPECULATIVE else 0
         if dev.index is not None:
             L.lvdgs_set_device(dev.index)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         p = _native.ptr
         rc = L.lvdgs_rasterize_forward(C.byref(prm), p(bg), p(m3), p(cp), p(op), p(sc), p(rot), p(cov), p(view), p(proj),
-                                       p(praw), p(shs), p(campos), bufs.cb, None, p(color), p(radii), p(depth),
-                                       p(opac_img), p(n_touched), C.byref(R), stream)
+                                       p(praw), p(shs), p(campos), resize_cb, None, C.c_int64(hint), p(color), p(radii),
+                                       p(depth), p(opac_img), p(n_touched), C.byref(R), C.byref(cap), stream)
+        del resize_cb
         _native.check(rc, "lvdgs_rasterize_forward")
         ctx.rs = rs
         ctx.num_rendered = int(R.value)
+        ctx.capacity = int(cap.value)
+        if SPECULATIVE:   # decay slowly, grow at once
+            _capacity_hint[dev.index] = max(int(R.value * 1.25) + 65536, int(hint * 0.98))
         ctx.bufs = bufs
         ctx.shapes = (P, M)
         ctx.aux = (bg, view, proj, praw, campos)
@@ -154,7 +163,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         b = ctx.bufs
         rc = L.lvdgs_rasterize_backward(C.byref(prm), p(bg), p(m3), p(radii), p(cp), p(op), p(sc), p(rot), p(cov), p(view),
                                         p(proj), p(praw), p(gc), p(gd), p(go), p(shs), p(campos), p(b.get(0)),
-                                        C.c_int64(ctx.num_rendered), p(b.get(1)), p(b.get(2)), p(scratch),
+                                        C.c_int64(ctx.num_rendered), C.c_int64(ctx.capacity), p(b.get(1)), p(b.get(2)),
+                                        p(scratch),
                                         C.c_size_t(scratch.numel()), p(g_means2D), p(g_colors), p(g_opac), p(g_means3D),
                                         p(g_cov), p(g_sh), p(g_sc), p(g_rot), None, p(g_tau), stream)
         _native.check(rc, "lvdgs_rasterize_backward")

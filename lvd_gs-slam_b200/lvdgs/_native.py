@@ -124,11 +124,11 @@ def lib():
     L.lvdgs_get_geom_layout.argtypes = [i32, C.POINTER(GeomLayout)]
     L.lvdgs_get_binning_layout.argtypes = [i64, C.POINTER(BinningLayout)]
     L.lvdgs_get_img_layout.argtypes = [i32, i32, C.POINTER(ImgLayout)]
-    L.lvdgs_rasterize_forward.argtypes = [C.POINTER(RasterParams)] + [vp] * 12 + [RESIZE_FN, vp] + [vp] * 5 + \
-                                         [C.POINTER(i64), vp]
+    L.lvdgs_rasterize_forward.argtypes = [C.POINTER(RasterParams)] + [vp] * 12 + [RESIZE_FN, vp, i64] + [vp] * 5 + \
+                                         [C.POINTER(i64), C.POINTER(i64), vp]
     L.lvdgs_backward_scratch_bytes.argtypes = [i32, i64]
     L.lvdgs_backward_scratch_bytes.restype = sz
-    L.lvdgs_rasterize_backward.argtypes = [C.POINTER(RasterParams)] + [vp] * 17 + [i64, vp, vp, vp, sz] + [vp] * 11
+    L.lvdgs_rasterize_backward.argtypes = [C.POINTER(RasterParams)] + [vp] * 17 + [i64, i64, vp, vp, vp, sz] + [vp] * 11
     L.lvdgs_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
     L.lvdgs_dist2_workspace_bytes.argtypes = [i32]
     L.lvdgs_dist2_workspace_bytes.restype = sz
@@ -153,7 +153,7 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def debug_views(bufs, P: int, R: int, W: int, H: int):
+def debug_views(bufs, P: int, R: int, W: int, H: int, capacity=None):
     """numpy copies of the arrays inside the three opaque buffers (parity tests / debugging only).
 
     `bufs` maps LVDGS_BUF_{GEOM,BINNING,IMG} -> torch uint8 tensor as handed out by the resize callback."""
@@ -167,12 +167,14 @@ def debug_views(bufs, P: int, R: int, W: int, H: int):
 
     gl, bl, il = GeomLayout(), BinningLayout(), ImgLayout()
     L.lvdgs_get_geom_layout(P, C.byref(gl))
-    L.lvdgs_get_binning_layout(R, C.byref(bl))
+    L.lvdgs_get_binning_layout(capacity if capacity is not None else R, C.byref(bl))
     L.lvdgs_get_img_layout(W, H, C.byref(il))
     g = bufs.get(0)
     if g is not None and P > 0:
         out["depths"] = grab(g, gl.depths, 4 * P, np.float32, (P,))
-        out["means2D"] = grab(g, gl.means2D, 8 * P, np.float32, (P, 2))
+        m4 = grab(g, gl.means2D, 16 * P, np.float32, (P, 4))
+        out["means2D"] = np.ascontiguousarray(m4[:, :2])
+        out["extent"] = np.ascontiguousarray(m4[:, 2:])
         out["conic_opacity"] = grab(g, gl.conic_opacity, 16 * P, np.float32, (P, 4))
         out["rgbd"] = grab(g, gl.rgbd, 16 * P, np.float32, (P, 4))
         out["rect"] = grab(g, gl.rect, 8 * P, np.int16, (P, 4)).astype(np.int32)

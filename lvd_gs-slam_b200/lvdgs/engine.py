@@ -69,7 +69,8 @@ class RasterEngine:
         self.g_cov = torch.zeros(P, 6, **f32)
         self.g_tau = torch.empty(6, **f32)
         self.R = 0
-        self._prm = None
+        self.capacity = 0            # instances the binning arena was last laid out for
+        self.hint = 0                # speculative-launch capacity hint for the next forward
         if self.dev.index is not None:
             self.L.lvdgs_set_device(self.dev.index)
 
@@ -90,14 +91,17 @@ class RasterEngine:
 
     def forward(self, vc: ViewCamera, means3D, opacities, scales, rotations, shs):
         R = C.c_int64(0)
+        cap = C.c_int64(0)
         prm = self._params(vc, self.flags)
         rc = self.L.lvdgs_rasterize_forward(C.byref(prm), ptr(vc.bg), ptr(means3D), None, ptr(opacities), ptr(scales),
                                             ptr(rotations), None, ptr(vc.view), ptr(vc.proj), ptr(vc.proj_raw), ptr(shs),
-                                            ptr(vc.campos), self._cb, None, ptr(self.color), ptr(self.radii),
-                                            ptr(self.depth), ptr(self.opacity), ptr(self.n_touched), C.byref(R),
-                                            self.stream())
+                                            ptr(vc.campos), self._cb, None, C.c_int64(self.hint), ptr(self.color),
+                                            ptr(self.radii), ptr(self.depth), ptr(self.opacity), ptr(self.n_touched),
+                                            C.byref(R), C.byref(cap), self.stream())
         _native.check(rc, "lvdgs_rasterize_forward")
         self.R = int(R.value)
+        self.capacity = int(cap.value)
+        self.hint = max(int(self.R * 1.25) + 65536, int(self.hint * 0.98))
         return self.R
 
     def backward(self, vc: ViewCamera, means3D, opacities, scales, rotations, shs, dL_dcolor, dL_ddepth=None,
@@ -108,7 +112,8 @@ class RasterEngine:
         rc = self.L.lvdgs_rasterize_backward(
             C.byref(prm), ptr(vc.bg), ptr(means3D), ptr(self.radii), None, ptr(opacities), ptr(scales), ptr(rotations),
             None, ptr(vc.view), ptr(vc.proj), ptr(vc.proj_raw), ptr(dL_dcolor), ptr(dL_ddepth), ptr(dL_dopacity), ptr(shs),
-            ptr(vc.campos), ptr(self.arena[0]), C.c_int64(self.R), ptr(self.arena[1]), ptr(self.arena[2]),
+            ptr(vc.campos), ptr(self.arena[0]), C.c_int64(self.R), C.c_int64(self.capacity), ptr(self.arena[1]),
+            ptr(self.arena[2]),
             ptr(self.scratch), C.c_size_t(self.scratch.numel()), ptr(self.g_means2D), ptr(self.g_colors), ptr(g["opacity"]),
             ptr(g["means3D"]), ptr(self.g_cov), ptr(g["shs"]), ptr(g["scales"]), ptr(g["rotations"]), None,
             ptr(self.g_tau), self.stream())

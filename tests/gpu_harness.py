@@ -48,7 +48,8 @@ def run_cuda(sc, cam, bg, grads=None, device="cuda", use_precomp_color=False, us
     R = color.grad_fn.num_rendered if hasattr(color.grad_fn, "num_rendered") else None
     internals = None
     if ctx_bufs is not None:
-        internals = _native.debug_views(ctx_bufs, means3D.shape[0], R, cam.image_width, cam.image_height)
+        internals = _native.debug_views(ctx_bufs, means3D.shape[0], R, cam.image_width, cam.image_height,
+                                        capacity=color.grad_fn.capacity)
         internals["R"] = R
     g = None
     if grads is not None:
