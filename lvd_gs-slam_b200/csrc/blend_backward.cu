@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     const float tx0 = (float)(blockIdx.x * TILE), ty0 = (float)(blockIdx.y * TILE);
     const size_t HW = (size_t)H * W;
     const uint2 range = ranges[tile];
+    const uint32_t a_id = smem_u32(s_id), a_xy = smem_u32(s_xy), a_q = smem_u32(s_co), a_cd = smem_u32(s_cd);
 
     // per-pixel state (q = 0: row py0, q = 1: row py0 + 4)
     float pfy[2], T[2], Tf[2], dp0[2], dp1[2], dp2[2], dpd[2], bgd[2], B0[2], B1[2], B2[2], Bd[2];
@@ -126,7 +127,8 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
             const float4 m = __ldg(means2D + id);
             s_id[threadIdx.x] = id;
             s_xy[threadIdx.x] = make_float2(m.x, m.y);
-            s_co[threadIdx.x] = __ldg(conic_opacity + id);
+            const float4 co = __ldg(conic_opacity + id);
+            s_co[threadIdx.x] = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);   // as forward
             s_cd[threadIdx.x] = __ldg(rgbd + id);
             const float rx = m.x - tx0, ry = m.y - ty0;
             uint32_t xb = 0, yb = 0;
@@ -151,9 +153,9 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 const int j = wp * 32 + b;
                 const uint32_t k = (uint32_t)(remaining - 1 - j);    // contributor index (0-based) of this entry
                 if (k >= wtop) continue;                             // warp-uniform
-                const float2 xy = s_xy[j];
-                const float4 co = s_co[j];
-                const float4 cd = s_cd[j];
+                const float2 xy = lds64(a_xy + j * 8);
+                const float4 co = lds128(a_q + j * 16);
+                const float4 cd = lds128(a_cd + j * 16);
                 const float dx = xy.x - pfx;
                 float v[16];
 #pragma unroll
@@ -163,9 +165,9 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 for (int q = 0; q < 2; ++q) {
                     if (k < last[q]) {
                         const float dy = xy.y - pfy[q];
-                        const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-                        if (power <= 0.f) {
-                            const float G = __expf(power);
+                        const float p2 = fmaf(co.z * dy, dy, dx * fmaf(co.x, dx, co.y * dy));
+                        if (p2 <= 0.f) {
+                            const float G = ex2_approx(p2);
                             const float alpha = fminf(0.99f, co.w * G);
                             if (alpha >= 1.f / 255.f) {
                                 valid = true;
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 }
                 if (__any_sync(0xffffffffu, valid)) {
                     transpose_reduce16(v, lane);
-                    if (commits) atomicAdd(acc + (size_t)s_id[j] * ACC_STRIDE + slot, v[0]);
+                    if (commits) atomicAdd(acc + (size_t)lds32(a_id + j * 4) * ACC_STRIDE + slot, v[0]);
                 }
             }
         }

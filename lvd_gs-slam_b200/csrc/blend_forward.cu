@@ -41,7 +41,9 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
     const int px = blockIdx.x * TILE + bx * 8 + (lane & 7);
     const int py = blockIdx.y * TILE + by * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
-    const float pfx = (float)px, pfy = (float)py;
+    float pfx = inside ? (float)px : PIX_PARKED;                   // parked pixels see alpha = 0 for every Gaussian
+    const float pfy = (float)py;
+    const uint32_t a_id = smem_u32(s_id), a_xy = smem_u32(s_xy), a_q = smem_u32(s_co), a_cd = smem_u32(s_cd);
     const float tx0 = (float)(blockIdx.x * TILE), ty0 = (float)(blockIdx.y * TILE);   // tile's first pixel centre
 
     const uint2 range = ranges[tile];
@@ -60,7 +62,9 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
             const float4 m = __ldg(means2D + id);
             s_id[threadIdx.x] = id;
             s_xy[threadIdx.x] = make_float2(m.x, m.y);
-            s_co[threadIdx.x] = __ldg(conic_opacity + id);
+            const float4 co = __ldg(conic_opacity + id);
+            // exponent in base 2 with the -1/2 folded in: p2 = A' dx^2 + B' dx dy + C' dy^2, alpha = o 2^p2
+            s_co[threadIdx.x] = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);
             s_cd[threadIdx.x] = __ldg(rgbd + id);
             const float rx = m.x - tx0, ry = m.y - ty0;
             uint32_t xb = 0, yb = 0;
@@ -89,21 +93,22 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
                 m &= m - 1;
                 const int j = wp * 32 + b;
                 bool hit = false;
-                if (!done) {
-                    const float2 xy = s_xy[j];
-                    const float4 co = s_co[j];
+                {
+                    const float2 xy = lds64(a_xy + j * 8);
+                    const float4 q = lds128(a_q + j * 16);
                     const float dx = xy.x - pfx, dy = xy.y - pfy;
-                    const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-                    if (power <= 0.f) {
-                        const float alpha = fminf(0.99f, co.w * __expf(power));
+                    const float p2 = fmaf(q.z * dy, dy, dx * fmaf(q.x, dx, q.y * dy));
+                    if (p2 <= 0.f) {
+                        const float alpha = fminf(0.99f, q.w * ex2_approx(p2));
                         if (alpha >= 1.f / 255.f) {
                             const float test_T = T * (1.f - alpha);
                             if (test_T < 0.0001f) {
                                 done = true;
+                                pfx = PIX_PARKED;
                             } else {
-                                const float4 cd = s_cd[j];
+                                const float4 cd = lds128(a_cd + j * 16);
                                 const float wgt = alpha * T;
-                                C0 += cd.x * wgt; C1 += cd.y * wgt; C2 += cd.z * wgt; D += cd.w * wgt;
+                                C0 = fmaf(cd.x, wgt, C0); C1 = fmaf(cd.y, wgt, C1); C2 = fmaf(cd.z, wgt, C2); D = fmaf(cd.w, wgt, D);
                                 hit = test_T > 0.5f;
                                 T = test_T;
                                 last_contributor = batch_first + (uint32_t)j + 1u;
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
                 }
                 if (warp_hi) {
                     const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                    if (bal && lane == 0) atomicAdd(n_touched + s_id[j], __popc(bal));
+                    if (bal && lane == 0) atomicAdd(n_touched + lds32(a_id + j * 4), __popc(bal));
                 }
             }
         }

@@ -49,6 +49,39 @@ __device__ __forceinline__ float dot3c(float a0, float b0, float a1, float b1, f
     return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
 }
 
+// ---- shared-memory loads through 32-bit shared-window addresses: one IMAD + LDS in the blend hot loops (indexing a
+// __shared__ array from divergent code makes nvcc 12.9 rebuild the cluster-window base, S2R CgaCtaId + LEA, per access)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    uint32_t a;   // volatile: computed once where written, never rematerialised inside the loops
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+    return a;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+// 2^x on the MUFU pipe (flushes to zero below 2^-126, which the alpha >= 1/255 test discards anyway)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float LOG2E = 1.4426950408889634f;
+// pixel x coordinate assigned to a finished / out-of-image pixel: every Gaussian then evaluates to alpha = 0, so the
+// hot loop needs no per-pixel "done" test (dx^2 ~ 1e36 stays finite in float)
+constexpr float PIX_PARKED = 1.0e18f;
+
 struct CameraConst {   // staged once per block in shared memory
     float view[16];
     float proj[16];
