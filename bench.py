@@ -3,7 +3,8 @@
 
 Workload (`config.workload` = "kitti_window8_500k"): one STEP = forward + backward of the 8 keyframe views of a
 mapping window (1241x376 each, SURVEY.md section 8d cameras k=0..7) against a replicated map of 500 000 synthetic
-Gaussians, parameter gradients summed over the views (the mapping loss is a sum, utils/slam_backend.py:266,300).
+Gaussians, parameter gradients summed over the views (the mapping loss is a sum, utils/slam_backend.py:266,300),
+followed by the Adam update of the map (utils/slam_backend.py:378-380).
 metric = fwd+bwd render Mpix/s = 8*H*W / step time.  At N GPUs the 8 views are sharded over the ranks
 (8/N each) and the [P,14] parameter-gradient block is SUM-allreduced over NCCL at the end of the step
 (strong scaling: the window is fixed).
@@ -145,6 +146,7 @@ def main():
     import torch.distributed as dist
     from lvdgs import synth, _native
     from lvdgs.engine import RasterEngine, ViewCamera
+    from lvdgs.mapping import ShardedMapper
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -159,9 +161,14 @@ def main():
     cams = [synth.make_camera(wl["cam"], k) for k in range(wl["views"])]
     my_views = list(range(rank, wl["views"], world))          # keyframe k -> rank k mod world
     sc = synth.make_scene(wl["N"], cams[0], seed=0)            # identical replicated map on every rank
-    H, W, P = cams[0].image_height, cams[0].image_width, wl["N"]
+    H, W = cams[0].image_height, cams[0].image_width
     t = lambda a: torch.tensor(a, dtype=torch.float32, device=dev).contiguous()
-    means3D, opac, scales, rots, shs = t(sc["means3D"]), t(sc["opacities"]), t(sc["scales"]), t(sc["rotations"]), t(sc["shs"])
+    # the replicated map lives in ONE flat parameter block (lvdgs.mapping.ShardedMapper) updated by the fused Adam kernel;
+    # learning rates are scaled down 1e-4 so that the synthetic workload stays stationary over the timed steps
+    base_lr = {"means3D": 1.6e-4, "shs": 2.5e-3, "opacity": 5e-2, "scales": 1e-3, "rotations": 1e-3}
+    mapper = ShardedMapper(P := wl["N"], sh_coeffs=1, device=dev, lrs={k: v * 1e-4 for k, v in base_lr.items()})
+    mapper.load(means3D=sc["means3D"], shs=sc["shs"], opacity=sc["opacities"], scales=sc["scales"], rotations=sc["rotations"])
+    means3D, opac, scales, rots, shs = (mapper.view(k) for k in ("means3D", "opacity", "scales", "rotations", "shs"))
     gc_np, gd_np = synth.make_upstream_grads(cams[0])
     gc, gd = t(gc_np), t(gd_np)
     vcs = {k: ViewCamera(cams[k], dev) for k in my_views}
@@ -178,8 +185,8 @@ def main():
         for k in my_views:
             eng.forward(vcs[k], means3D, opac, scales, rots, shs)
             eng.backward(vcs[k], means3D, opac, scales, rots, shs, gc, gd, accumulate=True)
-        if world > 1:
-            dist.all_reduce(eng.grad_flat)                      # SUM over keyframe shards (NCCL / NVLink)
+        mapper.reduce_gradients(eng.grad_flat)                 # SUM over keyframe shards (NCCL / NVLink); no-op at N=1
+        mapper.adam_step(eng.grad_flat)                        # identical fused Adam update on every rank
 
     for _ in range(args.warmup):
         step_resident()
@@ -205,7 +212,8 @@ def main():
 
     # ---------------- e2e: plugin surface, host buffers ----------------
     import diff_gaussian_rasterization as dgr
-    params = [x.clone().requires_grad_() for x in (means3D, opac, scales, rots, shs)]
+    params = [x.detach().clone().requires_grad_() for x in (means3D, opac, scales, rots, shs)]
+    e2e_opt = torch.optim.Adam(params, lr=1e-8)
     rng = np.random.default_rng(2)
     host = {}
     for k in my_views:
@@ -220,8 +228,7 @@ def main():
     d2h = res_host.numel() * 4
 
     def step_e2e():
-        for p_ in params:
-            p_.grad = None
+        e2e_opt.zero_grad(set_to_none=True)
         for j, k in enumerate(my_views):
             hb = host[k]
             img = hb["img"].to(dev, non_blocking=True); dep = hb["dep"].to(dev, non_blocking=True)
@@ -242,8 +249,9 @@ def main():
             res_host[j, 1:4].copy_(rho.grad, non_blocking=True)
             res_host[j, 4:7].copy_(theta.grad, non_blocking=True)
         if world > 1:
-            flat = torch.cat([p_.grad.reshape(-1) for p_ in params])
-            dist.all_reduce(flat)
+            for p_ in params:
+                dist.all_reduce(p_.grad)
+        e2e_opt.step()
         torch.cuda.current_stream().synchronize()               # the step's result is on the host
 
     for _ in range(max(3, args.warmup)):

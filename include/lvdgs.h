@@ -165,6 +165,17 @@ int lvdgs_dist2(int32_t P, const float *points, float *mean_dists, void *workspa
                 void *stream);
 
 /*
+ * Fused Adam update of a flat float32 parameter block with per-group learning rates (group k covers elements
+ * [group_end[k-1], group_end[k]); group_end and lr are HOST arrays of `groups` <= 8 entries; step >= 1 is the
+ * 1-based iteration for the bias correction).  Replaces the torch.optim.Adam.step the reference runs after every
+ * mapping iteration (utils/slam_backend.py:378-380); used after the gradient all-reduce of the keyframe-sharded
+ * mapping step so that every rank applies the identical update.
+ */
+int lvdgs_adam_step(int64_t n, float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int32_t groups,
+                    const int64_t *group_end, const float *lr, double beta1, double beta2, double eps, int32_t step,
+                    void *stream);
+
+/*
  * The binning sort on its own (stable LSD radix sort of u64 keys with u32 values over key bits
  * [0, end_bit)), exposed for parity tests and for the comparison against cub::DeviceRadixSort, the
  * library call upstream makes.  keys/vals: two buffers each of n elements; input in [0];

@@ -336,6 +336,15 @@ int lvdgs_dist2(int32_t P, const float *points, float *mean_dists, void *workspa
     return launch_dist2(P, points, mean_dists, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int lvdgs_adam_step(int64_t n, float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int32_t groups,
+                    const int64_t *group_end, const float *lr, double beta1, double beta2, double eps, int32_t step,
+                    void *stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !group_end || !lr || step < 1) { set_error("adam: bad arguments"); return 1; }
+    g_debug_sync = 0;
+    return launch_adam_step(n, params, grads, exp_avg, exp_avg_sq, groups, group_end, lr, beta1, beta2, eps, step,
+                            (cudaStream_t)stream);
+}
+
 size_t lvdgs_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n > 0 ? n : 1); }
 int lvdgs_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1,
                      int32_t end_bit, void *workspace, size_t workspace_bytes, int32_t *selector, void *stream) {

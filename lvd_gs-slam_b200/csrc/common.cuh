@@ -158,6 +158,10 @@ int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3
 
 int launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t s);
 
+int launch_adam_step(int64_t n, float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int groups,
+                     const int64_t *group_end, const float *lr, double beta1, double beta2, double eps, int step,
+                     cudaStream_t s);
+
 size_t dist2_workspace_bytes(int P);
 int launch_dist2(int P, const float *points, float *mean_dists, void *ws, size_t ws_bytes, cudaStream_t s);
 

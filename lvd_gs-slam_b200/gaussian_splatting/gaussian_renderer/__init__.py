@@ -54,12 +54,16 @@ def _render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, override_col
 
 
 def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None, mask=None):
+    if pc.get_xyz.shape[0] == 0:
+        return None
     return _render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, override_color, mask,
                    viewpoint_camera.image_height, viewpoint_camera.image_width)
 
 
 def render_with_custom_resolution(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None,
                                   mask=None, target_width=None, target_height=None):
+    if pc.get_xyz.shape[0] == 0:
+        return None
     W = target_width if target_width is not None else viewpoint_camera.image_width
     H = target_height if target_height is not None else viewpoint_camera.image_height
     return _render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, override_color, mask, H, W)

@@ -15,7 +15,7 @@ SRC_DIR = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 SO_PATH = os.path.join(PKG_DIR, "liblvdgs.so")
 SOURCES = ["api.cu", "preprocess.cu", "radix_sort.cu", "blend_forward.cu", "blend_backward.cu",
-           "preprocess_backward.cu", "knn.cu", "cub_compare.cu"]
+           "preprocess_backward.cu", "knn.cu", "adam.cu", "cub_compare.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", SO_PATH, *objs]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO_PATH, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
@@ -99,7 +99,7 @@ EXPORTS = ["lvdgs_version", "lvdgs_last_error", "lvdgs_set_device", "lvdgs_launc
            "lvdgs_profile_begin", "lvdgs_profile_end",
            "lvdgs_get_geom_layout", "lvdgs_get_binning_layout", "lvdgs_get_img_layout", "lvdgs_rasterize_forward",
            "lvdgs_backward_scratch_bytes", "lvdgs_rasterize_backward", "lvdgs_mark_visible",
-           "lvdgs_dist2_workspace_bytes", "lvdgs_dist2", "lvdgs_sort_workspace_bytes", "lvdgs_sort_pairs",
+           "lvdgs_dist2_workspace_bytes", "lvdgs_dist2", "lvdgs_adam_step", "lvdgs_sort_workspace_bytes", "lvdgs_sort_pairs",
            "lvdgs_cub_sort_workspace_bytes", "lvdgs_cub_sort_pairs"]
 
 
@@ -133,6 +133,7 @@ def lib():
     L.lvdgs_dist2_workspace_bytes.argtypes = [i32]
     L.lvdgs_dist2_workspace_bytes.restype = sz
     L.lvdgs_dist2.argtypes = [i32, vp, vp, vp, sz, vp]
+    L.lvdgs_adam_step.argtypes = [i64, vp, vp, vp, vp, i32, C.POINTER(i64), C.POINTER(f), C.c_double, C.c_double, C.c_double, i32, vp]
     L.lvdgs_sort_workspace_bytes.argtypes = [i64]
     L.lvdgs_sort_workspace_bytes.restype = sz
     L.lvdgs_sort_pairs.argtypes = [i64, vp, vp, vp, vp, i32, vp, sz, C.POINTER(i32), vp]
