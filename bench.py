@@ -31,6 +31,10 @@ for p in (ROOT, os.path.join(ROOT, "lvd_gs-slam_b200")):
 
 import numpy as np
 
+# keep stdout to the single JSON line the driver parses: NCCL prints its version banner there at VERSION level
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 METRIC = "fwd+bwd render Mpix/s at 1241x376, 500k Gaussians"
 WORKLOADS = {"kitti_window8_500k": dict(N=500_000, cam="kitti", views=8),
              "kitti_window8_1m": dict(N=1_000_000, cam="kitti", views=8)}
@@ -298,15 +302,15 @@ def main():
         nview = reps * len(my_views)
         pairs /= nview; Rs /= nview; vis /= nview
         passes = 6
-        alg = {  # algorithmic work per view (SURVEY.md section 8d / DESIGN.md section 7)
+        alg = {  # algorithmic work per view (SURVEY.md section 8d / DESIGN.md section 6)
             "preprocess_forward": ("hbm", 20.0 * (P - vis) + 131.0 * vis),
+            "binning_count": ("hbm", 4.0 * P + 12.0 * vis),
             "emit_keys": ("hbm", 12.0 * Rs + 20.0 * P),
-            "sort_histogram": ("hbm", 8.0 * Rs),
             "sort_onesweep": ("hbm", passes * 24.0 * Rs),
-            "tile_ranges": ("hbm", 8.0 * Rs),
             "blend_forward": ("fp32", 28.0 * pairs),
             "blend_backward": ("fp32", 70.0 * pairs),
             "preprocess_backward": ("hbm", 190.0 * vis + 52.0 * (P - vis)),
+            "adam_step": ("hbm", 28.0 * 14 * P / max(len(my_views), 1)),
         }
         for name, v in agg.items():
             per_view_ms = sum(v) / nview

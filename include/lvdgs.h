@@ -63,8 +63,9 @@ typedef struct lvdgs_geom_layout {
     size_t rgbd;           /* float4 [P]    rgb after SH + clamp, w = depth */
     size_t rect;           /* int16x4 [P]   tile rect min.x,min.y,max.x,max.y */
     size_t tiles_touched;  /* uint32 [P] */
-    size_t point_offsets;  /* uint32 [P]    inclusive scan of tiles_touched */
+    size_t point_offsets;  /* uint32 [P]    inclusive scan of tiles_touched (written by the key emission) */
     size_t clamped;        /* uint8  [P]    bit c set: channel c clamped at 0 */
+    size_t scan_state;     /* uint32 [ceil(P/256)] instances per preprocess block (-> exclusive offsets) + the R word */
     size_t total;
 } lvdgs_geom_layout;
 
@@ -80,6 +81,8 @@ typedef struct lvdgs_img_layout {
     size_t final_T;        /* float  [H*W] */
     size_t n_contrib;      /* uint32 [H*W] */
     size_t ranges;         /* uint2  [tiles] */
+    size_t tile_grid;      /* int32  [(gy+1)*(gx+1)] difference array -> per-tile instance counts */
+    size_t sort_hist;      /* uint32 [8][256] exclusive-scanned digit histograms of the sort keys */
     size_t total;
 } lvdgs_img_layout;
 

@@ -57,6 +57,7 @@ static void geom_layout(int32_t P, lvdgs_geom_layout &l) {
     l.tiles_touched = o; o += align_up(n * sizeof(uint32_t));
     l.point_offsets = o; o += align_up(n * sizeof(uint32_t));
     l.clamped = o; o += align_up(n * sizeof(uint8_t));
+    l.scan_state = o; o += align_up(((n + 255) / 256) * sizeof(uint32_t)) + 256;   // block sums + R word
     l.total = o;
 }
 static void binning_layout(int64_t R, lvdgs_binning_layout &l) {
@@ -75,6 +76,9 @@ static void img_layout(int32_t W, int32_t H, lvdgs_img_layout &l) {
     l.final_T = o; o += align_up(n * sizeof(float));
     l.n_contrib = o; o += align_up(n * sizeof(uint32_t));
     l.ranges = o; o += align_up(tiles * sizeof(uint2));
+    const size_t gridn = (size_t)((W + TILE - 1) / TILE + 1) * (size_t)((H + TILE - 1) / TILE + 1);
+    l.tile_grid = o; o += align_up(gridn * sizeof(int32_t));
+    l.sort_hist = o; o += align_up(SORT_MAX_PASSES * SORT_BINS * sizeof(uint32_t));
     l.total = o;
 }
 
@@ -86,6 +90,8 @@ static GeomPtrs geom_ptrs(void *base, int32_t P) {
     g.conic_opacity = (float4 *)(b + l.conic_opacity); g.rgbd = (float4 *)(b + l.rgbd);
     g.rect = (short4 *)(b + l.rect); g.tiles_touched = (uint32_t *)(b + l.tiles_touched);
     g.point_offsets = (uint32_t *)(b + l.point_offsets); g.clamped = (uint8_t *)(b + l.clamped);
+    g.block_sums = (uint32_t *)(b + l.scan_state);
+    g.num_instances = (uint32_t *)(b + l.total - 256);
     return g;
 }
 static BinPtrs bin_ptrs(void *base, int64_t R) {
@@ -101,6 +107,7 @@ static ImgPtrs img_ptrs(void *base, int32_t W, int32_t H) {
     char *b = (char *)base;
     ImgPtrs p;
     p.final_T = (float *)(b + l.final_T); p.n_contrib = (uint32_t *)(b + l.n_contrib); p.ranges = (uint2 *)(b + l.ranges);
+    p.tile_grid = (int32_t *)(b + l.tile_grid); p.sort_hist = (uint32_t *)(b + l.sort_hist);
     return p;
 }
 
@@ -173,16 +180,15 @@ static int launch_bin_and_blend(const lvdgs_raster_params &p, const GeomPtrs &g,
                                 float *out_opacity, int32_t *n_touched, cudaStream_t s) {
     const int W = p.width, H = p.height;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    const uint32_t *R_dev = g.point_offsets + (p.P - 1);
+    const uint32_t *R_dev = g.num_instances;
     LVDGS_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * (size_t)p.P, s));
     if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], b.vals[0], s)) return 1;
     const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
     int sel = 0;
     if (launch_sort_pairs(capacity, R_dev, b.keys[0], b.keys[1], b.vals[0], b.vals[1], end_bit, b.sort_ws,
-                          sort_workspace_bytes(capacity), &sel, s)) return 1;
+                          sort_workspace_bytes(capacity), im.sort_hist, &sel, s)) return 1;
     LVDGS_CHECK(cudaMemcpyAsync(b.sorted_sel, &sel, sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    if (launch_tile_ranges(capacity, R_dev, gx * gy, b.keys[sel], im.ranges, s)) return 1;
-    return launch_blend_forward(W, H, im.ranges, b.vals[sel], g, background, out_color, out_depth, out_opacity,
+    return launch_blend_forward(W, H, capacity, R_dev, im.ranges, b.vals[sel], g, background, out_color, out_depth, out_opacity,
                                 im.final_T, im.n_contrib, n_touched, s);
 }
 
@@ -224,7 +230,7 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     if (p.P == 0) {     // empty map: background only
         LVDGS_CHECK(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)gx * gy, s));
         GeomPtrs g{};
-        return launch_blend_forward(W, H, im.ranges, nullptr, g, background, out_color, out_depth, out_opacity, im.final_T,
+        return launch_blend_forward(W, H, 0, nullptr, im.ranges, nullptr, g, background, out_color, out_depth, out_opacity, im.final_T,
                                     im.n_contrib, n_touched, s);
     }
     if (!t_pinned_R) {
@@ -235,11 +241,13 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     void *geom_base = resize(resize_user, LVDGS_BUF_GEOM, gl.total);
     if (!geom_base) { set_error("resize callback returned NULL (geom)"); return 1; }
     GeomPtrs g = geom_ptrs(geom_base, p.P);
+    // the tile grid + digit histograms are accumulated with atomics: one memset
+    LVDGS_CHECK(cudaMemsetAsync(im.tile_grid, 0, il.total - il.tile_grid, s));
     if (launch_preprocess_forward(p, means3D, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
-                                  projmatrix, shs, campos, radii, g, s)) return 1;
-    // the scan's block sums (ceil(P/2048) words) borrow n_touched, which is zeroed before the blend
-    if (launch_scan_tiles(p.P, g.tiles_touched, g.point_offsets, reinterpret_cast<uint32_t *>(n_touched), s)) return 1;
-    LVDGS_CHECK(cudaMemcpyAsync(t_pinned_R, g.point_offsets + (p.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                                  projmatrix, shs, campos, radii, g, im, s)) return 1;
+    // block offsets, R, tile ranges and all digit histograms of the sort, from the block sums and per-tile counts
+    if (launch_binning_prep(p.P, W, H, 32 + tile_bits((uint32_t)(gx * gy)), g, im, s)) return 1;
+    LVDGS_CHECK(cudaMemcpyAsync(t_pinned_R, g.num_instances, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     LVDGS_CHECK(cudaEventRecord(t_R_event, s));
 
     // Speculative launch: with a capacity hint the whole rest of the forward is queued BEFORE the host waits for R,
@@ -350,7 +358,7 @@ int lvdgs_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *vals
                      int32_t end_bit, void *workspace, size_t workspace_bytes, int32_t *selector, void *stream) {
     g_debug_sync = 0;
     int sel = 0;
-    const int rc = launch_sort_pairs(n, nullptr, keys0, keys1, vals0, vals1, end_bit, workspace, workspace_bytes, &sel,
+    const int rc = launch_sort_pairs(n, nullptr, keys0, keys1, vals0, vals1, end_bit, workspace, workspace_bytes, nullptr, &sel,
                                      (cudaStream_t)stream);
     if (selector) *selector = sel;
     return rc;

@@ -21,7 +21,7 @@ namespace lvdgs {
 constexpr int BF_THREADS = TILE_PIX;
 constexpr int BF_WARPS = BF_THREADS / 32;      // 8 warps = 2 x 4 blocks of 8 x 4 pixels
 
-__global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H, int gx, const uint2 *__restrict__ ranges,
+__global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H, int gx, uint32_t capacity, const uint32_t *__restrict__ n_dev, const uint2 *__restrict__ ranges,
                                                                    const uint32_t *__restrict__ point_list,
                                                                    const float4 *__restrict__ means2D,
                                                                    const float4 *__restrict__ conic_opacity,
@@ -46,6 +46,9 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
     const uint32_t a_id = smem_u32(s_id), a_xy = smem_u32(s_xy), a_q = smem_u32(s_co), a_cd = smem_u32(s_cd);
     const float tx0 = (float)(blockIdx.x * TILE), ty0 = (float)(blockIdx.y * TILE);   // tile's first pixel centre
 
+    // a speculative launch whose capacity hint was too small has no valid sorted list (the sort retires, see
+    // radix_sort.cu); its output is discarded and the tail re-run by the host, so do nothing here
+    if (n_dev && __ldg(n_dev) > capacity) return;
     const uint2 range = ranges[tile];
     int todo = (int)(range.y - range.x);
     bool done = !inside;
@@ -136,12 +139,12 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
     }
 }
 
-int launch_blend_forward(int W, int H, const uint2 *ranges, const uint32_t *point_list, const GeomPtrs &g,
+int launch_blend_forward(int W, int H, int64_t capacity, const uint32_t *n_dev, const uint2 *ranges, const uint32_t *point_list, const GeomPtrs &g,
                          const float *bg, float *out_color, float *out_depth, float *out_opacity, float *final_T,
                          uint32_t *n_contrib, int32_t *n_touched, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     LVDGS_PRE(s);
-    blend_forward_kernel<<<dim3(gx, gy), BF_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
+    blend_forward_kernel<<<dim3(gx, gy), BF_THREADS, 0, s>>>(W, H, gx, (uint32_t)min(capacity, (int64_t)0xffffffffll), n_dev, ranges, point_list, g.means2D, g.conic_opacity,
                                                               g.rgbd, bg, out_color, out_depth, out_opacity, final_T,
                                                               n_contrib, n_touched);
     LVDGS_LAUNCHED(s, "blend_forward");

@@ -103,30 +103,36 @@ static inline int tile_bits(uint32_t n) {
 struct GeomPtrs {
     float *depths; float4 *means2D; float4 *conic_opacity; float4 *rgbd; short4 *rect;
     uint32_t *tiles_touched; uint32_t *point_offsets; uint8_t *clamped;
+    uint32_t *block_sums;             // [ceil(P/256)] instances per preprocess block -> exclusive offsets (binning_prep)
+    uint32_t *num_instances;          // R, written by binning_prep
 };
 struct BinPtrs {
     uint64_t *keys[2]; uint32_t *vals[2]; void *sort_ws; int32_t *sorted_sel;
 };
 struct ImgPtrs {
     float *final_T; uint32_t *n_contrib; uint2 *ranges;
+    int32_t *tile_grid;               // [(gy+1)*(gx+1)] 2-D difference array of the tile rects -> per-tile instance counts
+    uint32_t *sort_hist;              // [8][256] digit histograms of the (tile|depth) keys, exclusive-scanned by binning_prep
 };
+constexpr int SORT_MAX_PASSES = 8;
+constexpr int SORT_BINS = 256;
 
 int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D, const float *colors_precomp,
                               const float *opacities, const float *scales, const float *rotations,
                               const float *cov3D_precomp, const float *view, const float *proj, const float *shs,
-                              const float *campos, int32_t *radii, const GeomPtrs &g, cudaStream_t s);
-int launch_scan_tiles(int P, const uint32_t *tiles_touched, uint32_t *point_offsets, uint32_t *block_sums,
-                      cudaStream_t s);
+                              const float *campos, int32_t *radii, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s);
+int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s);
 int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, int64_t capacity, uint64_t *keys, uint32_t *vals,
                      cudaStream_t s);
-int launch_tile_ranges(int64_t capacity, const uint32_t *n_dev, int num_tiles, const uint64_t *keys_sorted, uint2 *ranges,
-                       cudaStream_t s);
 
 size_t sort_workspace_bytes(int64_t n);
+// pre_hist: optional [passes][256] exclusive-scanned digit histograms (device); when given, the histogram pass over the
+// keys is skipped (the forward derives them in preprocess / binning_prep).
 int launch_sort_pairs(int64_t n, const uint32_t *n_dev, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
-                      uint32_t *vals1, int end_bit, void *ws, size_t ws_bytes, int *selector, cudaStream_t s);
+                      uint32_t *vals1, int end_bit, void *ws, size_t ws_bytes, const uint32_t *pre_hist, int *selector,
+                      cudaStream_t s);
 
-int launch_blend_forward(int W, int H, const uint2 *ranges, const uint32_t *point_list, const GeomPtrs &g,
+int launch_blend_forward(int W, int H, int64_t capacity, const uint32_t *n_dev, const uint2 *ranges, const uint32_t *point_list, const GeomPtrs &g,
                          const float *bg, float *out_color, float *out_depth, float *out_opacity,
                          float *final_T, uint32_t *n_contrib, int32_t *n_touched, cudaStream_t s);
 

@@ -1,4 +1,5 @@
-// preprocess.cu -- K1 preprocess forward, K2 tile-count scan, K3 key emission, K5 tile ranges, K10 markVisible.
+// preprocess.cu -- K1 preprocess forward (with the K2 tile-count scan fused in), binning_prep (K5 tile ranges + sort
+// histograms from per-tile counts), K3 key emission, K10 markVisible.
 //
 // Behaviour follows SURVEY.md Appendix A.1 / A.2 (the reference's `preprocessCUDA`, `duplicateWithKeys`,
 // `identifyTileRanges`, `checkFrustum`, reached from utils/slam_frontend.py:1493 and utils/slam_backend.py:184
@@ -24,8 +25,8 @@ __device__ __constant__ float SH_C3[7] = {-0.5900435899266435f, 2.89061144264055
                                           -0.5900435899266435f};
 
 // coalesced load of 256 x 3 floats into shared memory (block-strided), then each thread picks its triple
-__device__ __forceinline__ float3 load3_staged(const float *__restrict__ base, int P, float *smem) {
-    const int blk0 = blockIdx.x * PRE_THREADS;
+__device__ __forceinline__ float3 load3_staged(const float *__restrict__ base, int P, float *smem, int bid) {
+    const int blk0 = bid * PRE_THREADS;
     const int n = min(PRE_THREADS, P - blk0) * 3;
     const float *src = base + (size_t)blk0 * 3;
     for (int k = threadIdx.x; k < n; k += PRE_THREADS) smem[k] = __ldg(src + k);
@@ -151,17 +152,19 @@ struct PreArgs {
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(const PreArgs a) {
     __shared__ float stage[PRE_THREADS * 3];
     __shared__ CameraConst cam;
+    __shared__ uint32_t s_warp[PRE_THREADS / 32];
+    const int bid = blockIdx.x;
     if (threadIdx.x < 16) cam.view[threadIdx.x] = __ldg(a.view + threadIdx.x);
     else if (threadIdx.x < 32) cam.proj[threadIdx.x - 16] = __ldg(a.proj + threadIdx.x - 16);
     else if (threadIdx.x < 35) cam.campos[threadIdx.x - 32] = __ldg(a.campos + threadIdx.x - 32);
-    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
-    const float3 p = load3_staged(a.means3D, a.P, stage);      // contains the __syncthreads that publishes `cam`
+    const int i = bid * PRE_THREADS + threadIdx.x;
+    const float3 p = load3_staged(a.means3D, a.P, stage, bid);      // contains the __syncthreads that publishes `cam`
     float3 sc = make_float3(0.f, 0.f, 0.f);
-    if (a.scales) sc = load3_staged(a.scales, a.P, stage);
+    if (a.scales) sc = load3_staged(a.scales, a.P, stage, bid);
     float3 sh0 = make_float3(0.f, 0.f, 0.f);
     const bool staged_color = a.colors_precomp != nullptr || a.M == 1;
-    if (staged_color) sh0 = load3_staged(a.colors_precomp ? a.colors_precomp : a.shs, a.P, stage);
-    if (i >= a.P) return;
+    if (staged_color) sh0 = load3_staged(a.colors_precomp ? a.colors_precomp : a.shs, a.P, stage, bid);
+    const bool in_range = i < a.P;
 
     int32_t radius = 0;
     uint32_t touched = 0;
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(const P
     const float tx = __fadd_rn(dot3c(V[0], p.x, V[4], p.y, V[8], p.z), V[12]);
     const float ty = __fadd_rn(dot3c(V[1], p.x, V[5], p.y, V[9], p.z), V[13]);
     const float tz = __fadd_rn(dot3c(V[2], p.x, V[6], p.y, V[10], p.z), V[14]);
-    if (tz > 0.2f) {
+    if (in_range && tz > 0.2f) {
         const float hx = __fadd_rn(dot3c(Pj[0], p.x, Pj[4], p.y, Pj[8], p.z), Pj[12]);
         const float hy = __fadd_rn(dot3c(Pj[1], p.x, Pj[5], p.y, Pj[9], p.z), Pj[13]);
         const float hw = __fadd_rn(dot3c(Pj[3], p.x, Pj[7], p.y, Pj[11], p.z), Pj[15]);
@@ -236,21 +239,37 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(const P
             }
         }
     }
-    a.radii[i] = radius;
-    a.g.depths[i] = depth;
-    a.g.means2D[i] = pix;
-    a.g.conic_opacity[i] = con_o;
-    a.g.rgbd[i] = make_float4(rgb.x, rgb.y, rgb.z, depth);
-    a.g.rect[i] = rect;
-    a.g.tiles_touched[i] = touched;
-    a.g.clamped[i] = clamped;
+    if (in_range) {
+        a.radii[i] = radius;
+        a.g.depths[i] = depth;
+        a.g.means2D[i] = pix;
+        a.g.conic_opacity[i] = con_o;
+        a.g.rgbd[i] = make_float4(rgb.x, rgb.y, rgb.z, depth);
+        a.g.rect[i] = rect;
+        a.g.tiles_touched[i] = touched;
+        a.g.clamped[i] = clamped;
+    }
+    // ---- K2, first half: this block's instance count (binning_prep scans the block sums, emit_keys scans inside) ----
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t sum = touched;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) s_warp[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int k = 0; k < PRE_THREADS / 32; ++k) t += s_warp[k];
+        a.g.block_sums[bid] = t;
+    }
 }
 
 int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D, const float *colors_precomp,
                               const float *opacities, const float *scales, const float *rotations,
                               const float *cov3D_precomp, const float *view, const float *proj, const float *shs,
-                              const float *campos, int32_t *radii, const GeomPtrs &g, cudaStream_t s) {
+                              const float *campos, int32_t *radii, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s) {
     PreArgs a;
+    (void)im;
     a.P = p.P; a.D = p.sh_degree; a.M = p.sh_coeffs; a.W = p.width; a.H = p.height;
     a.gx = (p.width + TILE - 1) / TILE; a.gy = (p.height + TILE - 1) / TILE;
     a.tanfovx = p.tan_fovx; a.tanfovy = p.tan_fovy;
@@ -266,103 +285,171 @@ int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K2: inclusive scan of tiles_touched.  Three small launches (reduce / scan block sums / rescan+add); the data
-// is 4 B per Gaussian, so this is launch-latency, not bandwidth.
+// binning_prep: one CTA.  Integrates the 2-D difference array into per-tile instance counts, turns them into the
+// tile ranges (K5 -- no pass over the sorted keys is needed: range(t) = [sum of counts before t, + count(t))),
+// derives the histograms of the key digits that hold the tile id, and exclusive-scans all digit histograms for the
+// onesweep passes (replaces the sort's own histogram kernel: the keys are never read for counting).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+// ---------------------------------------------------------------------------------------------------------
+// binning_count: per-tile instance counts and the histograms of the four depth digits of the sort keys, WITHOUT
+// touching the instances: every visible Gaussian contributes its tile rect as a 2-D difference (4 corner updates
+// instead of one update per covered tile) and `tiles_touched` to the bin of each depth byte.  A few large CTAs with
+// shared-memory-privatised tables, flushed once, so global atomics are ~1 per table cell per CTA.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int COUNT_THREADS = 1024;
+constexpr int PREP_GRID_SMEM = 10240;     // difference-array cells kept in shared memory (covers 1920x1080: 121 x 69)
 
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(COUNT_THREADS) binning_count_kernel(int P, int gx, int gy, const uint32_t *__restrict__ tiles_touched,
+                                                                      const short4 *__restrict__ rects, const float *__restrict__ depths,
+                                                                      int32_t *__restrict__ grid_g, uint32_t *__restrict__ hist_g) {
+    extern __shared__ int32_t s_tab[];          // [4*256] depth-digit histograms, then the grid if it fits
+    const int gw = gx + 1, cells = gw * (gy + 1);
+    const bool in_smem = cells <= PREP_GRID_SMEM;
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_tab);
+    int32_t *s_grid = s_tab + 4 * SORT_BINS;
+    for (int k = threadIdx.x; k < 4 * SORT_BINS + (in_smem ? cells : 0); k += COUNT_THREADS) s_tab[k] = 0;
+    __syncthreads();
+    int32_t *grid = in_smem ? s_grid : grid_g;
+    for (int i = blockIdx.x * COUNT_THREADS + threadIdx.x; i < P; i += gridDim.x * COUNT_THREADS) {
+        const uint32_t touched = __ldg(tiles_touched + i);
+        if (!touched) continue;
+        const short4 rc = __ldg(rects + i);
+        atomicAdd(grid + rc.y * gw + rc.x, 1);
+        atomicAdd(grid + rc.y * gw + rc.z, -1);
+        atomicAdd(grid + rc.w * gw + rc.x, -1);
+        atomicAdd(grid + rc.w * gw + rc.z, 1);
+        const uint32_t db = __float_as_uint(__ldg(depths + i));
+        atomicAdd(s_hist + 0 * SORT_BINS + (db & 0xffu), touched);
+        atomicAdd(s_hist + 1 * SORT_BINS + ((db >> 8) & 0xffu), touched);
+        atomicAdd(s_hist + 2 * SORT_BINS + ((db >> 16) & 0xffu), touched);
+        atomicAdd(s_hist + 3 * SORT_BINS + (db >> 24), touched);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4 * SORT_BINS; k += COUNT_THREADS)
+        if (s_hist[k]) atomicAdd(hist_g + k, s_hist[k]);
+    if (in_smem)
+        for (int k = threadIdx.x; k < cells; k += COUNT_THREADS)
+            if (s_grid[k]) atomicAdd(grid_g + k, s_grid[k]);
+}
+
+constexpr int PREP_THREADS = 1024;     // difference-array cells integrated in shared memory (covers 1920x1080: 121 x 69)
+
+// block-wide inclusive scan of one value per thread (1024 threads); returns the inclusive value, total via s_ws[31]
+__device__ __forceinline__ uint32_t prep_incl_scan(uint32_t c, uint32_t *s_ws) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += n;
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
     }
-    return v;
-}
-
-// block-wide exclusive scan of one value per thread; returns exclusive prefix, total via out param
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_sums, uint32_t &total) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t incl = warp_incl_scan(v);
-    if (lane == 31) warp_sums[w] = incl;
+    if (lane == 31) s_ws[warp] = incl;
     __syncthreads();
-    if (w == 0) {
-        uint32_t ws = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
-        ws = warp_incl_scan(ws);
-        warp_sums[lane] = ws;
+    if (warp == 0) {
+        uint32_t w = s_ws[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += n;
+        }
+        s_ws[lane] = w;
     }
     __syncthreads();
-    const uint32_t base = w ? warp_sums[w - 1] : 0;
-    total = warp_sums[(blockDim.x >> 5) - 1];
+    return (warp ? s_ws[warp - 1] : 0) + incl;
+}
+
+__global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int gy, int passes, int end_bit, int nblocks,
+                                                                    int32_t *__restrict__ grid_g, uint2 *__restrict__ ranges,
+                                                                    uint32_t *__restrict__ hist, uint32_t *__restrict__ block_sums,
+                                                                    uint32_t *__restrict__ R_out) {
+    extern __shared__ int32_t s_grid[];
+    __shared__ uint32_t s_h[SORT_MAX_PASSES * SORT_BINS];
+    __shared__ uint32_t s_ws[32];
+    __shared__ uint32_t s_carry;
+    const int gw = gx + 1, cells = gw * (gy + 1), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool in_smem = cells <= PREP_GRID_SMEM;
+    int32_t *grid = in_smem ? s_grid : grid_g;
+    for (int k = tid; k < SORT_MAX_PASSES * SORT_BINS; k += PREP_THREADS) s_h[k] = k < 4 * SORT_BINS ? hist[k] : 0u;
+    if (in_smem)
+        for (int k = tid; k < cells; k += PREP_THREADS) s_grid[k] = grid_g[k];
+    // (a) exclusive scan of the preprocess blocks' instance counts -> per-block key offsets, and R
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    return base + incl - v;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(int P, const uint32_t *__restrict__ in,
-                                                                   uint32_t *__restrict__ block_sums) {
-    __shared__ uint32_t ws[32];
-    const int base = blockIdx.x * SCAN_TILE;
-    uint32_t v = 0;
+    for (int base = 0; base < nblocks; base += PREP_THREADS) {
+        const int b = base + tid;
+        const uint32_t c = b < nblocks ? block_sums[b] : 0u;
+        const uint32_t incl = prep_incl_scan(c, s_ws);
+        if (b < nblocks) block_sums[b] = s_carry + incl - c;
+        __syncthreads();
+        if (tid == 0) s_carry += s_ws[31];
+        __syncthreads();
+    }
+    if (tid == 0) { *R_out = s_carry; s_carry = 0; }
+    // (b) 2-D inclusive prefix sum of the difference array: along x per row, then along y per column
+    for (int y = tid; y <= gy; y += PREP_THREADS) {
+        int run = 0;
+        for (int x = 0; x <= gx; ++x) { run += grid[y * gw + x]; grid[y * gw + x] = run; }
+    }
+    __syncthreads();
+    for (int x = tid; x <= gx; x += PREP_THREADS) {
+        int run = 0;
+        for (int y = 0; y <= gy; ++y) { run += grid[y * gw + x]; grid[y * gw + x] = run; }
+    }
+    __syncthreads();
+    // (c) exclusive scan of the counts in tile order -> ranges; histograms of the key digits that hold the tile id
+    const int tiles = gx * gy;
+    for (int base = 0; base < tiles; base += PREP_THREADS) {
+        const int t = base + tid;
+        uint32_t c = 0;
+        if (t < tiles) c = (uint32_t)grid[(t / gx) * gw + (t % gx)];
+        const uint32_t incl = prep_incl_scan(c, s_ws);
+        const uint32_t start = s_carry + incl - c;
+        if (t < tiles) {
+            ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
+            if (c) {
+                for (int q = 4; q < passes; ++q) {
+                    const int shift = 8 * (q - 4), nb = min(8, end_bit - 8 * q);
+                    atomicAdd(&s_h[q * SORT_BINS + (((uint32_t)t >> shift) & ((1u << nb) - 1u))], c);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += s_ws[31];
+        __syncthreads();
+    }
+    // (d) exclusive scan of every digit histogram: one warp per pass, 8 bins per lane
+    if (warp < passes) {
+        uint32_t v[8], sum = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        const int i = base + k * SCAN_THREADS + threadIdx.x;
-        if (i < P) v += in[i];
-    }
-    uint32_t total;
-    block_excl_scan(v, ws, total);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(1024) scan_block_sums_kernel(int nb, uint32_t *block_sums) {
-    __shared__ uint32_t ws[32];
-    uint32_t carry = 0;
-    for (int base = 0; base < nb; base += 1024) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = i < nb ? block_sums[i] : 0;
-        uint32_t total;
-        const uint32_t ex = block_excl_scan(v, ws, total);
-        if (i < nb) block_sums[i] = carry + ex;     // exclusive prefix of the block sums
-        carry += total;
-    }
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int P, const uint32_t *__restrict__ in,
-                                                                  const uint32_t *__restrict__ block_sums,
-                                                                  uint32_t *__restrict__ out) {
-    __shared__ uint32_t ws[32];
-    // thread owns SCAN_ITEMS consecutive elements (blocked arrangement)
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS];
-    uint32_t sum = 0;
+        for (int k = 0; k < 8; ++k) { v[k] = s_h[warp * SORT_BINS + lane * 8 + k]; sum += v[k]; }
+        uint32_t incl = sum;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        v[k] = (base + k < P) ? in[base + k] : 0;
-        sum += v[k];
-    }
-    uint32_t total;
-    uint32_t run = block_excl_scan(sum, ws, total) + block_sums[blockIdx.x];
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        uint32_t run = incl - sum;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        run += v[k];
-        if (base + k < P) out[base + k] = run;
+        for (int k = 0; k < 8; ++k) { hist[warp * SORT_BINS + lane * 8 + k] = run; run += v[k]; }
     }
 }
 
-int launch_scan_tiles(int P, const uint32_t *tiles_touched, uint32_t *point_offsets, uint32_t *block_sums,
-                      cudaStream_t s) {
-    const int nb = ceil_div(P, SCAN_TILE);
+int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s) {
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const int passes = (end_bit + 7) / 8;
+    const int cells = (gx + 1) * (gy + 1);
+    const size_t dyn = cells <= PREP_GRID_SMEM ? (size_t)cells * sizeof(int32_t) : 0;
+    {
+        const int blocks = min(148, ceil_div(P, COUNT_THREADS * 2));
+        LVDGS_PRE(s);
+        binning_count_kernel<<<blocks, COUNT_THREADS, 4 * SORT_BINS * sizeof(uint32_t) + dyn, s>>>(
+            P, gx, gy, g.tiles_touched, g.rect, g.depths, im.tile_grid, im.sort_hist);
+        LVDGS_LAUNCHED(s, "binning_count");
+    }
     LVDGS_PRE(s);
-    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(P, tiles_touched, block_sums);
-    LVDGS_LAUNCHED(s, "scan_reduce");
-    LVDGS_PRE(s);
-    scan_block_sums_kernel<<<1, 1024, 0, s>>>(nb, block_sums);
-    LVDGS_LAUNCHED(s, "scan_block_sums");
-    LVDGS_PRE(s);
-    scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>(P, tiles_touched, block_sums, point_offsets);
-    LVDGS_LAUNCHED(s, "scan_apply");
+    binning_prep_kernel<<<1, PREP_THREADS, dyn, s>>>(gx, gy, passes, end_bit, ceil_div(P, PRE_THREADS), im.tile_grid, im.ranges,
+                                                     im.sort_hist, g.block_sums, g.num_instances);
+    LVDGS_LAUNCHED(s, "binning_prep");
     return 0;
 }
 
@@ -374,19 +461,38 @@ int launch_scan_tiles(int P, const uint32_t *tiles_touched, uint32_t *point_offs
 // stable sort resolve identically.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int EMIT_THREADS = 256;
+static_assert(EMIT_THREADS == PRE_THREADS, "emit blocks must own the same Gaussians as preprocess blocks (block_sums)");
+static_assert(PRE_THREADS == SORT_BINS, "s_hist3 is indexed by threadIdx");
 
-__global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, uint32_t capacity, const uint32_t *__restrict__ offsets,
+__global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, uint32_t capacity, const uint32_t *__restrict__ block_offsets,
+                                                                 const uint32_t *__restrict__ tiles_touched, uint32_t *__restrict__ offsets,
                                                                  const short4 *__restrict__ rects,
                                                                  const float *__restrict__ depths,
                                                                  uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
     __shared__ uint32_t s_end[EMIT_THREADS];      // inclusive offsets of this block's Gaussians
     __shared__ short4 s_rect[EMIT_THREADS];
     __shared__ uint32_t s_depth[EMIT_THREADS];
+    __shared__ uint32_t s_wsum[EMIT_THREADS / 32];
     const int g0 = blockIdx.x * EMIT_THREADS;
     const int i = g0 + threadIdx.x;
-    const uint32_t span_begin = g0 ? offsets[g0 - 1] : 0;
+    const uint32_t span_begin = block_offsets[blockIdx.x];      // exclusive prefix over the preceding blocks (binning_prep)
+    // K2, second half: inclusive scan of this block's tile counts
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = i < P ? tiles_touched[i] : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int k = 0; k < EMIT_THREADS / 32; ++k) wbase += k < warp ? s_wsum[k] : 0u;
+    incl += span_begin + wbase;
     if (i < P) {
-        s_end[threadIdx.x] = offsets[i];
+        offsets[i] = incl;                                      // point_offsets, kept for inspection / parity tests
+        s_end[threadIdx.x] = incl;
         s_rect[threadIdx.x] = rects[i];
         s_depth[threadIdx.x] = __float_as_uint(depths[i]);
     } else {
@@ -418,37 +524,8 @@ int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, int64_t capacity, u
     (void)H;
     const int gx = (W + TILE - 1) / TILE;
     LVDGS_PRE(s);
-    emit_keys_kernel<<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, (uint32_t)min(capacity, (int64_t)0xffffffffll), g.point_offsets, g.rect, g.depths, keys, vals);
+    emit_keys_kernel<<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, (uint32_t)min(capacity, (int64_t)0xffffffffll), g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals);
     LVDGS_LAUNCHED(s, "emit_keys");
-    return 0;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// K5: tile ranges from the sorted keys.  `ranges` must be zeroed by the caller (untouched tiles stay (0,0)).
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t capacity, const uint32_t *__restrict__ n_dev,
-                                                          const uint64_t *__restrict__ keys, uint2 *__restrict__ ranges) {
-    const int64_t R = n_dev ? min((int64_t)__ldg(n_dev), capacity) : capacity;
-    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (r >= R) return;
-    const uint32_t t = (uint32_t)(keys[r] >> 32);
-    if (r == 0) ranges[t].x = 0;
-    else {
-        const uint32_t tp = (uint32_t)(keys[r - 1] >> 32);
-        if (t != tp) { ranges[tp].y = (uint32_t)r; ranges[t].x = (uint32_t)r; }
-    }
-    if (r == R - 1) ranges[t].y = (uint32_t)R;
-}
-
-int launch_tile_ranges(int64_t capacity, const uint32_t *n_dev, int num_tiles, const uint64_t *keys_sorted, uint2 *ranges,
-                       cudaStream_t s) {
-    const int64_t R = capacity;
-    LVDGS_CHECK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, s));
-    if (R > 0) {
-        LVDGS_PRE(s);
-        tile_ranges_kernel<<<ceil_div(R, 256), 256, 0, s>>>(R, n_dev, keys_sorted, ranges);
-        LVDGS_LAUNCHED(s, "tile_ranges");
-    }
     return 0;
 }
 
@@ -459,7 +536,7 @@ __global__ void __launch_bounds__(PRE_THREADS) mark_visible_kernel(int P, const 
                                                                    const float *__restrict__ view,
                                                                    uint8_t *__restrict__ present) {
     __shared__ float stage[PRE_THREADS * 3];
-    const float3 p = load3_staged(means3D, P, stage);
+    const float3 p = load3_staged(means3D, P, stage, blockIdx.x);
     const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
     if (i >= P) return;
     const float tz = __fadd_rn(dot3c(__ldg(view + 2), p.x, __ldg(view + 6), p.y, __ldg(view + 10), p.z), __ldg(view + 14));

@@ -117,7 +117,11 @@ struct __align__(16) RsSmem {
 __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                                                                  const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
                                                                  int64_t n_cap, const uint32_t *__restrict__ n_dev, int shift,
-                                                                 int nbits, int pass, SortWs *ws, uint32_t *lookback) {
+                                                                 int nbits, int pass, SortWs *ws, const uint32_t *__restrict__ hist_scanned,
+                                                                 uint32_t *lookback) {
+    // pre-computed histograms count ALL instances: if the launch capacity is too small (speculative forward whose hint
+    // was exceeded) the scatter offsets would run past the buffers; that launch's output is discarded anyway -> retire
+    if (n_dev && (int64_t)__ldg(n_dev) > n_cap) return;
     const int64_t n = rs_count(n_cap, n_dev);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmem &sm = *reinterpret_cast<RsSmem *>(smem_raw);
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
         }
         lb[(size_t)tile * RS_BINS + tid] = (excl + total) | LB_GLOBAL;
     }
-    sm.goff[tid] = ws->hist[pass][tid] + excl - bstart;
+    sm.goff[tid] = hist_scanned[pass * RS_BINS + tid] + excl - bstart;
     __syncthreads();
 
     // ---- scatter keys through shared memory, then coalesced runs to global ----
@@ -220,7 +224,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
 }
 
 int launch_sort_pairs(int64_t n, const uint32_t *n_dev, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
-                      uint32_t *vals1, int end_bit, void *ws_raw, size_t ws_bytes, int *selector, cudaStream_t s) {
+                      uint32_t *vals1, int end_bit, void *ws_raw, size_t ws_bytes, const uint32_t *pre_hist, int *selector,
+                      cudaStream_t s) {
     if (selector) *selector = 0;
     if (n <= 0) return 0;
     if (end_bit < 1 || end_bit > 64) { set_error("sort: end_bit %d out of range", end_bit); return 1; }
@@ -237,19 +242,23 @@ int launch_sort_pairs(int64_t n, const uint32_t *n_dev, uint64_t *keys0, uint64_
         LVDGS_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         attr_set = true;
     }
-    const int hist_blocks = (int)min((int64_t)148 * 8, (n + RS_THREADS * 8 - 1) / (RS_THREADS * 8));
-    LVDGS_PRE(s);
-    rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, s>>>(keys0, n, n_dev, passes, end_bit, ws);
-    LVDGS_LAUNCHED(s, "sort_histogram");
-    LVDGS_PRE(s);
-    rs_scan_hist_kernel<<<passes, RS_BINS, 0, s>>>(ws);
-    LVDGS_LAUNCHED(s, "sort_scan_hist");
+    const uint32_t *hist_scanned = pre_hist;
+    if (!pre_hist) {
+        const int hist_blocks = (int)min((int64_t)148 * 8, (n + RS_THREADS * 8 - 1) / (RS_THREADS * 8));
+        LVDGS_PRE(s);
+        rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, s>>>(keys0, n, n_dev, passes, end_bit, ws);
+        LVDGS_LAUNCHED(s, "sort_histogram");
+        LVDGS_PRE(s);
+        rs_scan_hist_kernel<<<passes, RS_BINS, 0, s>>>(ws);
+        LVDGS_LAUNCHED(s, "sort_scan_hist");
+        hist_scanned = &ws->hist[0][0];
+    }
     uint64_t *kin = keys0, *kout = keys1;
     uint32_t *vin = vals0, *vout = vals1;
     for (int p = 0; p < passes; ++p) {
         const int shift = p * 8, nb = min(8, end_bit - shift);
         LVDGS_PRE(s);
-        rs_onesweep_kernel<<<ntiles, RS_THREADS, sizeof(RsSmem), s>>>(kin, kout, vin, vout, n, n_dev, shift, nb, p, ws,
+        rs_onesweep_kernel<<<ntiles, RS_THREADS, sizeof(RsSmem), s>>>(kin, kout, vin, vout, n, n_dev, shift, nb, p, ws, hist_scanned,
                                                                       reinterpret_cast<uint32_t *>(lb_base + lb_stride * p));
         LVDGS_LAUNCHED(s, "sort_onesweep");
         uint64_t *tk = kin; kin = kout; kout = tk;

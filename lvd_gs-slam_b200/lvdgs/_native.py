@@ -81,7 +81,7 @@ class RasterParams(C.Structure):
 
 class GeomLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("depths", "means2D", "conic_opacity", "rgbd", "rect", "tiles_touched",
-                                          "point_offsets", "clamped", "total")]
+                                          "point_offsets", "clamped", "scan_state", "total")]
 
 
 class BinningLayout(C.Structure):
@@ -90,7 +90,7 @@ class BinningLayout(C.Structure):
 
 
 class ImgLayout(C.Structure):
-    _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "ranges", "total")]
+    _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "ranges", "tile_grid", "sort_hist", "total")]
 
 
 RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int32, C.c_size_t)
