@@ -138,8 +138,9 @@ size_t lvdgs_backward_scratch_bytes(int32_t P, int64_t R);
  *   dL_dout_color [3,H,W]; dL_dout_depth [H,W] or NULL; dL_dout_opacity [H,W] or NULL (used only with
  *   LVDGS_FLAG_OPACITY_GRAD; upstream drops it).  geom/binning/img buffers and R are those of the forward.
  * Outputs (every element written, no pre-zeroing needed -- except with LVDGS_FLAG_ACCUMULATE, where the parameter
- *   gradients dL_dcolors/opacity/means3D/cov3D/sh/scales/rots are added to the buffers' contents): dL_dmeans2D [P,3] (z = 0), dL_dcolors [P,3],
- *   dL_dopacity [P], dL_dmeans3D [P,3], dL_dcov3D [P,6], dL_dsh [P,M,3] (NULL ok with colors_precomp),
+ *   gradients dL_dcolors/opacity/means3D/cov3D/sh/scales/rots are added to the buffers' contents): dL_dmeans2D [P,3]
+ *   (z = 0; NULL ok), dL_dcolors [P,3] (NULL ok unless colors_precomp), dL_dopacity [P], dL_dmeans3D [P,3],
+ *   dL_dcov3D [P,6] (NULL ok unless cov3D_precomp), dL_dsh [P,M,3] (NULL ok with colors_precomp),
  *   dL_dscales [P,3], dL_drots [P,4] (NULL ok with cov3D_precomp), dL_dtau [P,6] = (rho, theta) per Gaussian
  *   (NULL ok), dL_dtau_sum [6] = the sum over Gaussians that upstream forms in Python
  *   (`grad_tau.view(-1,6).sum(0)`) (NULL ok).

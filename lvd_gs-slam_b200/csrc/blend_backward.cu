@@ -138,6 +138,17 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
             if (!(ry + m.w < 8.f) && !(ry - m.w > 15.f)) yb |= 2u;
             if (yb & 1u) blocks |= xb;
             if (yb & 2u) blocks |= xb << 2;
+            if (blocks) {       // exact ellipse-vs-block test on the survivors of the box test (as in the forward)
+                const float lvl = 2.02f * __logf(255.f * co.w) + 0.02f;
+                const float rA = __fdividef(1.f, co.x), rC = __fdividef(1.f, co.z);
+                uint32_t rest = blocks;
+                while (rest) {
+                    const int r = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    const float X0 = 8.f * (r & 1), Y0 = 8.f * (r >> 1);
+                    if (!ellipse_reaches_rect(rx, ry, co.x, co.y, co.z, rA, rC, lvl, X0, Y0, X0 + 7.f, Y0 + 7.f)) blocks &= ~(1u << r);
+                }
+            }
         }
 #pragma unroll
         for (int r = 0; r < BB_WARPS; ++r) {

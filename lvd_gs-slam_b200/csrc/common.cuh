@@ -82,6 +82,29 @@ constexpr float LOG2E = 1.4426950408889634f;
 // hot loop needs no per-pixel "done" test (dx^2 ~ 1e36 stays finite in float)
 constexpr float PIX_PARKED = 1.0e18f;
 
+// Exact test "does the ellipse {d : A dx^2 + 2B dx dy + C dy^2 <= lvl} around (mx,my) reach the rectangle of pixel centres
+// [X0,X1] x [Y0,Y1]?" -- the minimum of the convex quadratic over the rectangle is 0 if the centre is inside, else it
+// lies on one of the four edges, where it is a clamped 1-D parabola minimum.  Used by the blend staging on the pixel
+// blocks that survive the bounding-box test; `lvl` carries the same 1% + 0.02 slack as the box, so the test stays
+// conservative with respect to the reference's alpha >= 1/255 decision.
+__device__ __forceinline__ bool ellipse_reaches_rect(float mx, float my, float A, float B, float C, float rA, float rC,
+                                                     float lvl, float X0, float Y0, float X1, float Y1) {
+    const float dx0 = X0 - mx, dx1 = X1 - mx, dy0 = Y0 - my, dy1 = Y1 - my;
+    if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) return true;
+    float q = 3.0e38f;
+    {
+        const float t0 = fminf(fmaxf(-B * dx0 * rC, dy0), dy1), t1 = fminf(fmaxf(-B * dx1 * rC, dy0), dy1);
+        q = fminf(q, A * dx0 * dx0 + (2.f * B * dx0 + C * t0) * t0);
+        q = fminf(q, A * dx1 * dx1 + (2.f * B * dx1 + C * t1) * t1);
+    }
+    {
+        const float t0 = fminf(fmaxf(-B * dy0 * rA, dx0), dx1), t1 = fminf(fmaxf(-B * dy1 * rA, dx0), dx1);
+        q = fminf(q, C * dy0 * dy0 + (2.f * B * dy0 + A * t0) * t0);
+        q = fminf(q, C * dy1 * dy1 + (2.f * B * dy1 + A * t1) * t1);
+    }
+    return !(q > lvl);        // NaN -> keep
+}
+
 struct CameraConst {   // staged once per block in shared memory
     float view[16];
     float proj[16];

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
     float dscale[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
     const bool live = i < a.P && a.radii[i] > 0;
-    if (i < a.P) {
+    if (live) {
         // moments of the blend backward -> dL_dmean2D (NDC units), dL_dconic, dL_dopacity (see ACC_STRIDE, common.cuh)
         const float4 *row = reinterpret_cast<const float4 *>(a.acc + (size_t)i * ACC_STRIDE);
         const float4 m0 = row[0], m1 = row[1];
@@ -297,12 +297,15 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
         const bool accum = (a.flags & LVDGS_FLAG_ACCUMULATE) != 0;
 #define PUT(ptr, idx, v) do { if (accum) (ptr)[idx] += (v); else (ptr)[idx] = (v); } while (0)
         const size_t i3 = 3 * (size_t)i;
-        a.dL_dmeans2D[i3] = r0.x; a.dL_dmeans2D[i3 + 1] = r0.y; a.dL_dmeans2D[i3 + 2] = 0.f;
-        PUT(a.dL_dcolors, i3, r2.x); PUT(a.dL_dcolors, i3 + 1, r2.y); PUT(a.dL_dcolors, i3 + 2, r2.z);
+        if (a.dL_dmeans2D) { a.dL_dmeans2D[i3] = r0.x; a.dL_dmeans2D[i3 + 1] = r0.y; a.dL_dmeans2D[i3 + 2] = 0.f; }
+      if (live || !accum) {       // a culled Gaussian adds nothing: in accumulate mode its rows are not touched at all
+        if (a.dL_dcolors) { PUT(a.dL_dcolors, i3, r2.x); PUT(a.dL_dcolors, i3 + 1, r2.y); PUT(a.dL_dcolors, i3 + 2, r2.z); }
         PUT(a.dL_dopacity, i, r1.y);
         PUT(a.dL_dmeans3D, i3, dmean[0]); PUT(a.dL_dmeans3D, i3 + 1, dmean[1]); PUT(a.dL_dmeans3D, i3 + 2, dmean[2]);
+        if (a.dL_dcov3D) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) PUT(a.dL_dcov3D, 6 * (size_t)i + k, dcov[k]);
+            for (int k = 0; k < 6; ++k) PUT(a.dL_dcov3D, 6 * (size_t)i + k, dcov[k]);
+        }
         if (a.dL_dscales) { PUT(a.dL_dscales, i3, dscale[0]); PUT(a.dL_dscales, i3 + 1, dscale[1]); PUT(a.dL_dscales, i3 + 2, dscale[2]); }
         if (a.dL_drots) {
             float4 *dst = reinterpret_cast<float4 *>(a.dL_drots) + i;
@@ -310,6 +313,7 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
             if (accum) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
             *dst = v;
         }
+      }
         if (a.dL_dtau) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) a.dL_dtau[6 * (size_t)i + k] = tau[k];

@@ -145,8 +145,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         bg, view, proj, praw, campos = ctx.aux
         dev = grad_out_color.device
         f32 = dict(dtype=torch.float32, device=dev)
-        g_means2D = torch.empty(P, 3, **f32); g_colors = torch.empty(P, 3, **f32); g_opac = torch.empty(P, 1, **f32)
-        g_means3D = torch.empty(P, 3, **f32); g_cov = torch.empty(P, 6, **f32)
+        g_means2D = torch.empty(P, 3, **f32); g_opac = torch.empty(P, 1, **f32); g_means3D = torch.empty(P, 3, **f32)
+        g_colors = torch.empty(P, 3, **f32) if cp is not None else None
+        g_cov = torch.empty(P, 6, **f32) if cov is not None else None
         g_sh = torch.empty(P, M, 3, **f32) if shs is not None else None
         g_sc = torch.empty(P, 3, **f32) if cov is None else None
         g_rot = torch.empty(P, 4, **f32) if cov is None else None
@@ -171,8 +172,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         th_shape, rho_shape = ctx.in_shapes
         g_rho = g_tau[:3].reshape(rho_shape) if rho_shape is not None else None
         g_theta = g_tau[3:].reshape(th_shape) if th_shape is not None else None
-        return (g_means3D, g_means2D, g_sh, g_colors if cp is not None else None, g_opac, g_sc, g_rot,
-                g_cov if cov is not None else None, g_theta, g_rho, None)
+        return (g_means3D, g_means2D, g_sh, g_colors, g_opac, g_sc, g_rot, g_cov, g_theta, g_rho, None)
 
 
 class GaussianRasterizer(nn.Module):

@@ -65,8 +65,6 @@ class RasterEngine:
             self.grads[name] = self.grad_flat[off:off + k * P]
             off += k * P
         self.g_means2D = torch.empty(P, 3, **f32)
-        self.g_colors = torch.zeros(P, 3, **f32)
-        self.g_cov = torch.zeros(P, 6, **f32)
         self.g_tau = torch.empty(6, **f32)
         self.R = 0
         self.capacity = 0            # instances the binning arena was last laid out for
@@ -114,8 +112,8 @@ class RasterEngine:
             None, ptr(vc.view), ptr(vc.proj), ptr(vc.proj_raw), ptr(dL_dcolor), ptr(dL_ddepth), ptr(dL_dopacity), ptr(shs),
             ptr(vc.campos), ptr(self.arena[0]), C.c_int64(self.R), C.c_int64(self.capacity), ptr(self.arena[1]),
             ptr(self.arena[2]),
-            ptr(self.scratch), C.c_size_t(self.scratch.numel()), ptr(self.g_means2D), ptr(self.g_colors), ptr(g["opacity"]),
-            ptr(g["means3D"]), ptr(self.g_cov), ptr(g["shs"]), ptr(g["scales"]), ptr(g["rotations"]), None,
+            ptr(self.scratch), C.c_size_t(self.scratch.numel()), ptr(self.g_means2D), None, ptr(g["opacity"]),
+            ptr(g["means3D"]), None, ptr(g["shs"]), ptr(g["scales"]), ptr(g["rotations"]), None,
             ptr(self.g_tau), self.stream())
         _native.check(rc, "lvdgs_rasterize_backward")
 
