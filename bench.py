@@ -176,7 +176,7 @@ def main():
     gc_np, gd_np = synth.make_upstream_grads(cams[0])
     gc, gd = t(gc_np), t(gd_np)
     vcs = {k: ViewCamera(cams[k], dev) for k in my_views}
-    eng = RasterEngine(P, W, H, sh_coeffs=1, sh_degree=0, device=dev)
+    eng = RasterEngine(P, W, H, sh_coeffs=1, sh_degree=0, device=dev, slots=int(os.environ.get("LVDGS_SLOTS", "2")))
 
     def barrier():
         if world > 1:
@@ -184,11 +184,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- value: device-resident, C-ABI engine ----------------
+    my_vcs = [vcs[k] for k in my_views]
+    fixed_upstream = lambda k, slot: (gc, gd, None)           # fixed synthetic dL/dcolor, dL/ddepth
+
     def step_resident():
         eng.zero_grads()
-        for k in my_views:
-            eng.forward(vcs[k], means3D, opac, scales, rots, shs)
-            eng.backward(vcs[k], means3D, opac, scales, rots, shs, gc, gd, accumulate=True)
+        # forward of view k+1 overlaps the backward of view k (two streams, two buffer slots); gradients accumulate
+        eng.run_views(my_vcs, means3D, opac, scales, rots, shs, fixed_upstream)
         mapper.reduce_gradients(eng.grad_flat)                 # SUM over keyframe shards (NCCL / NVLink); no-op at N=1
         mapper.adam_step(eng.grad_flat)                        # identical fused Adam update on every rank
 

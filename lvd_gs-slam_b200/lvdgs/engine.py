@@ -8,6 +8,12 @@ the parameter-gradient block are preallocated, and the parameter gradients of al
 summed inside the backward kernel (LVDGS_FLAG_ACCUMULATE) into ONE contiguous float32 block
   [means3D 3 | features 3M | opacity 1 | scales 3 | rotations 4]  (per-array contiguous, back to back)
 which is exactly the buffer the multi-GPU mapping step hands to NCCL (no pack kernel).
+
+Views of one mapping iteration are independent given the map (utils/slam_backend.py:180-300 renders them one after
+the other only because the reference has one stream).  `run_views` therefore software-pipelines them over two CUDA
+streams and two buffer slots: the forward of view k+1 (preprocess, binning, six latency-bound sort passes, blend)
+runs on the forward stream while the backward of view k (issue-bound blend backward) runs on the backward stream;
+all backwards stay on one stream, so the accumulation into the gradient block is race-free.
 """
 from __future__ import annotations
 
@@ -35,26 +41,48 @@ class ViewCamera:
         self.bg = t(bg)
 
 
+class _Slot:
+    """One in-flight render: opaque arenas, image outputs, per-view gradient outputs."""
+
+    def __init__(self, eng):
+        L, P, W, H, dev = eng.L, eng.P, eng.W, eng.H, eng.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        gl, il = _native.GeomLayout(), _native.ImgLayout()
+        L.lvdgs_get_geom_layout(P, C.byref(gl))
+        L.lvdgs_get_img_layout(W, H, C.byref(il))
+        self.dev = dev
+        self.arena = {0: torch.empty(gl.total, **u8), 1: torch.empty(1 << 20, **u8), 2: torch.empty(il.total, **u8)}
+        self.scratch = torch.empty(L.lvdgs_backward_scratch_bytes(P, 0), **u8)
+        self.cb = _native.RESIZE_FN(self._resize)
+        self.color = torch.empty(3, H, W, **f32)
+        self.depth = torch.empty(1, H, W, **f32)
+        self.opacity = torch.empty(1, H, W, **f32)
+        self.radii = torch.empty(P, dtype=torch.int32, device=dev)
+        self.n_touched = torch.empty(P, dtype=torch.int32, device=dev)
+        self.g_means2D = torch.empty(P, 3, **f32)
+        self.g_tau = torch.empty(6, **f32)
+        self.R = 0
+        self.capacity = 0            # instances the binning arena was last laid out for
+        self.hint = 0                # speculative-launch capacity hint for the next forward
+
+    def _resize(self, _user, which, nbytes):
+        buf = self.arena[int(which)]
+        if buf.numel() < nbytes:                       # geometric growth; steady state never allocates
+            buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.dev)
+            self.arena[int(which)] = buf
+        return buf.data_ptr()
+
+
 class RasterEngine:
-    def __init__(self, P: int, W: int, H: int, sh_coeffs: int = 1, sh_degree: int = 0, device="cuda", flags: int = 0):
+    def __init__(self, P: int, W: int, H: int, sh_coeffs: int = 1, sh_degree: int = 0, device="cuda", flags: int = 0,
+                 slots: int = 2):
         self.L = _native.lib()
         self.dev = torch.device(device)
         self.P, self.W, self.H, self.M, self.D = P, W, H, sh_coeffs, sh_degree
         self.flags = flags
         f32 = dict(dtype=torch.float32, device=self.dev)
-        gl, il = _native.GeomLayout(), _native.ImgLayout()
-        self.L.lvdgs_get_geom_layout(P, C.byref(gl))
-        self.L.lvdgs_get_img_layout(W, H, C.byref(il))
-        u8 = dict(dtype=torch.uint8, device=self.dev)
-        self.arena = {0: torch.empty(gl.total, **u8), 1: torch.empty(1 << 20, **u8), 2: torch.empty(il.total, **u8)}
-        self.scratch = torch.empty(self.L.lvdgs_backward_scratch_bytes(P, 0), **u8)
-        self._cb = _native.RESIZE_FN(self._resize)
-        # outputs
-        self.color = torch.empty(3, H, W, **f32)
-        self.depth = torch.empty(1, H, W, **f32)
-        self.opacity = torch.empty(1, H, W, **f32)
-        self.radii = torch.empty(P, dtype=torch.int32, device=self.dev)
-        self.n_touched = torch.empty(P, dtype=torch.int32, device=self.dev)
+        self.slots = [_Slot(self) for _ in range(max(1, slots))]
         # gradient block (contiguous; one NCCL message)
         sizes = [("means3D", 3), ("shs", 3 * sh_coeffs), ("opacity", 1), ("scales", 3), ("rotations", 4)]
         total = sum(k for _, k in sizes) * P
@@ -64,65 +92,98 @@ class RasterEngine:
         for name, k in sizes:
             self.grads[name] = self.grad_flat[off:off + k * P]
             off += k * P
-        self.g_means2D = torch.empty(P, 3, **f32)
-        self.g_tau = torch.empty(6, **f32)
-        self.R = 0
-        self.capacity = 0            # instances the binning arena was last laid out for
-        self.hint = 0                # speculative-launch capacity hint for the next forward
+        self.s_fwd = torch.cuda.Stream(self.dev, priority=-1)     # short latency-bound kernels get SM slots first
+        self.s_bwd = torch.cuda.Stream(self.dev)
         if self.dev.index is not None:
             self.L.lvdgs_set_device(self.dev.index)
 
-    def _resize(self, _user, which, nbytes):
-        buf = self.arena[int(which)]
-        if buf.numel() < nbytes:                       # geometric growth; steady state never allocates
-            buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.dev)
-            self.arena[int(which)] = buf
-        return buf.data_ptr()
+    # ---- slot 0 shortcuts (single-view use) ----
+    color = property(lambda self: self.slots[0].color)
+    depth = property(lambda self: self.slots[0].depth)
+    opacity = property(lambda self: self.slots[0].opacity)
+    radii = property(lambda self: self.slots[0].radii)
+    n_touched = property(lambda self: self.slots[0].n_touched)
+    g_means2D = property(lambda self: self.slots[0].g_means2D)
+    g_tau = property(lambda self: self.slots[0].g_tau)
+    R = property(lambda self: self.slots[0].R)
+    arena = property(lambda self: self.slots[0].arena)
 
-    def _params(self, vc: ViewCamera, flags):
+    def _params(self, vc, flags):
         return RasterParams(P=self.P, sh_degree=self.D, sh_coeffs=self.M, width=vc.W, height=vc.H,
                             tan_fovx=vc.tanfovx, tan_fovy=vc.tanfovy, scale_modifier=1.0, prefiltered=0, debug=0,
                             flags=flags)
 
-    def stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+    def _stream(self, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        return C.c_void_p(s.cuda_stream)
 
-    def forward(self, vc: ViewCamera, means3D, opacities, scales, rotations, shs):
+    def forward(self, vc, means3D, opacities, scales, rotations, shs, slot: int = 0, stream=None):
+        sl = self.slots[slot]
         R = C.c_int64(0)
         cap = C.c_int64(0)
         prm = self._params(vc, self.flags)
         rc = self.L.lvdgs_rasterize_forward(C.byref(prm), ptr(vc.bg), ptr(means3D), None, ptr(opacities), ptr(scales),
                                             ptr(rotations), None, ptr(vc.view), ptr(vc.proj), ptr(vc.proj_raw), ptr(shs),
-                                            ptr(vc.campos), self._cb, None, C.c_int64(self.hint), ptr(self.color),
-                                            ptr(self.radii), ptr(self.depth), ptr(self.opacity), ptr(self.n_touched),
-                                            C.byref(R), C.byref(cap), self.stream())
+                                            ptr(vc.campos), sl.cb, None, C.c_int64(sl.hint), ptr(sl.color),
+                                            ptr(sl.radii), ptr(sl.depth), ptr(sl.opacity), ptr(sl.n_touched),
+                                            C.byref(R), C.byref(cap), self._stream(stream))
         _native.check(rc, "lvdgs_rasterize_forward")
-        self.R = int(R.value)
-        self.capacity = int(cap.value)
-        self.hint = max(int(self.R * 1.25) + 65536, int(self.hint * 0.98))
-        return self.R
+        sl.R = int(R.value)
+        sl.capacity = int(cap.value)
+        sl.hint = max(int(sl.R * 1.25) + 65536, int(sl.hint * 0.98))
+        return sl.R
 
-    def backward(self, vc: ViewCamera, means3D, opacities, scales, rotations, shs, dL_dcolor, dL_ddepth=None,
-                 dL_dopacity=None, accumulate=True):
+    def backward(self, vc, means3D, opacities, scales, rotations, shs, dL_dcolor, dL_ddepth=None,
+                 dL_dopacity=None, accumulate=True, slot: int = 0, stream=None):
+        sl = self.slots[slot]
         flags = self.flags | (FLAG_ACCUMULATE if accumulate else 0)
         prm = self._params(vc, flags)
         g = self.grads
         rc = self.L.lvdgs_rasterize_backward(
-            C.byref(prm), ptr(vc.bg), ptr(means3D), ptr(self.radii), None, ptr(opacities), ptr(scales), ptr(rotations),
+            C.byref(prm), ptr(vc.bg), ptr(means3D), ptr(sl.radii), None, ptr(opacities), ptr(scales), ptr(rotations),
             None, ptr(vc.view), ptr(vc.proj), ptr(vc.proj_raw), ptr(dL_dcolor), ptr(dL_ddepth), ptr(dL_dopacity), ptr(shs),
-            ptr(vc.campos), ptr(self.arena[0]), C.c_int64(self.R), C.c_int64(self.capacity), ptr(self.arena[1]),
-            ptr(self.arena[2]),
-            ptr(self.scratch), C.c_size_t(self.scratch.numel()), ptr(self.g_means2D), None, ptr(g["opacity"]),
+            ptr(vc.campos), ptr(sl.arena[0]), C.c_int64(sl.R), C.c_int64(sl.capacity), ptr(sl.arena[1]),
+            ptr(sl.arena[2]), ptr(sl.scratch), C.c_size_t(sl.scratch.numel()), ptr(sl.g_means2D), None, ptr(g["opacity"]),
             ptr(g["means3D"]), None, ptr(g["shs"]), ptr(g["scales"]), ptr(g["rotations"]), None,
-            ptr(self.g_tau), self.stream())
+            ptr(sl.g_tau), self._stream(stream))
         _native.check(rc, "lvdgs_rasterize_backward")
+
+    def run_views(self, vcs, means3D, opacities, scales, rotations, shs, upstream, on_view=None):
+        """Forward + backward of several views with gradients accumulated into `grad_flat`, software-pipelined over the
+        forward / backward streams and the buffer slots.  `upstream(k, slot)` is called on the backward stream after
+        view k's forward has finished and returns (dL_dcolor, dL_ddepth, dL_dopacity) for it -- the place where a caller
+        computes its loss from `slot.color/depth/opacity`.  `on_view(k, slot)` (optional) runs on the backward stream
+        after view k's backward (e.g. densification statistics from slot.g_means2D / slot.radii)."""
+        cur = torch.cuda.current_stream(self.dev)
+        n = len(self.slots)
+        start = torch.cuda.Event(); start.record(cur)
+        self.s_fwd.wait_event(start); self.s_bwd.wait_event(start)
+        bwd_done = [None] * n
+        for k, vc in enumerate(vcs):
+            s = k % n
+            if bwd_done[s] is not None:
+                self.s_fwd.wait_event(bwd_done[s])                 # slot s is free again
+            self.forward(vc, means3D, opacities, scales, rotations, shs, slot=s, stream=self.s_fwd)
+            fwd_done = torch.cuda.Event(); fwd_done.record(self.s_fwd)
+            self.s_bwd.wait_event(fwd_done)
+            with torch.cuda.stream(self.s_bwd):
+                gc, gd, go = upstream(k, self.slots[s])
+                self.backward(vc, means3D, opacities, scales, rotations, shs, gc, gd, go, accumulate=True, slot=s,
+                              stream=self.s_bwd)
+                if on_view is not None:
+                    on_view(k, self.slots[s])
+            bwd_done[s] = torch.cuda.Event(); bwd_done[s].record(self.s_bwd)
+        end = torch.cuda.Event(); end.record(self.s_bwd)
+        cur.wait_event(end)
+        endf = torch.cuda.Event(); endf.record(self.s_fwd)
+        cur.wait_event(endf)
 
     def zero_grads(self):
         self.grad_flat.zero_()
 
-    def pair_count(self):
+    def pair_count(self, slot: int = 0):
         """Sum over pixels of n_contrib of the last forward = blended (pixel, Gaussian) pairs the backward visits."""
         il = _native.ImgLayout()
         self.L.lvdgs_get_img_layout(self.W, self.H, C.byref(il))
-        nc = self.arena[2][il.n_contrib:il.n_contrib + 4 * self.W * self.H].view(torch.int32)
+        nc = self.slots[slot].arena[2][il.n_contrib:il.n_contrib + 4 * self.W * self.H].view(torch.int32)
         return int(nc.sum().item())
