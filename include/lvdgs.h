@@ -81,6 +81,7 @@ typedef struct lvdgs_img_layout {
     size_t final_T;        /* float  [H*W] */
     size_t n_contrib;      /* uint32 [H*W] */
     size_t ranges;         /* uint2  [tiles] */
+    size_t tile_order;     /* uint32 [tiles] tile ids, heaviest lists first: launch order of the blend kernels */
     size_t tile_grid;      /* int32  [(gy+1)*(gx+1)] difference array -> per-tile instance counts */
     size_t sort_hist;      /* uint32 [8][256] exclusive-scanned digit histograms of the sort keys */
     size_t total;

@@ -77,6 +77,7 @@ static void img_layout(int32_t W, int32_t H, lvdgs_img_layout &l) {
     l.n_contrib = o; o += align_up(n * sizeof(uint32_t));
     l.ranges = o; o += align_up(tiles * sizeof(uint2));
     const size_t gridn = (size_t)((W + TILE - 1) / TILE + 1) * (size_t)((H + TILE - 1) / TILE + 1);
+    l.tile_order = o; o += align_up(tiles * sizeof(uint32_t));
     l.tile_grid = o; o += align_up(gridn * sizeof(int32_t));
     l.sort_hist = o; o += align_up(SORT_MAX_PASSES * SORT_BINS * sizeof(uint32_t));
     l.total = o;
@@ -107,7 +108,7 @@ static ImgPtrs img_ptrs(void *base, int32_t W, int32_t H) {
     char *b = (char *)base;
     ImgPtrs p;
     p.final_T = (float *)(b + l.final_T); p.n_contrib = (uint32_t *)(b + l.n_contrib); p.ranges = (uint2 *)(b + l.ranges);
-    p.tile_grid = (int32_t *)(b + l.tile_grid); p.sort_hist = (uint32_t *)(b + l.sort_hist);
+    p.tile_order = (uint32_t *)(b + l.tile_order); p.tile_grid = (int32_t *)(b + l.tile_grid); p.sort_hist = (uint32_t *)(b + l.sort_hist);
     return p;
 }
 
@@ -188,7 +189,7 @@ static int launch_bin_and_blend(const lvdgs_raster_params &p, const GeomPtrs &g,
     if (launch_sort_pairs(capacity, R_dev, b.keys[0], b.keys[1], b.vals[0], b.vals[1], end_bit, b.sort_ws,
                           sort_workspace_bytes(capacity), im.sort_hist, &sel, s)) return 1;
     LVDGS_CHECK(cudaMemcpyAsync(b.sorted_sel, &sel, sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    return launch_blend_forward(W, H, capacity, R_dev, im.ranges, b.vals[sel], g, background, out_color, out_depth, out_opacity,
+    return launch_blend_forward(W, H, capacity, R_dev, im.ranges, b.vals[sel], g, im.tile_order, background, out_color, out_depth, out_opacity,
                                 im.final_T, im.n_contrib, n_touched, s);
 }
 
@@ -230,7 +231,7 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     if (p.P == 0) {     // empty map: background only
         LVDGS_CHECK(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)gx * gy, s));
         GeomPtrs g{};
-        return launch_blend_forward(W, H, 0, nullptr, im.ranges, nullptr, g, background, out_color, out_depth, out_opacity, im.final_T,
+        return launch_blend_forward(W, H, 0, nullptr, im.ranges, nullptr, g, nullptr, background, out_color, out_depth, out_opacity, im.final_T,
                                     im.n_contrib, n_touched, s);
     }
     if (!t_pinned_R) {
@@ -320,7 +321,7 @@ int lvdgs_rasterize_backward(const lvdgs_raster_params *prm, const float *backgr
         const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
         const int passes = (32 + tile_bits((uint32_t)(gx * gy)) + 7) / 8;
         const int sel = passes & 1;
-        if (launch_blend_backward(p.P, W, H, R, im.ranges, b.vals[sel], g, background, im.final_T, im.n_contrib,
+        if (launch_blend_backward(p.P, W, H, R, im.ranges, b.vals[sel], im.tile_order, g, background, im.final_T, im.n_contrib,
                                   dL_dout_color, dL_dout_depth, dL_dout_opacity, p.flags, bg, s)) return 1;
     }
     if (launch_preprocess_backward(p, means3D, radii, shs, scales, rotations, cov3D_precomp, viewmatrix, projmatrix,

@@ -16,8 +16,15 @@
 
 namespace lvdgs {
 
-constexpr int BB_THREADS = 128;
-constexpr int BB_WARPS = BB_THREADS / 32;      // 4 warps = 2 x 2 blocks of 8 x 8 pixels
+// PPT = pixels per thread (rows y, y+4, ...): a warp owns an 8 x (4*PPT) pixel block, a CTA of 8/PPT warps the tile.
+// PPT = 2 -> 4 warps, 8x8 blocks (finer culling); PPT = 4 -> 2 warps, 8x16 blocks (one reduction per 128 pairs).
+#ifndef LVDGS_BB_PPT
+#define LVDGS_BB_PPT 2
+#endif
+constexpr int BB_PPT = LVDGS_BB_PPT;
+constexpr int BB_WARPS = 8 / BB_PPT;
+constexpr int BB_THREADS = BB_WARPS * 32;
+constexpr int BB_ROWS = 4 * BB_PPT;            // pixel rows per warp block
 
 // After the call v[0] of lane L holds the warp-wide sum of slot ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
 __device__ __forceinline__ void transpose_reduce16(float (&v)[16], int lane) {
@@ -60,7 +67,7 @@ __device__ __forceinline__ void transpose_reduce16(float (&v)[16], int lane) {
 __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     int W, int H, int gx, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
     const float4 *__restrict__ means2D, const float4 *__restrict__ conic_opacity, const float4 *__restrict__ rgbd,
-    const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
+    const uint32_t *__restrict__ tile_order, const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
     const float *__restrict__ dL_dout_color, const float *__restrict__ dL_dout_depth,
     const float *__restrict__ dL_dout_opacity, float *__restrict__ acc) {
     __shared__ uint32_t s_id[BB_THREADS];
@@ -70,23 +77,24 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     __shared__ uint32_t s_mask[BB_WARPS][BB_WARPS];     // [staging warp][pixel block]
     __shared__ uint32_t s_top[BB_WARPS];
 
-    const int tile = blockIdx.y * gx + blockIdx.x;
+    const int tile = tile_order ? (int)__ldg(tile_order + blockIdx.x) : (int)blockIdx.x;   // heaviest tiles first
+    const int tile_x = tile % gx, tile_y = tile / gx;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bx = warp & 1, by = warp >> 1;
-    const int px = blockIdx.x * TILE + bx * 8 + (lane & 7);
-    const int py0 = blockIdx.y * TILE + by * 8 + (lane >> 3);
+    const int px = tile_x * TILE + bx * 8 + (lane & 7);
+    const int py0 = tile_y * TILE + by * BB_ROWS + (lane >> 3);
     const float pfx = (float)px;
-    const float tx0 = (float)(blockIdx.x * TILE), ty0 = (float)(blockIdx.y * TILE);
+    const float tx0 = (float)(tile_x * TILE), ty0 = (float)(tile_y * TILE);
     const size_t HW = (size_t)H * W;
     const uint2 range = ranges[tile];
     const uint32_t a_id = smem_u32(s_id), a_xy = smem_u32(s_xy), a_q = smem_u32(s_co), a_cd = smem_u32(s_cd);
 
-    // per-pixel state (q = 0: row py0, q = 1: row py0 + 4)
-    float pfy[2], T[2], Tf[2], dp0[2], dp1[2], dp2[2], dpd[2], bgd[2], B0[2], B1[2], B2[2], Bd[2];
-    uint32_t last[2];
+    // per-pixel state (pixel q of this thread is in row py0 + 4q)
+    float pfy[BB_PPT], T[BB_PPT], Tf[BB_PPT], dp0[BB_PPT], dp1[BB_PPT], dp2[BB_PPT], dpd[BB_PPT], bgd[BB_PPT], B0[BB_PPT], B1[BB_PPT], B2[BB_PPT], Bd[BB_PPT];
+    uint32_t last[BB_PPT];
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < BB_PPT; ++q) {
         const int py = py0 + 4 * q;
         const bool inside = px < W && py < H;
         const size_t pix = (size_t)py * W + px;
@@ -103,7 +111,9 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
         B0[q] = B1[q] = B2[q] = Bd[q] = 0.f;
     }
     // warp-wide and tile-wide max of n_contrib: nothing at or beyond it contributes
-    uint32_t wtop = max(last[0], last[1]);
+    uint32_t wtop = last[0];
+#pragma unroll
+    for (int q = 1; q < BB_PPT; ++q) wtop = max(wtop, last[q]);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) wtop = max(wtop, __shfl_xor_sync(0xffffffffu, wtop, d));
     if (lane == 0) s_top[warp] = wtop;
@@ -134,10 +144,12 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
             uint32_t xb = 0, yb = 0;
             if (!(rx + m.z < 0.f) && !(rx - m.z > 7.f)) xb |= 1u;
             if (!(rx + m.z < 8.f) && !(rx - m.z > 15.f)) xb |= 2u;
-            if (!(ry + m.w < 0.f) && !(ry - m.w > 7.f)) yb |= 1u;
-            if (!(ry + m.w < 8.f) && !(ry - m.w > 15.f)) yb |= 2u;
-            if (yb & 1u) blocks |= xb;
-            if (yb & 2u) blocks |= xb << 2;
+#pragma unroll
+            for (int r = 0; r < BB_WARPS / 2; ++r)
+                if (!(ry + m.w < (float)(BB_ROWS * r)) && !(ry - m.w > (float)(BB_ROWS * r + BB_ROWS - 1))) yb |= 1u << r;
+#pragma unroll
+            for (int r = 0; r < BB_WARPS / 2; ++r)
+                if (yb & (1u << r)) blocks |= xb << (2 * r);
             if (blocks) {       // exact ellipse-vs-block test on the survivors of the box test (as in the forward)
                 const float lvl = 2.02f * __logf(255.f * co.w) + 0.02f;
                 const float rA = __fdividef(1.f, co.x), rC = __fdividef(1.f, co.z);
@@ -145,8 +157,8 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 while (rest) {
                     const int r = __ffs(rest) - 1;
                     rest &= rest - 1;
-                    const float X0 = 8.f * (r & 1), Y0 = 8.f * (r >> 1);
-                    if (!ellipse_reaches_rect(rx, ry, co.x, co.y, co.z, rA, rC, lvl, X0, Y0, X0 + 7.f, Y0 + 7.f)) blocks &= ~(1u << r);
+                    const float X0 = 8.f * (r & 1), Y0 = (float)(BB_ROWS * (r >> 1));
+                    if (!ellipse_reaches_rect(rx, ry, co.x, co.y, co.z, rA, rC, lvl, X0, Y0, X0 + 7.f, Y0 + (float)(BB_ROWS - 1))) blocks &= ~(1u << r);
                 }
             }
         }
@@ -158,12 +170,15 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
         __syncthreads();
         for (int wp = 0; wp < BB_WARPS; ++wp) {
             uint32_t mask = s_mask[wp][warp];
+            {   // entries with contributor index >= wtop (j < remaining - wtop) contribute to no pixel of this warp
+                const int first_j = remaining - (int)wtop - wp * 32;
+                if (first_j >= 32) mask = 0; else if (first_j > 0) mask &= ~((1u << first_j) - 1u);
+            }
             while (mask) {
                 const int b = __ffs(mask) - 1;
                 mask &= mask - 1;
                 const int j = wp * 32 + b;
                 const uint32_t k = (uint32_t)(remaining - 1 - j);    // contributor index (0-based) of this entry
-                if (k >= wtop) continue;                             // warp-uniform
                 const float2 xy = lds64(a_xy + j * 8);
                 const float4 co = lds128(a_q + j * 16);
                 const float4 cd = lds128(a_cd + j * 16);
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 for (int i = 0; i < 16; ++i) v[i] = 0.f;
                 bool valid = false;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < BB_PPT; ++q) {
                     if (k < last[q]) {
                         const float dy = xy.y - pfy[q];
                         const float p2 = fmaf(co.z * dy, dy, dx * fmaf(co.x, dx, co.y * dy));
@@ -183,12 +198,13 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                             if (alpha >= 1.f / 255.f) {
                                 valid = true;
                                 const float one_m = 1.f - alpha;
-                                T[q] = __fdividef(T[q], one_m);
+                                const float inv = __fdividef(1.f, one_m);
+                                T[q] *= inv;
                                 const float wgt = alpha * T[q];
                                 float dL_dalpha = (cd.x - B0[q]) * dp0[q] + (cd.y - B1[q]) * dp1[q] +
                                                   (cd.z - B2[q]) * dp2[q] + (cd.w - Bd[q]) * dpd[q];
                                 dL_dalpha *= T[q];
-                                dL_dalpha += __fdividef(-Tf[q], one_m) * bgd[q];
+                                dL_dalpha -= Tf[q] * inv * bgd[q];
                                 B0[q] = alpha * cd.x + one_m * B0[q];
                                 B1[q] = alpha * cd.y + one_m * B1[q];
                                 B2[q] = alpha * cd.z + one_m * B2[q];
@@ -214,7 +230,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
 }
 
 int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, const uint32_t *point_list,
-                          const GeomPtrs &g, const float *bg, const float *final_T, const uint32_t *n_contrib,
+                          const uint32_t *tile_order, const GeomPtrs &g, const float *bg, const float *final_T, const uint32_t *n_contrib,
                           const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_opacity,
                           int flags, const BlendGradPtrs &o, cudaStream_t s) {
     (void)P;
@@ -222,8 +238,8 @@ int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, c
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const float *dop = (flags & LVDGS_FLAG_OPACITY_GRAD) ? dL_dout_opacity : nullptr;
     LVDGS_PRE(s);
-    blend_backward_kernel<<<dim3(gx, gy), BB_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
-                                                               g.rgbd, bg, final_T, n_contrib, dL_dout_color,
+    blend_backward_kernel<<<gx * gy, BB_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
+                                                               g.rgbd, tile_order, bg, final_T, n_contrib, dL_dout_color,
                                                                dL_dout_depth, dop, o.acc);
     LVDGS_LAUNCHED(s, "blend_backward");
     return 0;

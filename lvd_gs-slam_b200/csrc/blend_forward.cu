@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
                                                                    const uint32_t *__restrict__ point_list,
                                                                    const float4 *__restrict__ means2D,
                                                                    const float4 *__restrict__ conic_opacity,
-                                                                   const float4 *__restrict__ rgbd, const float *__restrict__ bg,
-                                                                   float *__restrict__ out_color, float *__restrict__ out_depth,
+                                                                   const float4 *__restrict__ rgbd, const uint32_t *__restrict__ tile_order,
+                                                                   const float *__restrict__ bg, float *__restrict__ out_color, float *__restrict__ out_depth,
                                                                    float *__restrict__ out_opacity, float *__restrict__ final_T,
                                                                    uint32_t *__restrict__ n_contrib, int32_t *__restrict__ n_touched) {
     __shared__ uint32_t s_id[BF_THREADS];
@@ -35,16 +35,17 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
     __shared__ float4 s_cd[BF_THREADS];
     __shared__ uint32_t s_mask[BF_WARPS][BF_WARPS];     // [staging warp][pixel block]
 
-    const int tile = blockIdx.y * gx + blockIdx.x;
+    const int tile = tile_order ? (int)__ldg(tile_order + blockIdx.x) : (int)blockIdx.x;   // heaviest tiles first
+    const int tile_x = tile % gx, tile_y = tile / gx;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bx = warp & 1, by = warp >> 1;                       // this warp's 8x4 block inside the tile
-    const int px = blockIdx.x * TILE + bx * 8 + (lane & 7);
-    const int py = blockIdx.y * TILE + by * 4 + (lane >> 3);
+    const int px = tile_x * TILE + bx * 8 + (lane & 7);
+    const int py = tile_y * TILE + by * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
     float pfx = inside ? (float)px : PIX_PARKED;                   // parked pixels see alpha = 0 for every Gaussian
     const float pfy = (float)py;
     const uint32_t a_id = smem_u32(s_id), a_xy = smem_u32(s_xy), a_q = smem_u32(s_co), a_cd = smem_u32(s_cd);
-    const float tx0 = (float)(blockIdx.x * TILE), ty0 = (float)(blockIdx.y * TILE);   // tile's first pixel centre
+    const float tx0 = (float)(tile_x * TILE), ty0 = (float)(tile_y * TILE);   // tile's first pixel centre
 
     // a speculative launch whose capacity hint was too small has no valid sorted list (the sort retires, see
     // radix_sort.cu); its output is discarded and the tail re-run by the host, so do nothing here
@@ -140,12 +141,12 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
 }
 
 int launch_blend_forward(int W, int H, int64_t capacity, const uint32_t *n_dev, const uint2 *ranges, const uint32_t *point_list, const GeomPtrs &g,
-                         const float *bg, float *out_color, float *out_depth, float *out_opacity, float *final_T,
+                         const uint32_t *tile_order, const float *bg, float *out_color, float *out_depth, float *out_opacity, float *final_T,
                          uint32_t *n_contrib, int32_t *n_touched, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     LVDGS_PRE(s);
-    blend_forward_kernel<<<dim3(gx, gy), BF_THREADS, 0, s>>>(W, H, gx, (uint32_t)min(capacity, (int64_t)0xffffffffll), n_dev, ranges, point_list, g.means2D, g.conic_opacity,
-                                                              g.rgbd, bg, out_color, out_depth, out_opacity, final_T,
+    blend_forward_kernel<<<gx * gy, BF_THREADS, 0, s>>>(W, H, gx, (uint32_t)min(capacity, (int64_t)0xffffffffll), n_dev, ranges, point_list, g.means2D, g.conic_opacity,
+                                                              g.rgbd, tile_order, bg, out_color, out_depth, out_opacity, final_T,
                                                               n_contrib, n_touched);
     LVDGS_LAUNCHED(s, "blend_forward");
     return 0;

@@ -135,6 +135,7 @@ struct BinPtrs {
 struct ImgPtrs {
     float *final_T; uint32_t *n_contrib; uint2 *ranges;
     int32_t *tile_grid;               // [(gy+1)*(gx+1)] 2-D difference array of the tile rects -> per-tile instance counts
+    uint32_t *tile_order;             // [tiles] tile ids, heaviest instance lists first (launch order of the blend kernels)
     uint32_t *sort_hist;              // [8][256] digit histograms of the (tile|depth) keys, exclusive-scanned by binning_prep
 };
 constexpr int SORT_MAX_PASSES = 8;
@@ -156,8 +157,8 @@ int launch_sort_pairs(int64_t n, const uint32_t *n_dev, uint64_t *keys0, uint64_
                       cudaStream_t s);
 
 int launch_blend_forward(int W, int H, int64_t capacity, const uint32_t *n_dev, const uint2 *ranges, const uint32_t *point_list, const GeomPtrs &g,
-                         const float *bg, float *out_color, float *out_depth, float *out_opacity,
-                         float *final_T, uint32_t *n_contrib, int32_t *n_touched, cudaStream_t s);
+                         const uint32_t *tile_order, const float *bg, float *out_color, float *out_depth,
+                         float *out_opacity, float *final_T, uint32_t *n_contrib, int32_t *n_touched, cudaStream_t s);
 
 // Per-Gaussian accumulators produced by the blend backward: one 48-byte row per Gaussian so that a warp can
 // commit its partial sums with three 128-bit vector reductions (red.global.add.v4.f32).
@@ -172,7 +173,7 @@ struct BlendGradPtrs {
     float *acc;          // [P][ACC_STRIDE], zeroed by the API before the blend backward
 };
 int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, const uint32_t *point_list,
-                          const GeomPtrs &g, const float *bg, const float *final_T, const uint32_t *n_contrib,
+                          const uint32_t *tile_order, const GeomPtrs &g, const float *bg, const float *final_T, const uint32_t *n_contrib,
                           const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_opacity,
                           int flags, const BlendGradPtrs &o, cudaStream_t s);
 

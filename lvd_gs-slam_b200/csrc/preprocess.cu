@@ -332,7 +332,15 @@ __global__ void __launch_bounds__(COUNT_THREADS) binning_count_kernel(int P, int
             if (s_grid[k]) atomicAdd(grid_g + k, s_grid[k]);
 }
 
-constexpr int PREP_THREADS = 1024;     // difference-array cells integrated in shared memory (covers 1920x1080: 121 x 69)
+constexpr int PREP_THREADS = 1024;
+constexpr int WORK_BUCKETS = 128;
+// bucket 0 = heaviest: 4 buckets per octave of the list length, descending
+__device__ __forceinline__ int work_bucket(uint32_t c) {
+    if (c == 0) return WORK_BUCKETS - 1;
+    const int l2 = 31 - __clz(c);
+    const int frac = l2 >= 2 ? (int)((c >> (l2 - 2)) & 3u) : 0;
+    return max(0, WORK_BUCKETS - 2 - (l2 * 4 + frac));
+}     // difference-array cells integrated in shared memory (covers 1920x1080: 121 x 69)
 
 // block-wide inclusive scan of one value per thread (1024 threads); returns the inclusive value, total via s_ws[31]
 __device__ __forceinline__ uint32_t prep_incl_scan(uint32_t c, uint32_t *s_ws) {
@@ -361,12 +369,14 @@ __device__ __forceinline__ uint32_t prep_incl_scan(uint32_t c, uint32_t *s_ws) {
 __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int gy, int passes, int end_bit, int nblocks,
                                                                     int32_t *__restrict__ grid_g, uint2 *__restrict__ ranges,
                                                                     uint32_t *__restrict__ hist, uint32_t *__restrict__ block_sums,
-                                                                    uint32_t *__restrict__ R_out) {
+                                                                    uint32_t *__restrict__ R_out, uint32_t *__restrict__ tile_order) {
     extern __shared__ int32_t s_grid[];
     __shared__ uint32_t s_h[SORT_MAX_PASSES * SORT_BINS];
     __shared__ uint32_t s_ws[32];
     __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_bucket[WORK_BUCKETS];
     const int gw = gx + 1, cells = gw * (gy + 1), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < WORK_BUCKETS) s_bucket[tid] = 0;
     const bool in_smem = cells <= PREP_GRID_SMEM;
     int32_t *grid = in_smem ? s_grid : grid_g;
     for (int k = tid; k < SORT_MAX_PASSES * SORT_BINS; k += PREP_THREADS) s_h[k] = k < 4 * SORT_BINS ? hist[k] : 0u;
@@ -406,6 +416,7 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
         const uint32_t start = s_carry + incl - c;
         if (t < tiles) {
             ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
+            atomicAdd(&s_bucket[work_bucket(c)], 1u);
             if (c) {
                 for (int q = 4; q < passes; ++q) {
                     const int shift = 8 * (q - 4), nb = min(8, end_bit - 8 * q);
@@ -416,6 +427,17 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
         __syncthreads();
         if (tid == 0) s_carry += s_ws[31];
         __syncthreads();
+    }
+    // (c') tile launch order for the blend kernels: heaviest lists first (longest-processing-time-first keeps the tail of
+    // the launch short); a counting sort over ~quarter-octave buckets of the list length is plenty
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int b = 0; b < WORK_BUCKETS; ++b) { const uint32_t n = s_bucket[b]; s_bucket[b] = run; run += n; }
+    }
+    __syncthreads();
+    for (int t = tid; t < tiles; t += PREP_THREADS) {
+        const uint32_t c = (uint32_t)grid[(t / gx) * gw + (t % gx)];
+        tile_order[atomicAdd(&s_bucket[work_bucket(c)], 1u)] = (uint32_t)t;
     }
     // (d) exclusive scan of every digit histogram: one warp per pass, 8 bins per lane
     if (warp < passes) {
@@ -448,7 +470,7 @@ int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, con
     }
     LVDGS_PRE(s);
     binning_prep_kernel<<<1, PREP_THREADS, dyn, s>>>(gx, gy, passes, end_bit, ceil_div(P, PRE_THREADS), im.tile_grid, im.ranges,
-                                                     im.sort_hist, g.block_sums, g.num_instances);
+                                                     im.sort_hist, g.block_sums, g.num_instances, im.tile_order);
     LVDGS_LAUNCHED(s, "binning_prep");
     return 0;
 }

@@ -16,7 +16,10 @@ namespace lvdgs {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
+#ifndef LVDGS_RS_ITEMS
+#define LVDGS_RS_ITEMS 16
+#endif
+constexpr int RS_ITEMS = LVDGS_RS_ITEMS;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 pairs per block
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
@@ -178,9 +181,15 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
 
     volatile uint32_t *lb = lookback;
     uint32_t excl = 0;
+#ifdef LVDGS_RS_NOLOOKBACK      // timing experiment only: results are wrong
+    if (true) {
+        lb[(size_t)tile * RS_BINS + tid] = total | LB_GLOBAL;
+    } else {
+#else
     if (tile == 0) {
         lb[(size_t)tile * RS_BINS + tid] = total | LB_GLOBAL;
     } else {
+#endif
         lb[(size_t)tile * RS_BINS + tid] = total | LB_LOCAL;
         int64_t t = (int64_t)tile - 1;
         while (true) {

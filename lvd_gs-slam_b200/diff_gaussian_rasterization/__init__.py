@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from typing import NamedTuple
 
 import torch
@@ -49,28 +50,42 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
-def _prep(t, device=None):
+def _prep(t):
     """float32, contiguous, 16-byte aligned CUDA tensor or None (None / empty tensors mean 'not provided')."""
     if t is None or t.numel() == 0:
         return None
-    if t.dtype != torch.float32 or not t.is_contiguous():
-        t = t.contiguous().float()
-    if t.data_ptr() % 16:
-        t = t.clone()
-    return t
+    if t.dtype is torch.float32 and t.is_contiguous() and not (t.data_ptr() & 15):
+        return t
+    t = t.contiguous().float()
+    return t.clone() if t.data_ptr() & 15 else t
 
 
-def _make_resizer(device, store):
-    """ctypes resize callback for the three opaque buffers of the C ABI.  `store` (a plain dict: which -> uint8 tensor)
-    is what the autograd ctx keeps alive; the callback object itself is dropped right after the forward call, so no
-    reference cycle delays the release of the buffers (they are tens of MB each)."""
+def _on(t, dev):
+    return t if t.device == dev else t.to(dev)
 
-    def _resize(_user, which, nbytes):
-        buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
-        store[int(which)] = buf
-        return buf.data_ptr()
 
-    return _native.RESIZE_FN(_resize)
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# One persistent ctypes callback per process; the per-call destination (the dict the autograd ctx keeps alive) is
+# thread-local, so no callback object -- and no reference cycle through it -- is created per render.
+_tls = threading.local()
+
+
+def _resize(_user, which, nbytes):
+    buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=_tls.dev)
+    _tls.store[int(which)] = buf
+    return buf.data_ptr()
+
+
+_RESIZE_CB = _native.RESIZE_FN(_resize)
+
+
+def _select_device(L, dev):
+    if getattr(_tls, "device_index", None) != dev.index and dev.index is not None:
+        L.lvdgs_set_device(dev.index)
+        _tls.device_index = dev.index
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta,
@@ -80,10 +95,9 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
 
 
 def _params(rs: GaussianRasterizationSettings, P: int, M: int) -> _native.RasterParams:
-    return _native.RasterParams(P=P, sh_degree=int(rs.sh_degree), sh_coeffs=M, width=int(rs.image_width),
-                                height=int(rs.image_height), tan_fovx=float(rs.tanfovx), tan_fovy=float(rs.tanfovy),
-                                scale_modifier=float(rs.scale_modifier), prefiltered=int(bool(rs.prefiltered)),
-                                debug=int(bool(rs.debug)), flags=FLAGS)
+    return _native.RasterParams(P, int(rs.sh_degree), M, int(rs.image_width), int(rs.image_height), float(rs.tanfovx),
+                                float(rs.tanfovy), float(rs.scale_modifier), int(bool(rs.prefiltered)),
+                                int(bool(rs.debug)), FLAGS)
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -101,31 +115,32 @@ class _RasterizeGaussians(torch.autograd.Function):
         sc = _prep(scales); rot = _prep(rotations); cov = _prep(cov3Ds_precomp)
         M = 0 if shs is None else shs.shape[1]
         H, W = int(rs.image_height), int(rs.image_width)
-        bg = _prep(rs.bg.to(dev)); view = _prep(rs.viewmatrix.to(dev)); proj = _prep(rs.projmatrix.to(dev))
-        praw = _prep(rs.projmatrix_raw.to(dev)); campos = _prep(rs.campos.to(dev))
-        color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
-        depth = torch.empty(1, H, W, dtype=torch.float32, device=dev)
-        opac_img = torch.empty(1, H, W, dtype=torch.float32, device=dev)
-        radii = torch.empty(P, dtype=torch.int32, device=dev)
-        n_touched = torch.empty(P, dtype=torch.int32, device=dev)
+        bg = _prep(_on(rs.bg, dev)); view = _prep(_on(rs.viewmatrix, dev)); proj = _prep(_on(rs.projmatrix, dev))
+        praw = _prep(_on(rs.projmatrix_raw, dev)); campos = _prep(_on(rs.campos, dev))
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        opac_img = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        n_touched = torch.empty((P,), dtype=torch.int32, device=dev)
         bufs = {}
-        resize_cb = _make_resizer(dev, bufs)
+        _tls.store, _tls.dev = bufs, dev
         prm = _params(rs, P, M)
         R = C.c_int64(0)
         cap = C.c_int64(0)
         hint = _capacity_hint.get(dev.index, 0) if SPECULATIVE else 0
-        if dev.index is not None:
-            L.lvdgs_set_device(dev.index)
-        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        p = _native.ptr
-        rc = L.lvdgs_rasterize_forward(C.byref(prm), p(bg), p(m3), p(cp), p(op), p(sc), p(rot), p(cov), p(view), p(proj),
-                                       p(praw), p(shs), p(campos), resize_cb, None, C.c_int64(hint), p(color), p(radii),
-                                       p(depth), p(opac_img), p(n_touched), C.byref(R), C.byref(cap), stream)
-        del resize_cb
+        _select_device(L, dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        p = _ptr
+        try:
+            rc = L.lvdgs_rasterize_forward(C.byref(prm), p(bg), p(m3), p(cp), p(op), p(sc), p(rot), p(cov), p(view),
+                                           p(proj), p(praw), p(shs), p(campos), _RESIZE_CB, None, hint, p(color),
+                                           p(radii), p(depth), p(opac_img), p(n_touched), C.byref(R), C.byref(cap), stream)
+        finally:
+            _tls.store = None
         _native.check(rc, "lvdgs_rasterize_forward")
         ctx.rs = rs
-        ctx.num_rendered = int(R.value)
-        ctx.capacity = int(cap.value)
+        ctx.num_rendered = R.value
+        ctx.capacity = cap.value
         if SPECULATIVE:   # decay slowly, grow at once
             _capacity_hint[dev.index] = max(int(R.value * 1.25) + 65536, int(hint * 0.98))
         ctx.bufs = bufs
@@ -144,35 +159,42 @@ class _RasterizeGaussians(torch.autograd.Function):
         m3, shs, cp, op, sc, rot, cov, radii = ctx.saved_tensors
         bg, view, proj, praw, campos = ctx.aux
         dev = grad_out_color.device
-        f32 = dict(dtype=torch.float32, device=dev)
-        g_means2D = torch.empty(P, 3, **f32); g_opac = torch.empty(P, 1, **f32); g_means3D = torch.empty(P, 3, **f32)
-        g_colors = torch.empty(P, 3, **f32) if cp is not None else None
-        g_cov = torch.empty(P, 6, **f32) if cov is not None else None
-        g_sh = torch.empty(P, M, 3, **f32) if shs is not None else None
-        g_sc = torch.empty(P, 3, **f32) if cov is None else None
-        g_rot = torch.empty(P, 4, **f32) if cov is None else None
-        g_tau = torch.empty(6, **f32)
-        scratch = torch.empty(L.lvdgs_backward_scratch_bytes(P, ctx.num_rendered), dtype=torch.uint8, device=dev)
+        # one allocation for every gradient tensor (+ the backward scratch), handed out as views
+        widths = [("means2D", 3), ("opac", 1), ("means3D", 3)]
+        if cp is not None: widths.append(("colors", 3))
+        if cov is not None: widths.append(("cov", 6))
+        else: widths += [("sc", 3), ("rot", 4)]
+        if shs is not None: widths.append(("sh", 3 * M))
+        nscratch = (L.lvdgs_backward_scratch_bytes(P, ctx.num_rendered) + 3) // 4
+        pad4 = lambda n: (n + 3) & ~3                  # every view starts 16-byte aligned (float4 stores in the kernels)
+        flat = torch.empty((8 + sum(pad4(w * P) for _, w in widths) + nscratch,), dtype=torch.float32, device=dev)
+        g, off = {}, 8                                # first 8 floats: dL_dtau_sum
+        for name, w in widths:
+            g[name] = flat[off:off + w * P]
+            off += pad4(w * P)
+        flat_s = flat[off:off + nscratch]
+        g_tau = flat[0:6]
         prm = _params(rs, P, M)
-        if dev.index is not None:
-            L.lvdgs_set_device(dev.index)
-        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        p = _native.ptr
+        _select_device(L, dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        p = _ptr
         gc = _prep(grad_out_color)
         gd = _prep(grad_out_depth) if grad_out_depth is not None else None
         go = _prep(grad_out_opacity) if (grad_out_opacity is not None and (FLAGS & 2)) else None
         b = ctx.bufs
         rc = L.lvdgs_rasterize_backward(C.byref(prm), p(bg), p(m3), p(radii), p(cp), p(op), p(sc), p(rot), p(cov), p(view),
                                         p(proj), p(praw), p(gc), p(gd), p(go), p(shs), p(campos), p(b.get(0)),
-                                        C.c_int64(ctx.num_rendered), C.c_int64(ctx.capacity), p(b.get(1)), p(b.get(2)),
-                                        p(scratch),
-                                        C.c_size_t(scratch.numel()), p(g_means2D), p(g_colors), p(g_opac), p(g_means3D),
-                                        p(g_cov), p(g_sh), p(g_sc), p(g_rot), None, p(g_tau), stream)
+                                        ctx.num_rendered, ctx.capacity, p(b.get(1)), p(b.get(2)), p(flat_s),
+                                        flat_s.numel() * 4, p(g["means2D"]), p(g.get("colors")), p(g["opac"]),
+                                        p(g["means3D"]), p(g.get("cov")), p(g.get("sh")), p(g.get("sc")), p(g.get("rot")),
+                                        None, p(g_tau), stream)
         _native.check(rc, "lvdgs_rasterize_backward")
         th_shape, rho_shape = ctx.in_shapes
         g_rho = g_tau[:3].reshape(rho_shape) if rho_shape is not None else None
         g_theta = g_tau[3:].reshape(th_shape) if th_shape is not None else None
-        return (g_means3D, g_means2D, g_sh, g_colors, g_opac, g_sc, g_rot, g_cov, g_theta, g_rho, None)
+        v = lambda name, *shape: g[name].view(*shape) if name in g else None
+        return (v("means3D", P, 3), v("means2D", P, 3), v("sh", P, M, 3), v("colors", P, 3), v("opac", P, 1), v("sc", P, 3),
+                v("rot", P, 4), v("cov", P, 6), g_theta, g_rho, None)
 
 
 class GaussianRasterizer(nn.Module):
