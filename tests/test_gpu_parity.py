@@ -19,6 +19,9 @@ CASES = {
     "kitti30k_bg": dict(cam="kitti", N=30_000, sh=0, bg=(0.3, 0.1, 0.7)),
     "mast3r_sh3": dict(cam="mast3r_kitti", N=8_000, sh=3, bg=(0.0, 0.0, 0.0)),
     "ragged_33x17": dict(cam=None, N=700, sh=1, bg=(0.1, 0.2, 0.3)),
+    # BASELINE.json's full sizes: the headline configuration and the nuScenes-shaped one (configs[3])
+    "kitti500k": dict(cam="kitti", N=500_000, sh=0, bg=(0.0, 0.0, 0.0)),
+    "nuscenes2m": dict(cam="nuscenes", N=2_000_000, sh=0, bg=(0.0, 0.0, 0.0)),
 }
 
 

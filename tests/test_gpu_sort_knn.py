@@ -64,7 +64,7 @@ def test_sort_matches_stable_reference(n, end_bit, dup):
     np.testing.assert_array_equal(vc, vs)
 
 
-@pytest.mark.parametrize("P", [4, 1000, 14_600])
+@pytest.mark.parametrize("P", [4, 1000, 2049, 14_600, 60_000])
 def test_dist2_matches_oracle(P):
     from simple_knn._C import distCUDA2
     rng = np.random.default_rng(P)
@@ -77,3 +77,19 @@ def test_dist2_matches_oracle(P):
     from scipy.spatial import cKDTree
     d, _ = cKDTree(pts.astype(np.float64)).query(pts.astype(np.float64), k=4)
     np.testing.assert_allclose(got, (d[:, 1:] ** 2).mean(1), rtol=1e-4, atol=1e-9)
+
+
+def test_dist2_large_surface_like_cloud_matches_kdtree():
+    """2 M points on a 2.5-D surface (what back-projected keyframe depth maps look like; BASELINE configs[3] size):
+    exactness against cKDTree, the all-pairs oracle being out of reach at this size."""
+    from simple_knn._C import distCUDA2
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(0)
+    P = 2_000_000
+    u, v = rng.uniform(-40, 40, P), rng.uniform(-10, 10, P)
+    z = 20 + 5 * np.sin(0.2 * u) + 0.05 * rng.normal(0, 1, P) + np.where(rng.uniform(0, 1, P) < 0.1, 30.0, 0.0)
+    pts = np.stack([u, v, z], 1).astype(np.float32)
+    got = distCUDA2(torch.tensor(pts, device="cuda")).cpu().numpy()
+    sub = rng.choice(P, 50_000, replace=False)
+    d, _ = cKDTree(pts.astype(np.float64)).query(pts[sub].astype(np.float64), k=4)
+    np.testing.assert_allclose(got[sub], (d[:, 1:] ** 2).mean(1), rtol=2e-4, atol=1e-9)
