@@ -146,8 +146,29 @@ __device__ __forceinline__ void best3_insert(float d, float &b0, float &b1, floa
     }
 }
 
+// second level: AABB of every run of KNN_SUPER consecutive boxes, so that a query rejects 32 boxes with one test
+constexpr int KNN_SUPER = 32;
+__global__ void __launch_bounds__(KNN_THREADS) knn_super_kernel(int nboxes, const float *__restrict__ boxes, float *__restrict__ supers) {
+    const int sidx = blockIdx.x * KNN_THREADS + threadIdx.x;
+    if (sidx * KNN_SUPER >= nboxes) return;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int b = sidx * KNN_SUPER; b < min(nboxes, (sidx + 1) * KNN_SUPER); ++b)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], boxes[6 * b + a]); mx[a] = fmaxf(mx[a], boxes[6 * b + 3 + a]); }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { supers[6 * sidx + a] = mn[a]; supers[6 * sidx + 3 + a] = mx[a]; }
+}
+
+__device__ __forceinline__ float aabb_dist2(const float *__restrict__ bx, float4 q) {
+    const float ex = fmaxf(fmaxf(__ldg(bx + 0) - q.x, q.x - __ldg(bx + 3)), 0.f);
+    const float ey = fmaxf(fmaxf(__ldg(bx + 1) - q.y, q.y - __ldg(bx + 4)), 0.f);
+    const float ez = fmaxf(fmaxf(__ldg(bx + 2) - q.z, q.z - __ldg(bx + 5)), 0.f);
+    return ex * ex + ey * ey + ez * ez;
+}
+
 __global__ void __launch_bounds__(KNN_THREADS) knn_search_kernel(int P, int nboxes, const float4 *__restrict__ sorted,
-                                                                 const float *__restrict__ boxes, float *__restrict__ out) {
+                                                                 const float *__restrict__ boxes, const float *__restrict__ supers,
+                                                                 float *__restrict__ out) {
     const int i = blockIdx.x * KNN_THREADS + threadIdx.x;
     if (i >= P) return;
     const float4 q = sorted[i];
@@ -162,14 +183,10 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_search_kernel(int P, int nbox
     // then collected from scratch out of the boxes, so no neighbour is counted twice
     const float bound = b2;
     b0 = b1 = b2 = FLT_MAX;
-    for (int b = 0; b < nboxes; ++b) {
-        const float *bx = boxes + 6 * b;
-        // squared distance from q to the box (0 inside)
-        const float ex = fmaxf(fmaxf(__ldg(bx + 0) - q.x, q.x - __ldg(bx + 3)), 0.f);
-        const float ey = fmaxf(fmaxf(__ldg(bx + 1) - q.y, q.y - __ldg(bx + 4)), 0.f);
-        const float ez = fmaxf(fmaxf(__ldg(bx + 2) - q.z, q.z - __ldg(bx + 5)), 0.f);
-        if (ex * ex + ey * ey + ez * ez > fminf(bound, b2)) continue;
-        const int j0 = b * KNN_BOX, j1 = min(P, j0 + KNN_BOX);
+    const int nsuper = (nboxes + KNN_SUPER - 1) / KNN_SUPER;
+    const int own = i / KNN_BOX;
+    {   // the query's own box first: it almost always holds the true neighbours, so the bound is tight for all the others
+        const int j0 = own * KNN_BOX, j1 = min(P, j0 + KNN_BOX);
         for (int j = j0; j < j1; ++j) {
             if (j == i) continue;
             const float4 c = __ldg(sorted + j);
@@ -177,10 +194,23 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_search_kernel(int P, int nbox
             best3_insert(dx * dx + dy * dy + dz * dz, b0, b1, b2);
         }
     }
+    for (int sb = 0; sb < nsuper; ++sb) {
+        if (aabb_dist2(supers + 6 * sb, q) > fminf(bound, b2)) continue;
+        for (int b = sb * KNN_SUPER; b < min(nboxes, (sb + 1) * KNN_SUPER); ++b) {
+            if (b == own || aabb_dist2(boxes + 6 * b, q) > fminf(bound, b2)) continue;
+            const int j0 = b * KNN_BOX, j1 = min(P, j0 + KNN_BOX);
+            for (int j = j0; j < j1; ++j) {
+                if (j == i) continue;
+                const float4 c = __ldg(sorted + j);
+                const float dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
+                best3_insert(dx * dx + dy * dy + dz * dz, b0, b1, b2);
+            }
+        }
+    }
     out[__float_as_uint(q.w)] = (b0 + b1 + b2) / 3.f;
 }
 
-struct KnnWs { size_t bbox, keys0, keys1, vals0, vals1, sorted, boxes, sort_ws, total; };
+struct KnnWs { size_t bbox, keys0, keys1, vals0, vals1, sorted, boxes, supers, sort_ws, total; };
 static KnnWs knn_layout(int P) {
     KnnWs w; size_t o = 0;
     const size_t n = (size_t)(P > 0 ? P : 1), nb = (n + KNN_BOX - 1) / KNN_BOX;
@@ -189,6 +219,7 @@ static KnnWs knn_layout(int P) {
     w.vals0 = o; o += align_up(n * 4); w.vals1 = o; o += align_up(n * 4);
     w.sorted = o; o += align_up(n * 16);
     w.boxes = o; o += align_up(nb * 24);
+    w.supers = o; o += align_up(((nb + KNN_SUPER - 1) / KNN_SUPER) * 24);
     w.sort_ws = o; o += align_up(sort_workspace_bytes((int64_t)n));
     w.total = o;
     return w;
@@ -211,7 +242,7 @@ int launch_dist2(int P, const float *points, float *mean_dists, void *ws, size_t
     uint64_t *k0 = (uint64_t *)(b + w.keys0), *k1 = (uint64_t *)(b + w.keys1);
     uint32_t *v0 = (uint32_t *)(b + w.vals0), *v1 = (uint32_t *)(b + w.vals1);
     float4 *sorted = (float4 *)(b + w.sorted);
-    float *boxes = (float *)(b + w.boxes);
+    float *boxes = (float *)(b + w.boxes), *supers = (float *)(b + w.supers);
     const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     LVDGS_CHECK(cudaMemcpyAsync(bbox, init, sizeof init, cudaMemcpyHostToDevice, s));
     LVDGS_PRE(s);
@@ -228,7 +259,10 @@ int launch_dist2(int P, const float *points, float *mean_dists, void *ws, size_t
     knn_boxes_kernel<<<nboxes, KNN_BOX, 0, s>>>(P, points, order, sorted, boxes);
     LVDGS_LAUNCHED(s, "knn_boxes");
     LVDGS_PRE(s);
-    knn_search_kernel<<<ceil_div(P, KNN_THREADS), KNN_THREADS, 0, s>>>(P, nboxes, sorted, boxes, mean_dists);
+    knn_super_kernel<<<ceil_div(ceil_div(nboxes, KNN_SUPER), KNN_THREADS), KNN_THREADS, 0, s>>>(nboxes, boxes, supers);
+    LVDGS_LAUNCHED(s, "knn_super");
+    LVDGS_PRE(s);
+    knn_search_kernel<<<ceil_div(P, KNN_THREADS), KNN_THREADS, 0, s>>>(P, nboxes, sorted, boxes, supers, mean_dists);
     LVDGS_LAUNCHED(s, "knn_search");
     return 0;
 }
