@@ -14,7 +14,10 @@
 
 namespace lvdgs {
 
-constexpr int RS_THREADS = 256;
+#ifndef LVDGS_RS_THREADS
+#define LVDGS_RS_THREADS 256
+#endif
+constexpr int RS_THREADS = LVDGS_RS_THREADS;
 constexpr int RS_WARPS = RS_THREADS / 32;
 #ifndef LVDGS_RS_ITEMS
 #define LVDGS_RS_ITEMS 16
@@ -101,10 +104,11 @@ __device__ __forceinline__ uint32_t rs_block_excl_scan(uint32_t v, uint32_t *war
     return base + incl - v;
 }
 
-__global__ void __launch_bounds__(RS_BINS) rs_scan_hist_kernel(SortWs *ws) {
+__global__ void __launch_bounds__(RS_THREADS) rs_scan_hist_kernel(SortWs *ws) {
     __shared__ uint32_t warp_sums[RS_WARPS];
-    const uint32_t v = ws->hist[blockIdx.x][threadIdx.x];
-    ws->hist[blockIdx.x][threadIdx.x] = rs_block_excl_scan(v, warp_sums);
+    const uint32_t v = threadIdx.x < RS_BINS ? ws->hist[blockIdx.x][threadIdx.x] : 0u;
+    const uint32_t e = rs_block_excl_scan(v, warp_sums);
+    if (threadIdx.x < RS_BINS) ws->hist[blockIdx.x][threadIdx.x] = e;
 }
 
 struct __align__(16) RsSmem {
@@ -168,41 +172,42 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
     }
     __syncthreads();
 
-    // ---- thread d owns digit d: warp-exclusive offsets, tile total, look-back ----
+    // ---- thread d (< 256) owns digit d: warp-exclusive offsets, tile total, look-back ----
     uint32_t total = 0;
+    if (tid < RS_BINS) {
 #pragma unroll
-    for (int ww = 0; ww < RS_WARPS; ++ww) {
-        const uint32_t c = sm.cnt[ww][tid];
-        sm.cnt[ww][tid] = total;
-        total += c;
+        for (int ww = 0; ww < RS_WARPS; ++ww) {
+            const uint32_t c = sm.cnt[ww][tid];
+            sm.cnt[ww][tid] = total;
+            total += c;
+        }
     }
     const uint32_t bstart = rs_block_excl_scan(total, sm.warp_sums);
-    sm.bin_start[tid] = bstart;
-
-    volatile uint32_t *lb = lookback;
-    uint32_t excl = 0;
+    if (tid < RS_BINS) {
+        sm.bin_start[tid] = bstart;
+        volatile uint32_t *lb = lookback;
+        uint32_t excl = 0;
 #ifdef LVDGS_RS_NOLOOKBACK      // timing experiment only: results are wrong
-    if (true) {
-        lb[(size_t)tile * RS_BINS + tid] = total | LB_GLOBAL;
-    } else {
+        if (true) {
 #else
-    if (tile == 0) {
-        lb[(size_t)tile * RS_BINS + tid] = total | LB_GLOBAL;
-    } else {
+        if (tile == 0) {
 #endif
-        lb[(size_t)tile * RS_BINS + tid] = total | LB_LOCAL;
-        int64_t t = (int64_t)tile - 1;
-        while (true) {
-            const uint32_t v = lb[(size_t)t * RS_BINS + tid];
-            if (v & (LB_LOCAL | LB_GLOBAL)) {
-                excl += v & LB_MASK;
-                if (v & LB_GLOBAL) break;
-                --t;
+            lb[(size_t)tile * RS_BINS + tid] = total | LB_GLOBAL;
+        } else {
+            lb[(size_t)tile * RS_BINS + tid] = total | LB_LOCAL;
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                const uint32_t v = lb[(size_t)t * RS_BINS + tid];
+                if (v & (LB_LOCAL | LB_GLOBAL)) {
+                    excl += v & LB_MASK;
+                    if (v & LB_GLOBAL) break;
+                    --t;
+                }
             }
+            lb[(size_t)tile * RS_BINS + tid] = (excl + total) | LB_GLOBAL;
         }
-        lb[(size_t)tile * RS_BINS + tid] = (excl + total) | LB_GLOBAL;
+        sm.goff[tid] = hist_scanned[pass * RS_BINS + tid] + excl - bstart;
     }
-    sm.goff[tid] = hist_scanned[pass * RS_BINS + tid] + excl - bstart;
     __syncthreads();
 
     // ---- scatter keys through shared memory, then coalesced runs to global ----
@@ -258,7 +263,7 @@ int launch_sort_pairs(int64_t n, const uint32_t *n_dev, uint64_t *keys0, uint64_
         rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, s>>>(keys0, n, n_dev, passes, end_bit, ws);
         LVDGS_LAUNCHED(s, "sort_histogram");
         LVDGS_PRE(s);
-        rs_scan_hist_kernel<<<passes, RS_BINS, 0, s>>>(ws);
+        rs_scan_hist_kernel<<<passes, RS_THREADS, 0, s>>>(ws);
         LVDGS_LAUNCHED(s, "sort_scan_hist");
         hist_scanned = &ws->hist[0][0];
     }
