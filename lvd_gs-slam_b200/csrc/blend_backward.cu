@@ -25,6 +25,10 @@ constexpr int BB_PPT = LVDGS_BB_PPT;
 constexpr int BB_WARPS = 8 / BB_PPT;
 constexpr int BB_THREADS = BB_WARPS * 32;
 constexpr int BB_ROWS = 4 * BB_PPT;            // pixel rows per warp block
+#ifndef LVDGS_BB_DIRECT_MAX
+#define LVDGS_BB_DIRECT_MAX 2
+#endif
+constexpr int BB_DIRECT_MAX = LVDGS_BB_DIRECT_MAX;   // up to this many contributing threads: skip the warp reduction
 
 // After the call v[0] of lane L holds the warp-wide sum of slot ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
 __device__ __forceinline__ void transpose_reduce16(float (&v)[16], int lane) {
@@ -220,9 +224,21 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                         }
                     }
                 }
-                if (__any_sync(0xffffffffu, valid)) {
-                    transpose_reduce16(v, lane);
-                    if (commits) atomicAdd(acc + (size_t)lds32(a_id + j * 4) * ACC_STRIDE + slot, v[0]);
+                const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                if (vmask) {
+                    float *row = acc + (size_t)lds32(a_id + j * 4) * ACC_STRIDE;
+                    if (__popc(vmask) <= BB_DIRECT_MAX) {
+                        // a Gaussian's edge often reaches only one or two threads of the block: their partial sums go
+                        // straight to the accumulator row (10 REDs) instead of through the 60-instruction reduction
+                        if (valid) {
+                            atomicAdd(row + 0, v[0]); atomicAdd(row + 1, v[1]); atomicAdd(row + 2, v[2]); atomicAdd(row + 3, v[3]);
+                            atomicAdd(row + 4, v[4]); atomicAdd(row + 5, v[5]); atomicAdd(row + 6, v[6]);
+                            atomicAdd(row + 8, v[8]); atomicAdd(row + 9, v[9]); atomicAdd(row + 10, v[10]);
+                        }
+                    } else {
+                        transpose_reduce16(v, lane);
+                        if (commits) atomicAdd(row + slot, v[0]);
+                    }
                 }
             }
         }
