@@ -32,6 +32,8 @@ extern "C" {
 #define LVDGS_FLAG_EXACT_PP 1      /* pose Jacobian keeps the principal-point entries Pr[8], Pr[9] */
 #define LVDGS_FLAG_OPACITY_GRAD 2  /* propagate dL/d(out_opacity) through the blend backward */
 #define LVDGS_FLAG_ACCUMULATE 4    /* backward ADDS the parameter gradients into the caller's buffers (sum over views) */
+#define LVDGS_FLAG_POSE_ONLY 8     /* backward produces only dL_dmeans2D (optional) and dL_dtau / dL_dtau_sum; every
+                                      parameter-gradient output may be NULL (tracking: only the camera is optimised) */
 
 /* which buffer a resize callback is asked for */
 #define LVDGS_BUF_GEOM 0

@@ -306,11 +306,13 @@ int lvdgs_rasterize_backward(const lvdgs_raster_params *prm, const float *backgr
     }
     if (!geom_buffer || !img_buffer || (R > 0 && !binning_buffer) || !scratch || !dL_dout_color) { set_error("NULL buffer"); return 1; }
     if (scratch_bytes < lvdgs_backward_scratch_bytes(p.P, R)) { set_error("backward scratch too small"); return 1; }
-    if (!dL_dopacity || !dL_dmeans3D) { set_error("NULL gradient output"); return 1; }
-    if (colors_precomp && !dL_dcolors) { set_error("dL_dcolors required with colors_precomp"); return 1; }
-    if (cov3D_precomp && !dL_dcov3D) { set_error("dL_dcov3D required with cov3D_precomp"); return 1; }
-    if (!colors_precomp && !dL_dsh) { set_error("dL_dsh required when shs are used"); return 1; }
-    if (!cov3D_precomp && (!dL_dscales || !dL_drots)) { set_error("dL_dscales / dL_drots required"); return 1; }
+    if (!(p.flags & LVDGS_FLAG_POSE_ONLY)) {
+        if (!dL_dopacity || !dL_dmeans3D) { set_error("NULL gradient output"); return 1; }
+        if (colors_precomp && !dL_dcolors) { set_error("dL_dcolors required with colors_precomp"); return 1; }
+        if (cov3D_precomp && !dL_dcov3D) { set_error("dL_dcov3D required with cov3D_precomp"); return 1; }
+        if (!colors_precomp && !dL_dsh) { set_error("dL_dsh required when shs are used"); return 1; }
+        if (!cov3D_precomp && (!dL_dscales || !dL_drots)) { set_error("dL_dscales / dL_drots required"); return 1; }
+    }
     const int W = p.width, H = p.height;
     GeomPtrs g = geom_ptrs(const_cast<void *>(geom_buffer), p.P);
     ImgPtrs im = img_ptrs(const_cast<void *>(img_buffer), W, H);

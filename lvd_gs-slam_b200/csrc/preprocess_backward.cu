@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
     float dscale[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
     const bool live = i < a.P && a.radii[i] > 0;
+    // tracking (utils/slam_frontend.py:1468-1521) optimises the camera only: no Gaussian parameter needs a gradient
+    const bool pose_only = (a.flags & LVDGS_FLAG_POSE_ONLY) != 0;
     if (live) {
         // moments of the blend backward -> dL_dmean2D (NDC units), dL_dconic, dL_dopacity (see ACC_STRIDE, common.cuh)
         const float4 *row = reinterpret_cast<const float4 *>(a.acc + (size_t)i * ACC_STRIDE);
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
             tau[4] += dz * -pc.x;
         }
         // ---- SH backward ----
-        if (a.dL_dsh && a.shs) {
+        if (!pose_only && a.dL_dsh && a.shs) {
             const float *sh = a.shs + (size_t)i * a.M * 3;
             float *dsh = a.dL_dsh + (size_t)i * a.M * 3;
             const uint8_t cl = a.clamped[i];
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
             }
         }
         // ---- cov3D -> scale / rotation ----
-        if (!a.cov3D_precomp) {
+        if (!pose_only && !a.cov3D_precomp) {
             const float Gm[9] = {dcov[0], 0.5f * dcov[1], 0.5f * dcov[2], 0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
                                  0.5f * dcov[2], 0.5f * dcov[4], dcov[5]};
             float Q[9];
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
             drot[2] = 2.f * (-2.f * qy * Q[0] + qx * Q[1] + r * Q[2] + qx * Q[3] + qz * Q[5] - r * Q[6] + qz * Q[7] - 2.f * qy * Q[8]);
             drot[3] = 2.f * (-2.f * qz * Q[0] - r * Q[1] + qx * Q[2] + r * Q[3] - 2.f * qz * Q[4] + qy * Q[5] + qx * Q[6] + qy * Q[7]);
         }
-    } else if (i < a.P && a.dL_dsh && !(a.flags & LVDGS_FLAG_ACCUMULATE)) {
+    } else if (i < a.P && a.dL_dsh && !pose_only && !(a.flags & LVDGS_FLAG_ACCUMULATE)) {
         float *dsh = a.dL_dsh + (size_t)i * a.M * 3;
         for (int k = 0; k < a.M * 3; ++k) dsh[k] = 0.f;
     }
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
 #define PUT(ptr, idx, v) do { if (accum) (ptr)[idx] += (v); else (ptr)[idx] = (v); } while (0)
         const size_t i3 = 3 * (size_t)i;
         if (a.dL_dmeans2D) { a.dL_dmeans2D[i3] = r0.x; a.dL_dmeans2D[i3 + 1] = r0.y; a.dL_dmeans2D[i3 + 2] = 0.f; }
-      if (live || !accum) {       // a culled Gaussian adds nothing: in accumulate mode its rows are not touched at all
+      if (!pose_only && (live || !accum)) {       // a culled Gaussian adds nothing: in accumulate mode its rows are not touched at all
         if (a.dL_dcolors) { PUT(a.dL_dcolors, i3, r2.x); PUT(a.dL_dcolors, i3 + 1, r2.y); PUT(a.dL_dcolors, i3 + 2, r2.z); }
         PUT(a.dL_dopacity, i, r1.y);
         PUT(a.dL_dmeans3D, i3, dmean[0]); PUT(a.dL_dmeans3D, i3 + 1, dmean[1]); PUT(a.dL_dmeans3D, i3 + 2, dmean[2]);

@@ -159,12 +159,18 @@ class _RasterizeGaussians(torch.autograd.Function):
         m3, shs, cp, op, sc, rot, cov, radii = ctx.saved_tensors
         bg, view, proj, praw, campos = ctx.aux
         dev = grad_out_color.device
+        # tracking differentiates w.r.t. the camera only (the frontend's Gaussians are detached copies,
+        # utils/multiprocessing_utils.py:29-30): then no per-Gaussian parameter gradient is computed or stored
+        nig = ctx.needs_input_grad
+        pose_only = not (nig[0] or nig[2] or nig[3] or nig[4] or nig[5] or nig[6] or nig[7])
         # one allocation for every gradient tensor (+ the backward scratch), handed out as views
-        widths = [("means2D", 3), ("opac", 1), ("means3D", 3)]
-        if cp is not None: widths.append(("colors", 3))
-        if cov is not None: widths.append(("cov", 6))
-        else: widths += [("sc", 3), ("rot", 4)]
-        if shs is not None: widths.append(("sh", 3 * M))
+        widths = [("means2D", 3)]
+        if not pose_only:
+            widths += [("opac", 1), ("means3D", 3)]
+            if cp is not None: widths.append(("colors", 3))
+            if cov is not None: widths.append(("cov", 6))
+            else: widths += [("sc", 3), ("rot", 4)]
+            if shs is not None: widths.append(("sh", 3 * M))
         nscratch = (L.lvdgs_backward_scratch_bytes(P, ctx.num_rendered) + 3) // 4
         pad4 = lambda n: (n + 3) & ~3                  # every view starts 16-byte aligned (float4 stores in the kernels)
         flat = torch.empty((8 + sum(pad4(w * P) for _, w in widths) + nscratch,), dtype=torch.float32, device=dev)
@@ -175,6 +181,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         flat_s = flat[off:off + nscratch]
         g_tau = flat[0:6]
         prm = _params(rs, P, M)
+        if pose_only:
+            prm.flags |= 8          # LVDGS_FLAG_POSE_ONLY
         _select_device(L, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         p = _ptr
@@ -185,8 +193,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         rc = L.lvdgs_rasterize_backward(C.byref(prm), p(bg), p(m3), p(radii), p(cp), p(op), p(sc), p(rot), p(cov), p(view),
                                         p(proj), p(praw), p(gc), p(gd), p(go), p(shs), p(campos), p(b.get(0)),
                                         ctx.num_rendered, ctx.capacity, p(b.get(1)), p(b.get(2)), p(flat_s),
-                                        flat_s.numel() * 4, p(g["means2D"]), p(g.get("colors")), p(g["opac"]),
-                                        p(g["means3D"]), p(g.get("cov")), p(g.get("sh")), p(g.get("sc")), p(g.get("rot")),
+                                        flat_s.numel() * 4, p(g["means2D"]), p(g.get("colors")), p(g.get("opac")),
+                                        p(g.get("means3D")), p(g.get("cov")), p(g.get("sh")), p(g.get("sc")), p(g.get("rot")),
                                         None, p(g_tau), stream)
         _native.check(rc, "lvdgs_rasterize_backward")
         th_shape, rho_shape = ctx.in_shapes

@@ -238,3 +238,48 @@ def test_speculative_launch_matches_exact_mode():
         np.testing.assert_array_equal(internals["ranges"], ref_int["ranges"])
         # gradients go through float atomics: equal up to summation order
         assert rel_err(g["means3D"], ref_g["means3D"]) < 1e-4
+
+
+def test_pose_only_backward_matches_full_backward():
+    """Tracking: only theta/rho (and the screen-space points) require grad -> LVDGS_FLAG_POSE_ONLY path; the pose
+    gradient must equal the one of the full backward, parameter gradients must be absent."""
+    import diff_gaussian_rasterization as dgr
+    from gpu_harness import settings_for
+    cam, sc, bg = make_case("kitti30k_bg")
+    H, W = cam.image_height, cam.image_width
+    rng = np.random.default_rng(12)
+    gc = torch.tensor(rng.normal(0, 1, (3, H, W)).astype(np.float32), device="cuda")
+    gd = torch.tensor(rng.normal(0, 1, (1, H, W)).astype(np.float32), device="cuda")
+    res = {}
+    for mode in ("full", "pose"):
+        rg = mode == "full"
+        t = lambda a: torch.tensor(a, device="cuda", requires_grad=rg)
+        means, opac, scales, rots, shs = t(sc["means3D"]), t(sc["opacities"]), t(sc["scales"]), t(sc["rotations"]), t(sc["shs"])
+        m2d = torch.zeros(means.shape, device="cuda", requires_grad=True)
+        theta = torch.zeros(3, device="cuda", requires_grad=True); rho = torch.zeros(3, device="cuda", requires_grad=True)
+        color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(settings_for(cam, bg, 0))(
+            means3D=means, means2D=m2d, opacities=opac, shs=shs, scales=scales, rotations=rots, theta=theta, rho=rho)
+        torch.autograd.backward([color, depth], [gc, gd])
+        res[mode] = (theta.grad.cpu().numpy(), rho.grad.cpu().numpy(), m2d.grad.cpu().numpy(), means.grad)
+    assert res["pose"][3] is None and res["full"][3] is not None
+    assert rel_err(res["pose"][0], res["full"][0]) < 1e-4 and rel_err(res["pose"][1], res["full"][1]) < 1e-4
+    assert rel_err(res["pose"][2], res["full"][2]) < 1e-4
+
+
+def test_map_size_churn_between_renders():
+    """Densify / prune churn (BASELINE configs[4]): the number of Gaussians and of instances changes from call to call,
+    which exercises buffer re-sizing and the speculative capacity hint (growing past it, shrinking below it)."""
+    import diff_gaussian_rasterization as dgr
+    dgr._capacity_hint.clear()
+    cam = synth.make_camera("mast3r_kitti")
+    full = synth.make_scene(60_000, cam, seed=21)
+    bg = np.zeros(3, np.float32)
+    for n in (5_000, 60_000, 20_000, 59_000, 1_000, 40_000):
+        sc = {k: (v[:n] if isinstance(v, np.ndarray) else v) for k, v in full.items()}
+        out, internals, _ = run_cuda(sc, cam, bg, debug=False)
+        fwd, _ = run_oracle(sc, cam, bg)
+        np.testing.assert_array_equal(out["radii"], fwd["radii"])
+        assert internals["R"] == fwd["R"]
+        np.testing.assert_array_equal(internals["point_list"], fwd["point_list"])
+        ok = fwd["margin"] > 1e-5
+        assert np.abs(out["color"][:, ok] - fwd["color"][:, ok]).max() < 1e-5
