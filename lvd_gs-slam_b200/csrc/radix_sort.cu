@@ -111,6 +111,13 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scan_hist_kernel(SortWs *ws) {
     if (threadIdx.x < RS_BINS) ws->hist[blockIdx.x][threadIdx.x] = e;
 }
 
+#ifdef LVDGS_RS_TIMING     // experiment: per-phase clock() stamps of thread 0 of every block, [block][8]
+__device__ long long g_rs_timing[4096 * 8];
+#define RS_MARK(k) do { if (threadIdx.x == 0 && blockIdx.x < 4096) g_rs_timing[blockIdx.x * 8 + (k)] = clock64(); } while (0)
+#else
+#define RS_MARK(k) do { } while (0)
+#endif
+
 struct __align__(16) RsSmem {
     uint64_t keys[RS_TILE];                 // reused as uint32 vals[RS_TILE] in the second phase
     uint32_t cnt[RS_WARPS][RS_BINS];        // per-warp digit counters -> per-warp exclusive offsets
@@ -138,6 +145,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
     if (tid == 0) sm.tile = atomicAdd(&ws->ticket[pass], 1u);
     for (int k = tid; k < RS_WARPS * RS_BINS; k += RS_THREADS) (&sm.cnt[0][0])[k] = 0;
     __syncthreads();
+    RS_MARK(0);
     const uint32_t tile = sm.tile;
     const int64_t tile_base = (int64_t)tile * RS_TILE;
     if (tile_base >= n) return;          // launch was sized for the capacity; tiles past the real count retire at once
@@ -153,6 +161,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
         val[k] = e < n_valid ? __ldg(vals_in + tile_base + e) : 0u;
     }
 
+    RS_MARK(1);
     // ---- stable rank inside the warp: items in order k = 0.., lanes ascending ----
     uint32_t rank[RS_ITEMS];
     const uint32_t lt_mask = (1u << lane) - 1;
@@ -171,6 +180,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
         __syncwarp();
     }
     __syncthreads();
+    RS_MARK(2);
 
     // ---- thread d (< 256) owns digit d: warp-exclusive offsets, tile total, look-back ----
     uint32_t total = 0;
@@ -209,6 +219,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
         sm.goff[tid] = hist_scanned[pass * RS_BINS + tid] + excl - bstart;
     }
     __syncthreads();
+    RS_MARK(3);
 
     // ---- scatter keys through shared memory, then coalesced runs to global ----
     uint32_t pos[RS_ITEMS];
@@ -220,21 +231,25 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
         sm.dig[pos[k]] = (uint8_t)d;
     }
     __syncthreads();
+    RS_MARK(4);
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; ++k) {
         const int s = k * RS_THREADS + tid;
         if (s < n_valid) keys_out[(uint32_t)(s + sm.goff[sm.dig[s]])] = sm.keys[s];
     }
     __syncthreads();
+    RS_MARK(5);
     uint32_t *svals = reinterpret_cast<uint32_t *>(sm.keys);
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; ++k) svals[pos[k]] = val[k];
     __syncthreads();
+    RS_MARK(6);
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; ++k) {
         const int s = k * RS_THREADS + tid;
         if (s < n_valid) vals_out[(uint32_t)(s + sm.goff[sm.dig[s]])] = svals[s];
     }
+    RS_MARK(7);
 }
 
 int launch_sort_pairs(int64_t n, const uint32_t *n_dev, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
@@ -281,5 +296,11 @@ int launch_sort_pairs(int64_t n, const uint32_t *n_dev, uint64_t *keys0, uint64_
     if (selector) *selector = passes & 1;
     return 0;
 }
+
+#ifdef LVDGS_RS_TIMING
+extern "C" int lvdgs_debug_sort_timing(long long *host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_rs_timing, sizeof(long long) * n);
+}
+#endif
 
 }  // namespace lvdgs
