@@ -346,9 +346,10 @@ def main():
             kernels.append(ent)
         kernels.sort(key=lambda e: -e["ms_per_view"])
         dom = next((e for e in kernels if "bound" in e), None)
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom["kernel"])
+        traffic, ncu = None, None
+        try:   # one `ncu --set full` capture of the same kernel, committed under profiles/ (per launch, like `achieved`)
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernel_metrics.json"))).get(dom["kernel"])
+            traffic = ncu["dram_bytes"]
         except Exception:
             pass
         if dom:
@@ -358,7 +359,10 @@ def main():
                     "peak_source": hbm_src if dom["bound"] == "hbm" else
                     f"computed {n_sm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (no measured FP32 peak in MEASURED_PEAKS.json; "
                     "tensor cores unused: the blend is FP32 FMA/MUFU issue-bound, not a dense contraction)",
-                    "algorithmic": {"pairs_per_view": pairs, "instances_per_view": Rs, "visible_per_view": vis}}
+                    "algorithmic": {"pairs_per_view": pairs, "instances_per_view": Rs, "visible_per_view": vis},
+                    "ncu": ncu,
+                    "note": "frac counts only the FLOPs of the A.3/A.4 blend math; the kernel's issue slots (ncu "
+                            "smsp__issue_active, in `ncu`) are the pipe-utilisation figure north_star asks for"}
 
     # ---------------- cpu baseline (rank 0, N=1): oracle port on the host cores, one view ----------------
     cpu = None
