@@ -149,8 +149,11 @@ struct PreArgs {
     GeomPtrs g;
 };
 
-__global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(const PreArgs a) {
-    __shared__ float stage[PRE_THREADS * 3];
+#ifndef LVDGS_PF_MINBLOCKS
+#define LVDGS_PF_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(PRE_THREADS, LVDGS_PF_MINBLOCKS) preprocess_forward_kernel(const PreArgs a) {
+    __shared__ float stage[PRE_THREADS * 9];
     __shared__ CameraConst cam;
     __shared__ uint32_t s_warp[PRE_THREADS / 32];
     const int bid = blockIdx.x;
@@ -158,12 +161,24 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(const P
     else if (threadIdx.x < 32) cam.proj[threadIdx.x - 16] = __ldg(a.proj + threadIdx.x - 16);
     else if (threadIdx.x < 35) cam.campos[threadIdx.x - 32] = __ldg(a.campos + threadIdx.x - 32);
     const int i = bid * PRE_THREADS + threadIdx.x;
-    const float3 p = load3_staged(a.means3D, a.P, stage, bid);      // contains the __syncthreads that publishes `cam`
-    float3 sc = make_float3(0.f, 0.f, 0.f);
-    if (a.scales) sc = load3_staged(a.scales, a.P, stage, bid);
-    float3 sh0 = make_float3(0.f, 0.f, 0.f);
+    // all three [P,3] inputs are staged with ONE barrier pair: the loads of means / scales / colour are in flight together
     const bool staged_color = a.colors_precomp != nullptr || a.M == 1;
-    if (staged_color) sh0 = load3_staged(a.colors_precomp ? a.colors_precomp : a.shs, a.P, stage, bid);
+    const float *color_src = a.colors_precomp ? a.colors_precomp : a.shs;
+    {
+        const int blk0 = bid * PRE_THREADS;
+        const int n = min(PRE_THREADS, a.P - blk0) * 3;
+        const size_t off = (size_t)blk0 * 3;
+        for (int k = threadIdx.x; k < n; k += PRE_THREADS) {
+            stage[k] = __ldg(a.means3D + off + k);
+            if (a.scales) stage[PRE_THREADS * 3 + k] = __ldg(a.scales + off + k);
+            if (staged_color) stage[PRE_THREADS * 6 + k] = __ldg(color_src + off + k);
+        }
+    }
+    __syncthreads();                                            // also publishes `cam`
+    const float3 p = make_float3(stage[3 * threadIdx.x], stage[3 * threadIdx.x + 1], stage[3 * threadIdx.x + 2]);
+    float3 sc = make_float3(0.f, 0.f, 0.f), sh0 = make_float3(0.f, 0.f, 0.f);
+    if (a.scales) sc = make_float3(stage[PRE_THREADS * 3 + 3 * threadIdx.x], stage[PRE_THREADS * 3 + 3 * threadIdx.x + 1], stage[PRE_THREADS * 3 + 3 * threadIdx.x + 2]);
+    if (staged_color) sh0 = make_float3(stage[PRE_THREADS * 6 + 3 * threadIdx.x], stage[PRE_THREADS * 6 + 3 * threadIdx.x + 1], stage[PRE_THREADS * 6 + 3 * threadIdx.x + 2]);
     const bool in_range = i < a.P;
 
     int32_t radius = 0;

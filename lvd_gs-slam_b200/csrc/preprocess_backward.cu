@@ -8,7 +8,13 @@
 
 namespace lvdgs {
 
-constexpr int PB_THREADS = 256;
+#ifndef LVDGS_PB_THREADS
+#define LVDGS_PB_THREADS 128
+#endif
+#ifndef LVDGS_PB_MINBLOCKS
+#define LVDGS_PB_MINBLOCKS 8      // <= 64 registers: the kernel is latency-bound, occupancy measured to pay (56 -> 43 us)
+#endif
+constexpr int PB_THREADS = LVDGS_PB_THREADS;
 
 __device__ __constant__ float B_SH_C0 = 0.28209479177387814f;
 __device__ __constant__ float B_SH_C1 = 0.4886025119029199f;
@@ -41,7 +47,7 @@ __device__ __forceinline__ void quat_R(float4 q, float R[9]) {
     R[6] = 2.f * (x * z - r * y); R[7] = 2.f * (y * z + r * x); R[8] = 1.f - 2.f * (x * x + y * y);
 }
 
-__global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const PbArgs a) {
+__global__ void __launch_bounds__(PB_THREADS, LVDGS_PB_MINBLOCKS) preprocess_backward_kernel(const PbArgs a) {
     __shared__ CameraConst cam;
     __shared__ float s_praw[16];
     __shared__ float s_tau[PB_THREADS / 32][6];
