@@ -35,6 +35,11 @@ extern "C" {
 #define LVDGS_FLAG_POSE_ONLY 8     /* backward produces only dL_dmeans2D (optional) and dL_dtau / dL_dtau_sum; every
                                       parameter-gradient output may be NULL (tracking: only the camera is optimised) */
 
+#define LVDGS_FLAG_GLOBAL_SORT 16  /* sort all (tile | depth) keys with the global onesweep radix sort (as upstream's
+                                      cub::DeviceRadixSort) instead of one shared-memory sort per tile segment; the
+                                      sorted keys / point list are bit-identical either way.  Must be the same in the
+                                      forward and its backward. */
+
 /* which buffer a resize callback is asked for */
 #define LVDGS_BUF_GEOM 0
 #define LVDGS_BUF_BINNING 1
@@ -72,7 +77,8 @@ typedef struct lvdgs_geom_layout {
 } lvdgs_geom_layout;
 
 typedef struct lvdgs_binning_layout {
-    size_t keys[2];        /* uint64 [R] x2  (tile << 32 | depth bits); double buffer */
+    size_t keys[2];        /* uint64 [R] x2  (tile << 32 | depth bits); double buffer.  Default (tile-segment) sort:
+                              [0] = per-tile segments of (depth bits << 32 | Gaussian) in slot order, [1] = sorted keys */
     size_t vals[2];        /* uint32 [R] x2  Gaussian index */
     size_t sort_ws;        /* onesweep histograms + look-back state */
     size_t sorted_sel;     /* int32: which of the two key/val buffers holds the sorted result */
@@ -85,7 +91,8 @@ typedef struct lvdgs_img_layout {
     size_t ranges;         /* uint2  [tiles] */
     size_t tile_order;     /* uint32 [tiles] tile ids, heaviest lists first: launch order of the blend kernels */
     size_t tile_grid;      /* int32  [(gy+1)*(gx+1)] difference array -> per-tile instance counts */
-    size_t sort_hist;      /* uint32 [8][256] exclusive-scanned digit histograms of the sort keys */
+    size_t sort_hist;      /* uint32 [8][256] exclusive-scanned digit histograms of the sort keys (LVDGS_FLAG_GLOBAL_SORT) */
+    size_t tile_cursor;    /* uint32 [tiles][8] (one per 32-byte sector) instances emitted so far into each tile's segment */
     size_t total;
 } lvdgs_img_layout;
 

@@ -80,6 +80,7 @@ static void img_layout(int32_t W, int32_t H, lvdgs_img_layout &l) {
     l.tile_order = o; o += align_up(tiles * sizeof(uint32_t));
     l.tile_grid = o; o += align_up(gridn * sizeof(int32_t));
     l.sort_hist = o; o += align_up(SORT_MAX_PASSES * SORT_BINS * sizeof(uint32_t));
+    l.tile_cursor = o; o += align_up(tiles * CURSOR_STRIDE * sizeof(uint32_t));
     l.total = o;
 }
 
@@ -109,6 +110,7 @@ static ImgPtrs img_ptrs(void *base, int32_t W, int32_t H) {
     ImgPtrs p;
     p.final_T = (float *)(b + l.final_T); p.n_contrib = (uint32_t *)(b + l.n_contrib); p.ranges = (uint2 *)(b + l.ranges);
     p.tile_order = (uint32_t *)(b + l.tile_order); p.tile_grid = (int32_t *)(b + l.tile_grid); p.sort_hist = (uint32_t *)(b + l.sort_hist);
+    p.tile_cursor = (uint32_t *)(b + l.tile_cursor);
     return p;
 }
 
@@ -177,17 +179,26 @@ static thread_local cudaEvent_t t_R_event = nullptr;
 // everything after the instance count is known on the DEVICE: keys, sort, ranges, blend.  `capacity` sizes the
 // launches and the binning arena; the kernels clamp to min(R, capacity) read from device memory.
 static int launch_bin_and_blend(const lvdgs_raster_params &p, const GeomPtrs &g, const BinPtrs &b, const ImgPtrs &im,
-                                int64_t capacity, const float *background, float *out_color, float *out_depth,
+                                int64_t capacity, bool rerun, const float *background, float *out_color, float *out_depth,
                                 float *out_opacity, int32_t *n_touched, cudaStream_t s) {
     const int W = p.width, H = p.height;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const uint32_t *R_dev = g.num_instances;
     LVDGS_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * (size_t)p.P, s));
-    if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], b.vals[0], s)) return 1;
-    const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
     int sel = 0;
-    if (launch_sort_pairs(capacity, R_dev, b.keys[0], b.keys[1], b.vals[0], b.vals[1], end_bit, b.sort_ws,
-                          sort_workspace_bytes(capacity), im.sort_hist, &sel, s)) return 1;
+    if (p.flags & LVDGS_FLAG_GLOBAL_SORT) {
+        if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], b.vals[0], nullptr, nullptr, s)) return 1;
+        const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
+        if (launch_sort_pairs(capacity, R_dev, b.keys[0], b.keys[1], b.vals[0], b.vals[1], end_bit, b.sort_ws,
+                              sort_workspace_bytes(capacity), im.sort_hist, &sel, s)) return 1;
+    } else {
+        // instances go straight into their tile's segment of keys[0]; one CTA per tile sorts it into keys[1] / vals[1]
+        // the cursors were zeroed together with the tile grid; a re-run after a failed speculative launch resets them
+        if (rerun) LVDGS_CHECK(cudaMemsetAsync(im.tile_cursor, 0, sizeof(uint32_t) * CURSOR_STRIDE * (size_t)gx * gy, s));
+        if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], nullptr, im.tile_cursor, im.ranges, s)) return 1;
+        if (launch_tile_sort(gx * gy, capacity, R_dev, im.ranges, im.tile_order, b.keys[0], b.keys[1], b.vals[1], s)) return 1;
+        sel = 1;
+    }
     LVDGS_CHECK(cudaMemcpyAsync(b.sorted_sel, &sel, sizeof(int32_t), cudaMemcpyHostToDevice, s));
     return launch_blend_forward(W, H, capacity, R_dev, im.ranges, b.vals[sel], g, im.tile_order, background, out_color, out_depth, out_opacity,
                                 im.final_T, im.n_contrib, n_touched, s);
@@ -247,7 +258,7 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     if (launch_preprocess_forward(p, means3D, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
                                   projmatrix, shs, campos, radii, g, im, s)) return 1;
     // block offsets, R, tile ranges and all digit histograms of the sort, from the block sums and per-tile counts
-    if (launch_binning_prep(p.P, W, H, 32 + tile_bits((uint32_t)(gx * gy)), g, im, s)) return 1;
+    if (launch_binning_prep(p.P, W, H, (p.flags & LVDGS_FLAG_GLOBAL_SORT) ? 32 + tile_bits((uint32_t)(gx * gy)) : 0, g, im, s)) return 1;
     LVDGS_CHECK(cudaMemcpyAsync(t_pinned_R, g.num_instances, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     LVDGS_CHECK(cudaEventRecord(t_R_event, s));
 
@@ -260,7 +271,7 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
         lvdgs_binning_layout bl; binning_layout(capacity, bl);
         void *bin_base = resize(resize_user, LVDGS_BUF_BINNING, bl.total);
         if (!bin_base) { set_error("resize callback returned NULL (binning)"); return 1; }
-        if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, background, out_color, out_depth,
+        if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, false, background, out_color, out_depth,
                                  out_opacity, n_touched, s)) return 1;
         launched = true;
     }
@@ -273,7 +284,7 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
         lvdgs_binning_layout bl; binning_layout(capacity, bl);
         void *bin_base = resize(resize_user, LVDGS_BUF_BINNING, bl.total);
         if (!bin_base) { set_error("resize callback returned NULL (binning)"); return 1; }
-        if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, background, out_color, out_depth,
+        if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, launched, background, out_color, out_depth,
                                  out_opacity, n_touched, s)) return 1;
     }
     *binning_capacity = capacity;
@@ -322,7 +333,7 @@ int lvdgs_rasterize_backward(const lvdgs_raster_params *prm, const float *backgr
         BinPtrs b = bin_ptrs(const_cast<void *>(binning_buffer), binning_capacity);
         const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
         const int passes = (32 + tile_bits((uint32_t)(gx * gy)) + 7) / 8;
-        const int sel = passes & 1;
+        const int sel = (p.flags & LVDGS_FLAG_GLOBAL_SORT) ? (passes & 1) : 1;
         if (launch_blend_backward(p.P, W, H, R, im.ranges, b.vals[sel], im.tile_order, g, background, im.final_T, im.n_contrib,
                                   dL_dout_color, dL_dout_depth, dL_dout_opacity, p.flags, bg, s)) return 1;
     }

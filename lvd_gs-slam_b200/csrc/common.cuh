@@ -137,7 +137,13 @@ struct ImgPtrs {
     int32_t *tile_grid;               // [(gy+1)*(gx+1)] 2-D difference array of the tile rects -> per-tile instance counts
     uint32_t *tile_order;             // [tiles] tile ids, heaviest instance lists first (launch order of the blend kernels)
     uint32_t *sort_hist;              // [8][256] digit histograms of the (tile|depth) keys, exclusive-scanned by binning_prep
+    uint32_t *tile_cursor;            // [tiles][CURSOR_STRIDE] instances emitted so far into each tile's segment (tile-segment sort)
 };
+// one cursor per 32-byte sector: same-sector atomics serialise in L2, and all cursors packed would be ~60 lines
+#ifndef LVDGS_CURSOR_STRIDE
+#define LVDGS_CURSOR_STRIDE 8
+#endif
+constexpr int CURSOR_STRIDE = LVDGS_CURSOR_STRIDE;
 constexpr int SORT_MAX_PASSES = 8;
 constexpr int SORT_BINS = 256;
 
@@ -147,7 +153,10 @@ int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D
                               const float *campos, int32_t *radii, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s);
 int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s);
 int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, int64_t capacity, uint64_t *keys, uint32_t *vals,
-                     cudaStream_t s);
+                     uint32_t *tile_cursor, const uint2 *ranges, cudaStream_t s);
+// tile-segment sort (tile_sort.cu): seg holds each tile's (depth bits << 32 | Gaussian) words in ranges[tile], unordered
+int launch_tile_sort(int tiles, int64_t capacity, const uint32_t *n_dev, const uint2 *ranges, const uint32_t *tile_order,
+                     uint64_t *seg, uint64_t *keys_out, uint32_t *vals_out, cudaStream_t s);
 
 size_t sort_workspace_bytes(int64_t n);
 // pre_hist: optional [passes][256] exclusive-scanned digit histograms (device); when given, the histogram pass over the

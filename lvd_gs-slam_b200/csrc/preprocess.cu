@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) binning_count_kernel(int P, int
         atomicAdd(grid + rc.y * gw + rc.z, -1);
         atomicAdd(grid + rc.w * gw + rc.x, -1);
         atomicAdd(grid + rc.w * gw + rc.z, 1);
+        if (!depths) continue;                  // tile-segment sort: no digit histograms
         const uint32_t db = __float_as_uint(__ldg(depths + i));
         atomicAdd(s_hist + 0 * SORT_BINS + (db & 0xffu), touched);
         atomicAdd(s_hist + 1 * SORT_BINS + ((db >> 8) & 0xffu), touched);
@@ -340,8 +341,9 @@ __global__ void __launch_bounds__(COUNT_THREADS) binning_count_kernel(int P, int
         atomicAdd(s_hist + 3 * SORT_BINS + (db >> 24), touched);
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < 4 * SORT_BINS; k += COUNT_THREADS)
-        if (s_hist[k]) atomicAdd(hist_g + k, s_hist[k]);
+    if (depths)
+        for (int k = threadIdx.x; k < 4 * SORT_BINS; k += COUNT_THREADS)
+            if (s_hist[k]) atomicAdd(hist_g + k, s_hist[k]);
     if (in_smem)
         for (int k = threadIdx.x; k < cells; k += COUNT_THREADS)
             if (s_grid[k]) atomicAdd(grid_g + k, s_grid[k]);
@@ -471,16 +473,18 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
     }
 }
 
+// end_bit > 0: global onesweep sort follows (digit histograms are prepared); end_bit == 0: tile-segment sort (cursors)
 int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const int passes = (end_bit + 7) / 8;
+    const bool onesweep = end_bit > 0;
     const int cells = (gx + 1) * (gy + 1);
     const size_t dyn = cells <= PREP_GRID_SMEM ? (size_t)cells * sizeof(int32_t) : 0;
     {
         const int blocks = min(148, ceil_div(P, COUNT_THREADS * 2));
         LVDGS_PRE(s);
         binning_count_kernel<<<blocks, COUNT_THREADS, 4 * SORT_BINS * sizeof(uint32_t) + dyn, s>>>(
-            P, gx, gy, g.tiles_touched, g.rect, g.depths, im.tile_grid, im.sort_hist);
+            P, gx, gy, g.tiles_touched, g.rect, onesweep ? g.depths : nullptr, im.tile_grid, im.sort_hist);
         LVDGS_LAUNCHED(s, "binning_count");
     }
     LVDGS_PRE(s);
@@ -501,11 +505,15 @@ constexpr int EMIT_THREADS = 256;
 static_assert(EMIT_THREADS == PRE_THREADS, "emit blocks must own the same Gaussians as preprocess blocks (block_sums)");
 static_assert(PRE_THREADS == SORT_BINS, "s_hist3 is indexed by threadIdx");
 
+// BUCKET = true (tile-segment sort, tile_sort.cu): the instance goes to the next free slot of its tile's segment as the
+// word (depth bits << 32 | Gaussian); slot order is arbitrary, the per-tile sort makes the result unique.
+template <bool BUCKET>
 __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, uint32_t capacity, const uint32_t *__restrict__ block_offsets,
                                                                  const uint32_t *__restrict__ tiles_touched, uint32_t *__restrict__ offsets,
                                                                  const short4 *__restrict__ rects,
                                                                  const float *__restrict__ depths,
-                                                                 uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                                                                 uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                                                 uint32_t *__restrict__ tile_cursor, const uint2 *__restrict__ ranges) {
     __shared__ uint32_t s_end[EMIT_THREADS];      // inclusive offsets of this block's Gaussians
     __shared__ short4 s_rect[EMIT_THREADS];
     __shared__ uint32_t s_depth[EMIT_THREADS];
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
     }
     __syncthreads();
     const int last = min(EMIT_THREADS, P - g0) - 1;
-    const uint32_t span_end = min(s_end[last], capacity);      // never write past the arena the launch was sized for
+    const uint32_t span_end = BUCKET ? s_end[last] : min(s_end[last], capacity);      // never write past the arena the launch was sized for
     for (uint32_t r = span_begin + threadIdx.x; r < span_end; r += EMIT_THREADS) {
         // smallest j with s_end[j] > r
         int lo = 0, hi = last;
@@ -551,17 +559,26 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
         const uint32_t w = (uint32_t)(rc.z - rc.x);
         const uint32_t yy = local / w, xx = local - yy * w;
         const uint32_t tile = (uint32_t)(rc.y + (int)yy) * (uint32_t)gx + (uint32_t)(rc.x + (int)xx);
-        keys[r] = ((uint64_t)tile << 32) | s_depth[lo];
-        vals[r] = (uint32_t)(g0 + lo);
+        if (BUCKET) {
+            const uint32_t pos = __ldg(&ranges[tile].x) + atomicAdd(tile_cursor + (size_t)tile * CURSOR_STRIDE, 1u);
+            if (pos < capacity) keys[pos] = ((uint64_t)s_depth[lo] << 32) | (uint32_t)(g0 + lo);
+        } else {
+            keys[r] = ((uint64_t)tile << 32) | s_depth[lo];
+            vals[r] = (uint32_t)(g0 + lo);
+        }
     }
 }
 
 int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, int64_t capacity, uint64_t *keys, uint32_t *vals,
-                     cudaStream_t s) {
+                     uint32_t *tile_cursor, const uint2 *ranges, cudaStream_t s) {
     (void)H;
     const int gx = (W + TILE - 1) / TILE;
+    const uint32_t cap = (uint32_t)min(capacity, (int64_t)0xffffffffll);
     LVDGS_PRE(s);
-    emit_keys_kernel<<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, (uint32_t)min(capacity, (int64_t)0xffffffffll), g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals);
+    if (tile_cursor)
+        emit_keys_kernel<true><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, tile_cursor, ranges);
+    else
+        emit_keys_kernel<false><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, nullptr, nullptr);
     LVDGS_LAUNCHED(s, "emit_keys");
     return 0;
 }

@@ -1,0 +1,293 @@
+// tile_sort.cu -- K4 as a segmented sort: one CTA sorts one tile's instance list in shared memory.
+//
+// The reference sorts all R (tile | depth) keys with one global stable radix sort (cub::DeviceRadixSort, SURVEY.md K4:
+// 6 passes x 24 B per instance through HBM, and at R ~ 1-2 M every pass is one latency-bound wave).  Here the tile
+// ranges are known BEFORE any key exists (binning_prep integrates the per-tile counts), so the key emission drops every
+// instance straight into its tile's segment (slot = atomicAdd on the tile's cursor) and what is left is ~2000
+// independent sorts of ~1000 elements -- shared-memory work with no HBM round trips.
+//
+// Bit-exactness: the stable global sort orders a tile's instances by depth bits, ties by emission order = ascending
+// Gaussian index (a Gaussian appears at most once per tile).  That is the total order of the 64-bit word
+// (depth bits << 32 | Gaussian index), whose sorted sequence is unique -- so ANY sorting network yields the
+// reference's list, regardless of the (non-deterministic) slot order the atomics produced.
+//
+// Network: bitonic sort in its all-ascending form (first step of every merge level compares i with its mirror image
+// inside the 2^k block, the remaining steps compare i with i + j).  Because every comparator moves the smaller word to
+// the lower index, elements beyond n behave like +inf without being stored: comparators whose upper index is >= n are
+// skipped, and with the index maps below the live comparators of a stage are a PREFIX [0, cnt) -- the work is
+// proportional to n, not to the next power of two.
+// Lists longer than the shared-memory capacity are handled by the same network with the wide stages run in place in
+// global memory (L2) and the narrow ones chunk by chunk in shared memory.
+#include "common.cuh"
+
+namespace lvdgs {
+
+__device__ __forceinline__ uint64_t lds_u64(uint32_t a) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u64(uint32_t a, uint64_t v) {
+    asm volatile("st.shared.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory");
+}
+
+// ---- register-blocked network --------------------------------------------------------------------------------------
+// A plain shared-memory bitonic sort is bound by the LSU pipe (4 accesses per comparator, 66 stages at n = 2048, 2-4-way
+// bank conflicts at small strides).  Here a thread takes EIGHT words into registers and runs up to three consecutive
+// stages on them before writing back, so a round trip through shared memory serves 12 comparators instead of 4:
+//   * levels 2, 4, 8            : 8 consecutive words, all six stages in one round trip;
+//   * head of level K >= 16     : 4 words r + S m of the lower half of a K-block and their 4 mirror images (S = K/8):
+//                                 the flip stage and the stages j = K/4, K/8;
+//   * rest of the level         : words i0 + S m (m = 0..7): the stages j = 4S, 2S, S, three at a time down to j = 1.
+// Word i lives at i + (i >> 4) (one pad word per 16): every access pattern above is conflict-free (two wavefronts per
+// 64-bit warp access) AND the eight addresses of a thread are its first address plus compile-time constants
+// (d + (d >> 4) for d = S m: the low four bits never carry, see the index maps), so a round trip is one address
+// computation + 8 LDS + 8 STS with immediate offsets.  Words [n, next power of two) are physically filled with TS_PAD,
+// which removes every bounds test from the loads and stores (a comparator never moves a pad word below n).
+// 24 round trips for n = 2048 instead of 66 conflicted stages; the kernel is bound by the ALU pipe (6 ALU instructions
+// per 64-bit comparator: sm_100a has no 64-bit min/max, and DMNMX on the words read as doubles does not exist either).
+constexpr uint64_t TS_PAD = ~0ull;
+constexpr int ts_phys(int i) { return i + (i >> 4); }
+constexpr size_t ts_smem_bytes(int cap) { return (size_t)ts_phys(cap) * sizeof(uint64_t); }
+__device__ __forceinline__ uint32_t ts_addr(uint32_t a_s, int i) { return a_s + (uint32_t)((i + (i >> 4)) << 3); }
+__device__ __forceinline__ void ce(uint64_t &a, uint64_t &b) {        // a sits at the lower index
+    const bool sw = a > b;
+    const uint64_t lo = sw ? b : a, hi = sw ? a : b;
+    a = lo; b = hi;
+}
+
+template <int THREADS>
+__device__ __forceinline__ void ts_levels_2_4_8(uint32_t a_s, int n, int tid) {
+    __syncthreads();
+    for (int g = tid; g * 8 < n; g += THREADS) {
+        const uint32_t a0 = ts_addr(a_s, 8 * g);
+        uint64_t v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = lds_u64(a0 + 8 * m);
+        ce(v[0], v[1]); ce(v[2], v[3]); ce(v[4], v[5]); ce(v[6], v[7]);
+        ce(v[0], v[3]); ce(v[1], v[2]); ce(v[4], v[7]); ce(v[5], v[6]);
+        ce(v[0], v[1]); ce(v[2], v[3]); ce(v[4], v[5]); ce(v[6], v[7]);
+        ce(v[0], v[7]); ce(v[1], v[6]); ce(v[2], v[5]); ce(v[3], v[4]);
+        ce(v[0], v[2]); ce(v[1], v[3]); ce(v[4], v[6]); ce(v[5], v[7]);
+        ce(v[0], v[1]); ce(v[2], v[3]); ce(v[4], v[5]); ce(v[6], v[7]);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) sts_u64(a0 + 8 * m, v[m]);
+    }
+}
+
+// flip stage of level K and the stages j = K/4, K/8
+template <int THREADS, int K>
+__device__ __forceinline__ void ts_flip_group(uint32_t a_s, int n, int tid) {
+    constexpr int S = K / 8;
+    const int G = ((n + K - 1) / K) * S;
+    __syncthreads();
+    for (int g = tid; g < G; g += THREADS) {
+        const int r = g & (S - 1), base = (g / S) * K;
+        const int il = base + r, iu = base + K - 1 - r;
+        if (il >= n) continue;
+        const uint32_t al = ts_addr(a_s, il), au = ts_addr(a_s, iu);
+        uint64_t lo[4], up[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { lo[m] = lds_u64(al + 8 * ts_phys(S * m)); up[m] = lds_u64(au - 8 * ts_phys(S * m)); }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) ce(lo[m], up[m]);
+        ce(lo[0], lo[2]); ce(lo[1], lo[3]); ce(up[2], up[0]); ce(up[3], up[1]);
+        ce(lo[0], lo[1]); ce(lo[2], lo[3]); ce(up[1], up[0]); ce(up[3], up[2]);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { sts_u64(al + 8 * ts_phys(S * m), lo[m]); sts_u64(au - 8 * ts_phys(S * m), up[m]); }
+    }
+}
+
+// the last CNT of the stages j = 4S, 2S, S
+template <int THREADS, int S, int CNT>
+__device__ __forceinline__ void ts_j_group(uint32_t a_s, int n, int tid) {
+    const int G = ((n + 8 * S - 1) / (8 * S)) * S;
+    __syncthreads();
+    for (int g = tid; g < G; g += THREADS) {
+        const int i0 = (g / S) * (8 * S) + (g & (S - 1));
+        if (i0 + S >= n) continue;             // fewer than two live words: nothing to compare
+        const uint32_t a0 = ts_addr(a_s, i0);
+        uint64_t v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = lds_u64(a0 + 8 * ts_phys(S * m));
+        if (CNT >= 3) { ce(v[0], v[4]); ce(v[1], v[5]); ce(v[2], v[6]); ce(v[3], v[7]); }
+        if (CNT >= 2) { ce(v[0], v[2]); ce(v[1], v[3]); ce(v[4], v[6]); ce(v[5], v[7]); }
+        ce(v[0], v[1]); ce(v[2], v[3]); ce(v[4], v[5]); ce(v[6], v[7]);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) sts_u64(a0 + 8 * ts_phys(S * m), v[m]);
+    }
+}
+
+constexpr int ts_ilog2(int x) { return x <= 1 ? 0 : 1 + ts_ilog2(x / 2); }
+
+// stages j = J, J/2, ... 1
+template <int THREADS, int J>
+__device__ __forceinline__ void ts_j_stages_from(uint32_t a_s, int n, int tid) {
+    if constexpr (J >= 1) {
+        constexpr int CNT = ts_ilog2(J) + 1 >= 3 ? 3 : ts_ilog2(J) + 1;
+        constexpr int S = J >> (CNT - 1);
+        if (S < n) ts_j_group<THREADS, S, CNT>(a_s, n, tid);
+        ts_j_stages_from<THREADS, S / 2>(a_s, n, tid);
+    }
+}
+
+// merge levels K, 2K, ... CAP (K >= 16) on the n (<= CAP) words at shared address a_s
+template <int THREADS, int K, int CAP>
+__device__ __forceinline__ void ts_levels_from(uint32_t a_s, int n, int tid) {
+    if constexpr (K <= CAP) {
+        if (K / 2 < n) {              // otherwise the data is already one sorted run
+            ts_flip_group<THREADS, K>(a_s, n, tid);
+            ts_j_stages_from<THREADS, K / 16>(a_s, n, tid);
+            ts_levels_from<THREADS, K * 2, CAP>(a_s, n, tid);
+        }
+    }
+}
+
+// words [n, upto) := TS_PAD; upto = 0: the next power of two >= max(n, 8), which bounds every index a full sort touches
+template <int THREADS>
+__device__ __forceinline__ void ts_fill_pad(uint32_t a_s, int n, int tid, int upto = 0) {
+    const int npad = upto ? upto : (n <= 8 ? 8 : 1 << (32 - __clz(n - 1)));
+    for (int i = n + tid; i < npad; i += THREADS) sts_u64(ts_addr(a_s, i), TS_PAD);
+}
+
+// full sort of n <= CAP words; the caller has written them (through ts_addr) and must barrier before reading them back
+template <int THREADS, int CAP>
+__device__ __forceinline__ void ts_sort_smem(uint32_t a_s, int n, int tid) {
+    ts_fill_pad<THREADS>(a_s, n, tid);
+    ts_levels_2_4_8<THREADS>(a_s, n, tid);
+    ts_levels_from<THREADS, 16, CAP>(a_s, n, tid);
+}
+
+__device__ __forceinline__ void ce_global(uint64_t *g, int lo, int hi) {
+    const uint64_t a = g[lo], b = g[hi];
+    if (a > b) { g[lo] = b; g[hi] = a; }
+}
+
+// Sorts the segments of the tiles whose length n satisfies n_lo <= n < n_hi (one launch per size class).  tile_order
+// lists the tiles by decreasing length class (quarter-octave buckets, so a power-of-two boundary never splits a bucket):
+// the long-list class runs as a few persistent CTAs that walk the head of tile_order and stop at the first short list;
+// the short-list class has one CTA per tile.  seg: (depth bits << 32 | Gaussian) in slot order (sorted in place when
+// n > CAP).
+template <int THREADS, int CAP, bool CHUNKED>
+__device__ __forceinline__ void tile_sort_one(int tile, uint2 range, uint64_t *seg, uint64_t *__restrict__ keys_out,
+                                              uint32_t *__restrict__ vals_out, uint64_t *s_words) {
+    const uint32_t n32 = range.y - range.x;
+    const int n = (int)n32, tid = threadIdx.x;
+    const uint32_t a_s = smem_u32(s_words);
+    uint64_t *g = seg + range.x;
+    const uint64_t tile_hi = (uint64_t)(uint32_t)tile << 32;
+    if (!CHUNKED || n <= CAP) {
+        for (int i = tid; i < n; i += THREADS) sts_u64(ts_addr(a_s, i), g[i]);
+        ts_sort_smem<THREADS, CAP>(a_s, n, tid);
+        __syncthreads();
+        for (int i = tid; i < n; i += THREADS) {
+            const uint64_t w = lds_u64(ts_addr(a_s, i));
+            keys_out[range.x + i] = tile_hi | (w >> 32);
+            vals_out[range.x + i] = (uint32_t)w;
+        }
+        return;
+    }
+    if constexpr (CHUNKED) {
+        // phase 1: every CAP-chunk becomes a sorted run
+        for (int base = 0; base < n; base += CAP) {
+            const int cn = min(CAP, n - base);
+            __syncthreads();
+            for (int i = tid; i < cn; i += THREADS) sts_u64(ts_addr(a_s, i), g[base + i]);
+            ts_sort_smem<THREADS, CAP>(a_s, cn, tid);
+            __syncthreads();
+            for (int i = tid; i < cn; i += THREADS) g[base + i] = lds_u64(ts_addr(a_s, i));
+        }
+        // phase 2: merge levels above CAP; wide stages in global memory, stages below CAP per chunk in shared memory
+        for (int64_t k = 2 * (int64_t)CAP; (k >> 1) < n; k <<= 1) {
+            __syncthreads();
+            {
+                const int hk = (int)(k >> 1);
+                const int cnt = (int)(n / k) * hk + max(0, (int)(n % k) - hk);
+                for (int c = tid; c < cnt; c += THREADS) {
+                    const int r = c & (hk - 1), mid = ((c - r) << 1) + hk;
+                    ce_global(g, mid - 1 - r, mid + r);
+                }
+            }
+            for (int j = (int)(k >> 2); j >= CAP; j >>= 1) {
+                __syncthreads();
+                const int cnt = (n / (2 * j)) * j + max(0, n % (2 * j) - j);
+                for (int c = tid; c < cnt; c += THREADS) {
+                    const int lo = c + (c & ~(j - 1));
+                    ce_global(g, lo, lo + j);
+                }
+            }
+            for (int base = 0; base < n; base += CAP) {
+                const int cn = min(CAP, n - base);
+                __syncthreads();
+                for (int i = tid; i < cn; i += THREADS) sts_u64(ts_addr(a_s, i), g[base + i]);
+                ts_fill_pad<THREADS>(a_s, cn, tid, CAP);     // the wide groups of a partial chunk reach up to CAP
+                ts_j_stages_from<THREADS, CAP / 2>(a_s, cn, tid);
+                __syncthreads();
+                for (int i = tid; i < cn; i += THREADS) g[base + i] = lds_u64(ts_addr(a_s, i));
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += THREADS) {
+            const uint64_t w = g[i];
+            keys_out[range.x + i] = tile_hi | (w >> 32);
+            vals_out[range.x + i] = (uint32_t)w;
+        }
+    }
+}
+
+template <int THREADS, int CAP>
+__global__ void __launch_bounds__(THREADS) tile_sort_short_kernel(uint32_t n_hi, uint32_t capacity, const uint32_t *__restrict__ n_dev,
+                                                                  const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_order,
+                                                                  uint64_t *seg, uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+    __shared__ uint64_t s_words[ts_phys(CAP)];
+    const int tile = (int)__ldg(tile_order + blockIdx.x);
+    const uint2 range = ranges[tile];
+    const uint32_t n = range.y - range.x;
+    if (n == 0 || n >= n_hi) return;
+    if (n_dev && __ldg(n_dev) > capacity) return;       // speculative launch with too small an arena: the host re-runs
+    tile_sort_one<THREADS, CAP, false>(tile, range, seg, keys_out, vals_out, s_words);
+}
+
+template <int THREADS, int CAP>
+__global__ void __launch_bounds__(THREADS) tile_sort_long_kernel(uint32_t n_lo, int tiles, uint32_t capacity, const uint32_t *__restrict__ n_dev,
+                                                                 const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_order,
+                                                                 uint64_t *seg, uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+    extern __shared__ uint64_t s_dyn[];
+    if (n_dev && __ldg(n_dev) > capacity) return;
+    for (int i = blockIdx.x; i < tiles; i += gridDim.x) {
+        const int tile = (int)__ldg(tile_order + i);
+        const uint2 range = ranges[tile];
+        if (range.y - range.x < n_lo) break;            // tile_order is sorted by length class: nothing longer follows
+        __syncthreads();
+        tile_sort_one<THREADS, CAP, true>(tile, range, seg, keys_out, vals_out, s_dyn);
+    }
+}
+
+#ifndef LVDGS_TS_SHORT_THREADS
+#define LVDGS_TS_SHORT_THREADS 256
+#endif
+constexpr int TS_SHORT_THREADS = LVDGS_TS_SHORT_THREADS, TS_SHORT_CAP = 2048;    // lists of 1 .. 2047 instances
+constexpr int TS_LONG_THREADS = 1024, TS_LONG_CAP = 16384;
+
+int launch_tile_sort(int tiles, int64_t capacity, const uint32_t *n_dev, const uint2 *ranges, const uint32_t *tile_order,
+                     uint64_t *seg, uint64_t *keys_out, uint32_t *vals_out, cudaStream_t s) {
+    if (tiles <= 0) return 0;
+    const uint32_t cap = (uint32_t)min(capacity, (int64_t)0xffffffffll);
+    static int sm_count = 0;
+    auto long_k = tile_sort_long_kernel<TS_LONG_THREADS, TS_LONG_CAP>;
+    if (!sm_count) {
+        int dev = 0;
+        LVDGS_CHECK(cudaGetDevice(&dev));
+        LVDGS_CHECK(cudaFuncSetAttribute(long_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts_smem_bytes(TS_LONG_CAP)));
+        LVDGS_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    LVDGS_PRE(s);
+    long_k<<<min(tiles, sm_count), TS_LONG_THREADS, ts_smem_bytes(TS_LONG_CAP), s>>>((uint32_t)TS_SHORT_CAP, tiles, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out);
+    LVDGS_LAUNCHED(s, "tile_sort_long");
+    LVDGS_PRE(s);
+    tile_sort_short_kernel<TS_SHORT_THREADS, TS_SHORT_CAP><<<tiles, TS_SHORT_THREADS, 0, s>>>((uint32_t)TS_SHORT_CAP, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out);
+    LVDGS_LAUNCHED(s, "tile_sort");
+    return 0;
+}
+
+}  // namespace lvdgs

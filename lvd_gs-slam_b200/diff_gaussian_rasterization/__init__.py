@@ -139,6 +139,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             _tls.store = None
         _native.check(rc, "lvdgs_rasterize_forward")
         ctx.rs = rs
+        ctx.flags = prm.flags          # the backward must see the forward's sort layout
         ctx.num_rendered = R.value
         ctx.capacity = cap.value
         if SPECULATIVE:   # decay slowly, grow at once
@@ -181,6 +182,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         flat_s = flat[off:off + nscratch]
         g_tau = flat[0:6]
         prm = _params(rs, P, M)
+        prm.flags = ctx.flags
         if pose_only:
             prm.flags |= 8          # LVDGS_FLAG_POSE_ONLY
         _select_device(L, dev)

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC_DIR = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 SO_PATH = os.path.join(PKG_DIR, "liblvdgs.so")
-SOURCES = ["api.cu", "preprocess.cu", "radix_sort.cu", "blend_forward.cu", "blend_backward.cu",
+SOURCES = ["api.cu", "preprocess.cu", "radix_sort.cu", "tile_sort.cu", "blend_forward.cu", "blend_backward.cu",
            "preprocess_backward.cu", "knn.cu", "adam.cu", "cub_compare.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("LVDGS_NVCC_DEFS", "").split()
@@ -90,7 +90,7 @@ class BinningLayout(C.Structure):
 
 
 class ImgLayout(C.Structure):
-    _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "ranges", "tile_order", "tile_grid", "sort_hist", "total")]
+    _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "ranges", "tile_order", "tile_grid", "sort_hist", "tile_cursor", "total")]
 
 
 RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int32, C.c_size_t)

@@ -283,3 +283,75 @@ def test_map_size_churn_between_renders():
         np.testing.assert_array_equal(internals["point_list"], fwd["point_list"])
         ok = fwd["margin"] > 1e-5
         assert np.abs(out["color"][:, ok] - fwd["color"][:, ok]).max() < 1e-5
+
+
+def _crowded_scene(cam, n_crowd, n_rest, seed=4):
+    """Most Gaussians project into a handful of tiles (a zoomed-in surface): lists of tens of thousands of instances,
+    many of them with EQUAL depth bits (ties must resolve by Gaussian index)."""
+    rng = np.random.default_rng(seed)
+    sc = synth.make_scene(n_crowd + n_rest, cam, seed=seed)
+    z = rng.uniform(4.0, 6.0, n_crowd)
+    z[: n_crowd // 3] = np.float32(5.0)                      # exact depth ties
+    px = rng.uniform(300.0, 318.0, n_crowd); py = rng.uniform(100.0, 118.0, n_crowd)
+    sc["means3D"][:n_crowd, 0] = (px - cam.cx) / cam.fx * z
+    sc["means3D"][:n_crowd, 1] = (py - cam.cy) / cam.fy * z
+    sc["means3D"][:n_crowd, 2] = z
+    sc["scales"][:n_crowd] = (z[:, None] / cam.fx) * rng.uniform(0.3, 1.2, (n_crowd, 3))
+    sc["opacities"][:n_crowd] = rng.uniform(0.01, 0.05, (n_crowd, 1))
+    perm = rng.permutation(n_crowd + n_rest)
+    for k in ("means3D", "scales", "rotations", "opacities", "shs"):
+        sc[k] = np.ascontiguousarray(sc[k][perm])
+    return sc
+
+
+@pytest.mark.parametrize("n_crowd", [3_000, 30_000, 150_000])
+def test_tile_sort_long_lists_and_ties(n_crowd):
+    """The per-tile shared-memory sort (default) on lists beyond its short class (2047), beyond the shared-memory
+    capacity of the long class (16384: wide stages in global memory, one / several levels), with depth ties; against the
+    oracle's stable sort and against the global onesweep path (LVDGS_FLAG_GLOBAL_SORT)."""
+    import diff_gaussian_rasterization as dgr
+    cam = synth.make_camera("vga")
+    sc = _crowded_scene(cam, n_crowd, 5_000)
+    bg = np.zeros(3, np.float32)
+    fwd, _ = run_oracle(sc, cam, bg)
+    r = fwd["ranges"].reshape(-1, 2).astype(np.int64)
+    longest = int((r[:, 1] - r[:, 0]).max())
+    assert longest > {3_000: 2047, 30_000: 16384, 150_000: 70_000}[n_crowd], longest
+    res = {}
+    old = dgr.FLAGS
+    try:
+        for flags in (0, 16):
+            dgr.FLAGS = flags
+            dgr._capacity_hint.clear()
+            out, internals, _ = run_cuda(sc, cam, bg, debug=False)
+            res[flags] = (out, internals)
+            np.testing.assert_array_equal(internals["ranges"], fwd["ranges"])
+            np.testing.assert_array_equal(internals["keys_sorted"], fwd["keys_sorted"])
+            np.testing.assert_array_equal(internals["point_list"], fwd["point_list"])
+    finally:
+        dgr.FLAGS = old
+    for k in ("color", "depth", "opacity", "radii", "n_touched"):
+        np.testing.assert_array_equal(res[0][0][k], res[16][0][k])
+
+
+def test_global_sort_flag_matches_default_with_gradients():
+    import diff_gaussian_rasterization as dgr
+    cam, sc, bg = make_case("kitti30k_bg")
+    H, W = cam.image_height, cam.image_width
+    rng = np.random.default_rng(8)
+    gc = rng.normal(0, 1, (3, H, W)).astype(np.float32)
+    gd = rng.normal(0, 1, (1, H, W)).astype(np.float32)
+    old = dgr.FLAGS
+    res = {}
+    try:
+        for flags in (0, 16):
+            dgr.FLAGS = flags
+            res[flags] = run_cuda(sc, cam, bg, grads=(gc, gd, None), debug=False)
+    finally:
+        dgr.FLAGS = old
+    for k in ("keys_sorted", "point_list", "ranges", "n_contrib"):
+        np.testing.assert_array_equal(res[0][1][k], res[16][1][k])
+    for k in ("color", "depth", "opacity"):
+        np.testing.assert_array_equal(res[0][0][k], res[16][0][k])
+    assert rel_err(res[0][2]["means3D"], res[16][2]["means3D"]) < 1e-4
+    assert rel_err(res[0][2]["theta"], res[16][2]["theta"]) < 1e-4
