@@ -25,6 +25,13 @@ constexpr int BB_PPT = LVDGS_BB_PPT;
 constexpr int BB_WARPS = 8 / BB_PPT;
 constexpr int BB_THREADS = BB_WARPS * 32;
 constexpr int BB_ROWS = 4 * BB_PPT;            // pixel rows per warp block
+// instances staged per thread and barrier pair: the four warps of a tile meet once per batch, and the busiest block of a
+// batch sets the pace -- a longer batch averages the per-block hit counts out (fewer, better balanced rendezvous)
+#ifndef LVDGS_BB_SPT
+#define LVDGS_BB_SPT 2
+#endif
+constexpr int BB_SPT = LVDGS_BB_SPT;
+constexpr int BB_BATCH = BB_THREADS * BB_SPT;
 #ifndef LVDGS_BB_DIRECT_MAX
 #define LVDGS_BB_DIRECT_MAX 2
 #endif
@@ -74,11 +81,11 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     const uint32_t *__restrict__ tile_order, const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
     const float *__restrict__ dL_dout_color, const float *__restrict__ dL_dout_depth,
     const float *__restrict__ dL_dout_opacity, float *__restrict__ acc) {
-    __shared__ uint32_t s_id[BB_THREADS];
-    __shared__ float2 s_xy[BB_THREADS];
-    __shared__ float4 s_co[BB_THREADS];
-    __shared__ float4 s_cd[BB_THREADS];
-    __shared__ uint32_t s_mask[BB_WARPS][BB_WARPS];     // [staging warp][pixel block]
+    __shared__ uint32_t s_id[BB_BATCH];
+    __shared__ float2 s_xy[BB_BATCH];
+    __shared__ float4 s_co[BB_BATCH];
+    __shared__ float4 s_cd[BB_BATCH];
+    __shared__ uint32_t s_mask[BB_BATCH / 32][BB_WARPS];     // [group of 32 staged entries][pixel block]
     __shared__ uint32_t s_top[BB_WARPS];
 
     const int tile = tile_order ? (int)__ldg(tile_order + blockIdx.x) : (int)blockIdx.x;   // heaviest tiles first
@@ -132,47 +139,51 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     const bool commits = !(lane & 1) && slot < 11 && slot != 7;
 
     // entries are visited in decreasing contributor index k = top-1 ... 0
-    for (int remaining = (int)top; remaining > 0; remaining -= BB_THREADS) {
+    for (int remaining = (int)top; remaining > 0; remaining -= BB_BATCH) {
         __syncthreads();
-        const int nb = min(BB_THREADS, remaining);
-        uint32_t blocks = 0;
-        if ((int)threadIdx.x < nb) {
-            const uint32_t id = __ldg(point_list + range.x + (uint32_t)(remaining - 1 - (int)threadIdx.x));
-            const float4 m = __ldg(means2D + id);
-            s_id[threadIdx.x] = id;
-            s_xy[threadIdx.x] = make_float2(m.x, m.y);
-            const float4 co = __ldg(conic_opacity + id);
-            s_co[threadIdx.x] = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);   // as forward
-            s_cd[threadIdx.x] = __ldg(rgbd + id);
-            const float rx = m.x - tx0, ry = m.y - ty0;
-            uint32_t xb = 0, yb = 0;
-            if (!(rx + m.z < 0.f) && !(rx - m.z > 7.f)) xb |= 1u;
-            if (!(rx + m.z < 8.f) && !(rx - m.z > 15.f)) xb |= 2u;
+        const int nb = min(BB_BATCH, remaining);
 #pragma unroll
-            for (int r = 0; r < BB_WARPS / 2; ++r)
-                if (!(ry + m.w < (float)(BB_ROWS * r)) && !(ry - m.w > (float)(BB_ROWS * r + BB_ROWS - 1))) yb |= 1u << r;
+        for (int u = 0; u < BB_SPT; ++u) {
+            const int e = u * BB_THREADS + (int)threadIdx.x;      // entry of the batch this thread stages
+            uint32_t blocks = 0;
+            if (e < nb) {
+                const uint32_t id = __ldg(point_list + range.x + (uint32_t)(remaining - 1 - e));
+                const float4 m = __ldg(means2D + id);
+                s_id[e] = id;
+                s_xy[e] = make_float2(m.x, m.y);
+                const float4 co = __ldg(conic_opacity + id);
+                s_co[e] = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);   // as forward
+                s_cd[e] = __ldg(rgbd + id);
+                const float rx = m.x - tx0, ry = m.y - ty0;
+                uint32_t xb = 0, yb = 0;
+                if (!(rx + m.z < 0.f) && !(rx - m.z > 7.f)) xb |= 1u;
+                if (!(rx + m.z < 8.f) && !(rx - m.z > 15.f)) xb |= 2u;
 #pragma unroll
-            for (int r = 0; r < BB_WARPS / 2; ++r)
-                if (yb & (1u << r)) blocks |= xb << (2 * r);
-            if (blocks) {       // exact ellipse-vs-block test on the survivors of the box test (as in the forward)
-                const float lvl = 2.02f * __logf(255.f * co.w) + 0.02f;
-                const float rA = __fdividef(1.f, co.x), rC = __fdividef(1.f, co.z);
-                uint32_t rest = blocks;
-                while (rest) {
-                    const int r = __ffs(rest) - 1;
-                    rest &= rest - 1;
-                    const float X0 = 8.f * (r & 1), Y0 = (float)(BB_ROWS * (r >> 1));
-                    if (!ellipse_reaches_rect(rx, ry, co.x, co.y, co.z, rA, rC, lvl, X0, Y0, X0 + 7.f, Y0 + (float)(BB_ROWS - 1))) blocks &= ~(1u << r);
+                for (int r = 0; r < BB_WARPS / 2; ++r)
+                    if (!(ry + m.w < (float)(BB_ROWS * r)) && !(ry - m.w > (float)(BB_ROWS * r + BB_ROWS - 1))) yb |= 1u << r;
+#pragma unroll
+                for (int r = 0; r < BB_WARPS / 2; ++r)
+                    if (yb & (1u << r)) blocks |= xb << (2 * r);
+                if (blocks) {       // exact ellipse-vs-block test on the survivors of the box test (as in the forward)
+                    const float lvl = 2.02f * __logf(255.f * co.w) + 0.02f;
+                    const float rA = __fdividef(1.f, co.x), rC = __fdividef(1.f, co.z);
+                    uint32_t rest = blocks;
+                    while (rest) {
+                        const int r = __ffs(rest) - 1;
+                        rest &= rest - 1;
+                        const float X0 = 8.f * (r & 1), Y0 = (float)(BB_ROWS * (r >> 1));
+                        if (!ellipse_reaches_rect(rx, ry, co.x, co.y, co.z, rA, rC, lvl, X0, Y0, X0 + 7.f, Y0 + (float)(BB_ROWS - 1))) blocks &= ~(1u << r);
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int r = 0; r < BB_WARPS; ++r) {
-            const uint32_t m = __ballot_sync(0xffffffffu, (blocks >> r) & 1u);
-            if (lane == r) s_mask[warp][r] = m;
+            for (int r = 0; r < BB_WARPS; ++r) {
+                const uint32_t m = __ballot_sync(0xffffffffu, (blocks >> r) & 1u);
+                if (lane == r) s_mask[u * BB_WARPS + warp][r] = m;
+            }
         }
         __syncthreads();
-        for (int wp = 0; wp < BB_WARPS; ++wp) {
+        for (int wp = 0; wp < BB_BATCH / 32; ++wp) {
             uint32_t mask = s_mask[wp][warp];
             {   // entries with contributor index >= wtop (j < remaining - wtop) contribute to no pixel of this warp
                 const int first_j = remaining - (int)wtop - wp * 32;
@@ -187,44 +198,58 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 const float4 co = lds128(a_q + j * 16);
                 const float4 cd = lds128(a_cd + j * 16);
                 const float dx = xy.x - pfx;
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                // phase 1 (cheap, per pixel): does this pixel blend the Gaussian at all?  The rest of the body is
+                // branch-free: a pixel that does not contributes with alpha = 0 and G = 0, which leaves its T / B
+                // recurrences untouched and adds zeros to the warp's sums -- no divergent regions, and the two pixels'
+                // instruction streams interleave.
+                float dy[BB_PPT], G[BB_PPT], al[BB_PPT];
                 bool valid = false;
 #pragma unroll
                 for (int q = 0; q < BB_PPT; ++q) {
-                    if (k < last[q]) {
-                        const float dy = xy.y - pfy[q];
-                        const float p2 = fmaf(co.z * dy, dy, dx * fmaf(co.x, dx, co.y * dy));
-                        if (p2 <= 0.f) {
-                            const float G = ex2_approx(p2);
-                            const float alpha = fminf(0.99f, co.w * G);
-                            if (alpha >= 1.f / 255.f) {
-                                valid = true;
-                                const float one_m = 1.f - alpha;
-                                const float inv = __fdividef(1.f, one_m);
-                                T[q] *= inv;
-                                const float wgt = alpha * T[q];
-                                float dL_dalpha = (cd.x - B0[q]) * dp0[q] + (cd.y - B1[q]) * dp1[q] +
-                                                  (cd.z - B2[q]) * dp2[q] + (cd.w - Bd[q]) * dpd[q];
-                                dL_dalpha *= T[q];
-                                dL_dalpha -= Tf[q] * inv * bgd[q];
-                                B0[q] = alpha * cd.x + one_m * B0[q];
-                                B1[q] = alpha * cd.y + one_m * B1[q];
-                                B2[q] = alpha * cd.z + one_m * B2[q];
-                                Bd[q] = alpha * cd.w + one_m * Bd[q];
-                                const float m = G * dL_dalpha;
-                                const float mdx = m * dx, mdy = m * dy;
-                                v[0] += mdx; v[1] += mdy;
-                                v[2] += mdx * dx; v[3] += mdx * dy; v[4] += mdy * dy;
-                                v[5] += m;
-                                v[6] += wgt * dpd[q];
-                                v[8] += wgt * dp0[q]; v[9] += wgt * dp1[q]; v[10] += wgt * dp2[q];
-                            }
-                        }
-                    }
+                    dy[q] = xy.y - pfy[q];
+                    const float p2 = fmaf(co.z * dy[q], dy[q], dx * fmaf(co.x, dx, co.y * dy[q]));
+                    const float g = ex2_approx(p2);
+                    const float a = fminf(0.99f, co.w * g);
+                    const bool ok = k < last[q] && p2 <= 0.f && a >= 1.f / 255.f;
+                    G[q] = ok ? g : 0.f;
+                    al[q] = ok ? a : 0.f;
+                    valid |= ok;
                 }
                 const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                if (!vmask) continue;
+                float v[16];
+#pragma unroll
+                for (int q = 0; q < BB_PPT; ++q) {
+                    const float alpha = al[q];
+                    const float one_m = 1.f - alpha;
+                    const float inv = rcp_approx(one_m);          // 1 - alpha >= 0.01: no denormal handling needed
+                    T[q] *= inv;
+                    const float wgt = alpha * T[q];
+                    float dL_dalpha = (cd.x - B0[q]) * dp0[q] + (cd.y - B1[q]) * dp1[q] +
+                                      (cd.z - B2[q]) * dp2[q] + (cd.w - Bd[q]) * dpd[q];
+                    dL_dalpha *= T[q];
+                    dL_dalpha -= Tf[q] * inv * bgd[q];
+                    B0[q] = alpha * cd.x + one_m * B0[q];
+                    B1[q] = alpha * cd.y + one_m * B1[q];
+                    B2[q] = alpha * cd.z + one_m * B2[q];
+                    Bd[q] = alpha * cd.w + one_m * Bd[q];
+                    const float m = G[q] * dL_dalpha;
+                    const float mdx = m * dx, mdy = m * dy[q];
+                    if (q == 0) {
+                        v[0] = mdx; v[1] = mdy;
+                        v[2] = mdx * dx; v[3] = mdx * dy[q]; v[4] = mdy * dy[q];
+                        v[5] = m;
+                        v[6] = wgt * dpd[q];
+                        v[8] = wgt * dp0[q]; v[9] = wgt * dp1[q]; v[10] = wgt * dp2[q];
+                    } else {
+                        v[0] += mdx; v[1] += mdy;
+                        v[2] = fmaf(mdx, dx, v[2]); v[3] = fmaf(mdx, dy[q], v[3]); v[4] = fmaf(mdy, dy[q], v[4]);
+                        v[5] += m;
+                        v[6] = fmaf(wgt, dpd[q], v[6]);
+                        v[8] = fmaf(wgt, dp0[q], v[8]); v[9] = fmaf(wgt, dp1[q], v[9]); v[10] = fmaf(wgt, dp2[q], v[10]);
+                    }
+                }
+                v[7] = v[11] = v[12] = v[13] = v[14] = v[15] = 0.f;
                 if (vmask) {
                     float *row = acc + (size_t)lds32(a_id + j * 4) * ACC_STRIDE;
                     if (__popc(vmask) <= BB_DIRECT_MAX) {

@@ -20,6 +20,11 @@ namespace lvdgs {
 
 constexpr int BF_THREADS = TILE_PIX;
 constexpr int BF_WARPS = BF_THREADS / 32;      // 8 warps = 2 x 4 blocks of 8 x 4 pixels
+#ifndef LVDGS_BF_SPT
+#define LVDGS_BF_SPT 1
+#endif
+constexpr int BF_SPT = LVDGS_BF_SPT;           // instances staged per thread and barrier pair (see blend_backward.cu)
+constexpr int BF_BATCH = BF_THREADS * BF_SPT;
 
 __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H, int gx, uint32_t capacity, const uint32_t *__restrict__ n_dev, const uint2 *__restrict__ ranges,
                                                                    const uint32_t *__restrict__ point_list,
@@ -29,11 +34,11 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
                                                                    const float *__restrict__ bg, float *__restrict__ out_color, float *__restrict__ out_depth,
                                                                    float *__restrict__ out_opacity, float *__restrict__ final_T,
                                                                    uint32_t *__restrict__ n_contrib, int32_t *__restrict__ n_touched) {
-    __shared__ uint32_t s_id[BF_THREADS];
-    __shared__ float2 s_xy[BF_THREADS];
-    __shared__ float4 s_co[BF_THREADS];
-    __shared__ float4 s_cd[BF_THREADS];
-    __shared__ uint32_t s_mask[BF_WARPS][BF_WARPS];     // [staging warp][pixel block]
+    __shared__ uint32_t s_id[BF_BATCH];
+    __shared__ float2 s_xy[BF_BATCH];
+    __shared__ float4 s_co[BF_BATCH];
+    __shared__ float4 s_cd[BF_BATCH];
+    __shared__ uint32_t s_mask[BF_BATCH / 32][BF_WARPS];     // [group of 32 staged entries][pixel block]
 
     const int tile = tile_order ? (int)__ldg(tile_order + blockIdx.x) : (int)blockIdx.x;   // heaviest tiles first
     const int tile_x = tile % gx, tile_y = tile / gx;
@@ -58,37 +63,41 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
     uint32_t batch_first = 0;                                      // list position of the batch's first entry
     bool warp_hi = true;     // some pixel of this warp may still satisfy T(1-alpha) > 0.5
 
-    for (uint32_t base = range.x; todo > 0; base += BF_THREADS, todo -= BF_THREADS, batch_first += BF_THREADS) {
+    for (uint32_t base = range.x; todo > 0; base += BF_BATCH, todo -= BF_BATCH, batch_first += BF_BATCH) {
         if (__syncthreads_count(done) == BF_THREADS) break;
-        uint32_t blocks = 0;                                        // bit (by*2+bx): instance may reach that block
-        if ((int)threadIdx.x < todo) {
-            const uint32_t id = __ldg(point_list + base + threadIdx.x);
-            const float4 m = __ldg(means2D + id);
-            s_id[threadIdx.x] = id;
-            s_xy[threadIdx.x] = make_float2(m.x, m.y);
-            const float4 co = __ldg(conic_opacity + id);
-            // exponent in base 2 with the -1/2 folded in: p2 = A' dx^2 + B' dx dy + C' dy^2, alpha = o 2^p2
-            s_co[threadIdx.x] = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);
-            s_cd[threadIdx.x] = __ldg(rgbd + id);
-            const float rx = m.x - tx0, ry = m.y - ty0;
-            uint32_t xb = 0, yb = 0;
-            // block column bx spans pixel centres [8bx, 8bx+7]; keep it unless the box [rx-hx, rx+hx] misses it
-            if (!(rx + m.z < 0.f) && !(rx - m.z > 7.f)) xb |= 1u;
-            if (!(rx + m.z < 8.f) && !(rx - m.z > 15.f)) xb |= 2u;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (!(ry + m.w < 4.f * q) && !(ry - m.w > 4.f * q + 3.f)) yb |= 1u << q;
+        for (int u = 0; u < BF_SPT; ++u) {
+            const int e = u * BF_THREADS + (int)threadIdx.x;       // entry of the batch this thread stages
+            uint32_t blocks = 0;                                    // bit (by*2+bx): instance may reach that block
+            if (e < todo) {
+                const uint32_t id = __ldg(point_list + base + e);
+                const float4 m = __ldg(means2D + id);
+                s_id[e] = id;
+                s_xy[e] = make_float2(m.x, m.y);
+                const float4 co = __ldg(conic_opacity + id);
+                // exponent in base 2 with the -1/2 folded in: p2 = A' dx^2 + B' dx dy + C' dy^2, alpha = o 2^p2
+                s_co[e] = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);
+                s_cd[e] = __ldg(rgbd + id);
+                const float rx = m.x - tx0, ry = m.y - ty0;
+                uint32_t xb = 0, yb = 0;
+                // block column bx spans pixel centres [8bx, 8bx+7]; keep it unless the box [rx-hx, rx+hx] misses it
+                if (!(rx + m.z < 0.f) && !(rx - m.z > 7.f)) xb |= 1u;
+                if (!(rx + m.z < 8.f) && !(rx - m.z > 15.f)) xb |= 2u;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (yb & (1u << q)) blocks |= xb << (2 * q);
-        }
+                for (int q = 0; q < 4; ++q)
+                    if (!(ry + m.w < 4.f * q) && !(ry - m.w > 4.f * q + 3.f)) yb |= 1u << q;
 #pragma unroll
-        for (int r = 0; r < BF_WARPS; ++r) {
-            const uint32_t m = __ballot_sync(0xffffffffu, (blocks >> r) & 1u);
-            if (lane == r) s_mask[warp][r] = m;
+                for (int q = 0; q < 4; ++q)
+                    if (yb & (1u << q)) blocks |= xb << (2 * q);
+            }
+#pragma unroll
+            for (int r = 0; r < BF_WARPS; ++r) {
+                const uint32_t m = __ballot_sync(0xffffffffu, (blocks >> r) & 1u);
+                if (lane == r) s_mask[u * BF_WARPS + warp][r] = m;
+            }
         }
         __syncthreads();
-        for (int wp = 0; wp < BF_WARPS; ++wp) {
+        for (int wp = 0; wp < BF_BATCH / 32; ++wp) {
             uint32_t m = s_mask[wp][warp];
             if (__all_sync(0xffffffffu, done)) break;
             if (warp_hi) warp_hi = __any_sync(0xffffffffu, !done && T > 0.5f);

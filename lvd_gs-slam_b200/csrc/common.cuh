@@ -77,6 +77,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 1/x on the MUFU pipe for normal-range x (no scaling around denormals, unlike __fdividef / __frcp_rn)
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 constexpr float LOG2E = 1.4426950408889634f;
 // pixel x coordinate assigned to a finished / out-of-image pixel: every Gaussian then evaluates to alpha = 0, so the
 // hot loop needs no per-pixel "done" test (dx^2 ~ 1e36 stays finite in float)
