@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     const uint32_t a_id = smem_u32(s_id), a_xy = smem_u32(s_xy), a_q = smem_u32(s_co), a_cd = smem_u32(s_cd);
 
     // per-pixel state (pixel q of this thread is in row py0 + 4q)
-    float pfy[BB_PPT], T[BB_PPT], Tf[BB_PPT], dp0[BB_PPT], dp1[BB_PPT], dp2[BB_PPT], dpd[BB_PPT], bgd[BB_PPT], B0[BB_PPT], B1[BB_PPT], B2[BB_PPT], Bd[BB_PPT];
+    float pfy[BB_PPT], T[BB_PPT], Tf[BB_PPT], dp0[BB_PPT], dp1[BB_PPT], dp2[BB_PPT], dpd[BB_PPT], bgd[BB_PPT], S[BB_PPT];
     uint32_t last[BB_PPT];
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
 #pragma unroll
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
         dpd[q] = (inside && dL_dout_depth) ? dL_dout_depth[pix] : 0.f;
         bgd[q] = bg0 * dp0[q] + bg1 * dp1[q] + bg2 * dp2[q];
         if (inside && dL_dout_opacity) bgd[q] -= dL_dout_opacity[pix];   // d(1 - T_final)/dalpha = +T_final/(1-alpha)
-        B0[q] = B1[q] = B2[q] = Bd[q] = 0.f;
+        S[q] = 0.f;
     }
     // warp-wide and tile-wide max of n_contrib: nothing at or beyond it contributes
     uint32_t wtop = last[0];
@@ -225,14 +225,12 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                     const float inv = rcp_approx(one_m);          // 1 - alpha >= 0.01: no denormal handling needed
                     T[q] *= inv;
                     const float wgt = alpha * T[q];
-                    float dL_dalpha = (cd.x - B0[q]) * dp0[q] + (cd.y - B1[q]) * dp1[q] +
-                                      (cd.z - B2[q]) * dp2[q] + (cd.w - Bd[q]) * dpd[q];
-                    dL_dalpha *= T[q];
+                    // the colour / depth blended BEHIND this Gaussian enters only through its dot product with dL/dpixel:
+                    // S = <B, dp> obeys the same recurrence as B itself (S <- alpha <c, dp> + (1 - alpha) S)
+                    const float cdp = fmaf(cd.w, dpd[q], fmaf(cd.z, dp2[q], fmaf(cd.y, dp1[q], cd.x * dp0[q])));
+                    float dL_dalpha = (cdp - S[q]) * T[q];
                     dL_dalpha -= Tf[q] * inv * bgd[q];
-                    B0[q] = alpha * cd.x + one_m * B0[q];
-                    B1[q] = alpha * cd.y + one_m * B1[q];
-                    B2[q] = alpha * cd.z + one_m * B2[q];
-                    Bd[q] = alpha * cd.w + one_m * Bd[q];
+                    S[q] = fmaf(alpha, cdp, one_m * S[q]);
                     const float m = G[q] * dL_dalpha;
                     const float mdx = m * dx, mdy = m * dy[q];
                     if (q == 0) {

@@ -105,30 +105,25 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
                 const int j = wp * 32 + b;
-                bool hit = false;
-                {
-                    const float2 xy = lds64(a_xy + j * 8);
-                    const float4 q = lds128(a_q + j * 16);
-                    const float dx = xy.x - pfx, dy = xy.y - pfy;
-                    const float p2 = fmaf(q.z * dy, dy, dx * fmaf(q.x, dx, q.y * dy));
-                    if (p2 <= 0.f) {
-                        const float alpha = fminf(0.99f, q.w * ex2_approx(p2));
-                        if (alpha >= 1.f / 255.f) {
-                            const float test_T = T * (1.f - alpha);
-                            if (test_T < 0.0001f) {
-                                done = true;
-                                pfx = PIX_PARKED;
-                            } else {
-                                const float4 cd = lds128(a_cd + j * 16);
-                                const float wgt = alpha * T;
-                                C0 = fmaf(cd.x, wgt, C0); C1 = fmaf(cd.y, wgt, C1); C2 = fmaf(cd.z, wgt, C2); D = fmaf(cd.w, wgt, D);
-                                hit = test_T > 0.5f;
-                                T = test_T;
-                                last_contributor = batch_first + (uint32_t)j + 1u;
-                            }
-                        }
-                    }
-                }
+                // branch-free body: a pixel that skips the Gaussian (alpha < 1/255, power > 0) or terminates on it
+                // blends with weight 0 and keeps its state; a terminated pixel is parked and sees alpha = 0 from then on
+                const float2 xy = lds64(a_xy + j * 8);
+                const float4 q = lds128(a_q + j * 16);
+                const float4 cd = lds128(a_cd + j * 16);
+                const float dx = xy.x - pfx, dy = xy.y - pfy;
+                const float p2 = fmaf(q.z * dy, dy, dx * fmaf(q.x, dx, q.y * dy));
+                const float alpha = fminf(0.99f, q.w * ex2_approx(p2));
+                const bool ok = p2 <= 0.f && alpha >= 1.f / 255.f;
+                const float test_T = T * (1.f - alpha);
+                const bool term = ok && test_T < 0.0001f;
+                const bool contrib = ok && !term;
+                const float wgt = contrib ? alpha * T : 0.f;
+                C0 = fmaf(cd.x, wgt, C0); C1 = fmaf(cd.y, wgt, C1); C2 = fmaf(cd.z, wgt, C2); D = fmaf(cd.w, wgt, D);
+                T = contrib ? test_T : T;
+                last_contributor = contrib ? batch_first + (uint32_t)j + 1u : last_contributor;
+                pfx = term ? PIX_PARKED : pfx;
+                done |= term;
+                const bool hit = contrib && test_T > 0.5f;
                 if (warp_hi) {
                     const uint32_t bal = __ballot_sync(0xffffffffu, hit);
                     if (bal && lane == 0) atomicAdd(n_touched + lds32(a_id + j * 4), __popc(bal));
