@@ -16,12 +16,10 @@
 
 namespace lvdgs {
 
-// PPT = pixels per thread (rows y, y+4, ...): a warp owns an 8 x (4*PPT) pixel block, a CTA of 8/PPT warps the tile.
-// PPT = 2 -> 4 warps, 8x8 blocks (finer culling); PPT = 4 -> 2 warps, 8x16 blocks (one reduction per 128 pairs).
-#ifndef LVDGS_BB_PPT
-#define LVDGS_BB_PPT 2
-#endif
-constexpr int BB_PPT = LVDGS_BB_PPT;
+// Two pixels per thread (rows y and y + 4): a warp owns an 8x8 pixel block, a CTA of 4 warps the tile (1 and 4 pixels per
+// thread measured slower: one reduction per 32 pairs / coarser culling).  The two pixels' arithmetic runs as packed
+// FP32 pairs (FFMA2 / FMUL2 / FADD2), one issue slot for both.
+constexpr int BB_PPT = 2;
 constexpr int BB_WARPS = 8 / BB_PPT;
 constexpr int BB_THREADS = BB_WARPS * 32;
 constexpr int BB_ROWS = 4 * BB_PPT;            // pixel rows per warp block
@@ -100,26 +98,31 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     const uint2 range = ranges[tile];
     const uint32_t a_id = smem_u32(s_id), a_xy = smem_u32(s_xy), a_q = smem_u32(s_co), a_cd = smem_u32(s_cd);
 
-    // per-pixel state (pixel q of this thread is in row py0 + 4q)
-    float pfy[BB_PPT], T[BB_PPT], Tf[BB_PPT], dp0[BB_PPT], dp1[BB_PPT], dp2[BB_PPT], dpd[BB_PPT], bgd[BB_PPT], S[BB_PPT];
-    uint32_t last[BB_PPT];
-    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
+    // per-pixel state, packed (lo = row py0, hi = row py0 + 4)
+    uint32_t last[2];
+    f32x2 npfy2, T2, nTfbgd2, dp0_2, dp1_2, dp2_2, dpd_2, S2 = bc(0.f);
+    {
+        float pfy[2], Tf[2], dp0[2], dp1[2], dp2[2], dpd[2], bgd[2];
+        const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
 #pragma unroll
-    for (int q = 0; q < BB_PPT; ++q) {
-        const int py = py0 + 4 * q;
-        const bool inside = px < W && py < H;
-        const size_t pix = (size_t)py * W + px;
-        pfy[q] = (float)py;
-        last[q] = inside ? n_contrib[pix] : 0u;
-        Tf[q] = inside ? final_T[pix] : 0.f;
-        T[q] = Tf[q];
-        dp0[q] = inside ? dL_dout_color[pix] : 0.f;
-        dp1[q] = inside ? dL_dout_color[HW + pix] : 0.f;
-        dp2[q] = inside ? dL_dout_color[2 * HW + pix] : 0.f;
-        dpd[q] = (inside && dL_dout_depth) ? dL_dout_depth[pix] : 0.f;
-        bgd[q] = bg0 * dp0[q] + bg1 * dp1[q] + bg2 * dp2[q];
-        if (inside && dL_dout_opacity) bgd[q] -= dL_dout_opacity[pix];   // d(1 - T_final)/dalpha = +T_final/(1-alpha)
-        S[q] = 0.f;
+        for (int q = 0; q < 2; ++q) {
+            const int py = py0 + 4 * q;
+            const bool inside = px < W && py < H;
+            const size_t pix = (size_t)py * W + px;
+            pfy[q] = (float)py;
+            last[q] = inside ? n_contrib[pix] : 0u;
+            Tf[q] = inside ? final_T[pix] : 0.f;
+            dp0[q] = inside ? dL_dout_color[pix] : 0.f;
+            dp1[q] = inside ? dL_dout_color[HW + pix] : 0.f;
+            dp2[q] = inside ? dL_dout_color[2 * HW + pix] : 0.f;
+            dpd[q] = (inside && dL_dout_depth) ? dL_dout_depth[pix] : 0.f;
+            bgd[q] = bg0 * dp0[q] + bg1 * dp1[q] + bg2 * dp2[q];
+            if (inside && dL_dout_opacity) bgd[q] -= dL_dout_opacity[pix];   // d(1 - T_final)/dalpha = +T_final/(1-alpha)
+        }
+        npfy2 = pk(-pfy[0], -pfy[1]);
+        T2 = pk(Tf[0], Tf[1]);
+        nTfbgd2 = pk(-Tf[0] * bgd[0], -Tf[1] * bgd[1]);
+        dp0_2 = pk(dp0[0], dp0[1]); dp1_2 = pk(dp1[0], dp1[1]); dp2_2 = pk(dp2[0], dp2[1]); dpd_2 = pk(dpd[0], dpd[1]);
     }
     // warp-wide and tile-wide max of n_contrib: nothing at or beyond it contributes
     uint32_t wtop = last[0];
@@ -198,55 +201,40 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 const float4 co = lds128(a_q + j * 16);
                 const float4 cd = lds128(a_cd + j * 16);
                 const float dx = xy.x - pfx;
-                // phase 1 (cheap, per pixel): does this pixel blend the Gaussian at all?  The rest of the body is
-                // branch-free: a pixel that does not contributes with alpha = 0 and G = 0, which leaves its T / B
-                // recurrences untouched and adds zeros to the warp's sums -- no divergent regions, and the two pixels'
-                // instruction streams interleave.
-                float dy[BB_PPT], G[BB_PPT], al[BB_PPT];
-                bool valid = false;
-#pragma unroll
-                for (int q = 0; q < BB_PPT; ++q) {
-                    dy[q] = xy.y - pfy[q];
-                    const float p2 = fmaf(co.z * dy[q], dy[q], dx * fmaf(co.x, dx, co.y * dy[q]));
-                    const float g = ex2_approx(p2);
-                    const float a = fminf(0.99f, co.w * g);
-                    const bool ok = k < last[q] && p2 <= 0.f && a >= 1.f / 255.f;
-                    G[q] = ok ? g : 0.f;
-                    al[q] = ok ? a : 0.f;
-                    valid |= ok;
-                }
+                // phase 1 (cheap): does either pixel blend the Gaussian at all?  The rest of the body is branch-free: a
+                // pixel that does not contributes with alpha = 0 and G = 0, which leaves its T / S recurrences untouched
+                // (rcp(1) = 1 exactly) and adds zeros to the warp's sums.
+                const f32x2 dy2 = add2(bc(xy.y), npfy2);
+                const f32x2 p2 = fma2(mul2(bc(co.z), dy2), dy2, mul2(bc(dx), add2(bc(co.x * dx), mul2(bc(co.y), dy2))));
+                const float p2a = lo_of(p2), p2b = hi_of(p2);
+                const float ga = ex2_approx(p2a), gb = ex2_approx(p2b);
+                const float aa = fminf(0.99f, co.w * ga), ab = fminf(0.99f, co.w * gb);
+                const bool oka = k < last[0] && p2a <= 0.f && aa >= 1.f / 255.f;
+                const bool okb = k < last[1] && p2b <= 0.f && ab >= 1.f / 255.f;
+                const bool valid = oka || okb;
                 const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
                 if (!vmask) continue;
+                const f32x2 G2 = pk(oka ? ga : 0.f, okb ? gb : 0.f);
+                const f32x2 al2 = pk(oka ? aa : 0.f, okb ? ab : 0.f);
+                const f32x2 one_m2 = fma2(al2, bc(-1.f), bc(1.f));
+                const f32x2 inv2 = pk(rcp_approx(lo_of(one_m2)), rcp_approx(hi_of(one_m2)));   // 1 - alpha >= 0.01
+                T2 = mul2(T2, inv2);
+                const f32x2 wgt2 = mul2(al2, T2);
+                // the colour / depth blended BEHIND this Gaussian enters only through its dot product with dL/dpixel:
+                // S = <B, dp> obeys the same recurrence as B itself (S <- alpha <c, dp> + (1 - alpha) S)
+                const f32x2 cdp2 = fma2(bc(cd.w), dpd_2, fma2(bc(cd.z), dp2_2, fma2(bc(cd.y), dp1_2, mul2(bc(cd.x), dp0_2))));
+                f32x2 dL2 = mul2(fma2(S2, bc(-1.f), cdp2), T2);
+                dL2 = fma2(inv2, nTfbgd2, dL2);                   // - T_final / (1 - alpha) * <bg, dp>
+                S2 = fma2(al2, cdp2, mul2(one_m2, S2));
+                const f32x2 m2 = mul2(G2, dL2);
+                const f32x2 mdx2 = mul2(m2, bc(dx)), mdy2 = mul2(m2, dy2);
                 float v[16];
-#pragma unroll
-                for (int q = 0; q < BB_PPT; ++q) {
-                    const float alpha = al[q];
-                    const float one_m = 1.f - alpha;
-                    const float inv = rcp_approx(one_m);          // 1 - alpha >= 0.01: no denormal handling needed
-                    T[q] *= inv;
-                    const float wgt = alpha * T[q];
-                    // the colour / depth blended BEHIND this Gaussian enters only through its dot product with dL/dpixel:
-                    // S = <B, dp> obeys the same recurrence as B itself (S <- alpha <c, dp> + (1 - alpha) S)
-                    const float cdp = fmaf(cd.w, dpd[q], fmaf(cd.z, dp2[q], fmaf(cd.y, dp1[q], cd.x * dp0[q])));
-                    float dL_dalpha = (cdp - S[q]) * T[q];
-                    dL_dalpha -= Tf[q] * inv * bgd[q];
-                    S[q] = fmaf(alpha, cdp, one_m * S[q]);
-                    const float m = G[q] * dL_dalpha;
-                    const float mdx = m * dx, mdy = m * dy[q];
-                    if (q == 0) {
-                        v[0] = mdx; v[1] = mdy;
-                        v[2] = mdx * dx; v[3] = mdx * dy[q]; v[4] = mdy * dy[q];
-                        v[5] = m;
-                        v[6] = wgt * dpd[q];
-                        v[8] = wgt * dp0[q]; v[9] = wgt * dp1[q]; v[10] = wgt * dp2[q];
-                    } else {
-                        v[0] += mdx; v[1] += mdy;
-                        v[2] = fmaf(mdx, dx, v[2]); v[3] = fmaf(mdx, dy[q], v[3]); v[4] = fmaf(mdy, dy[q], v[4]);
-                        v[5] += m;
-                        v[6] = fmaf(wgt, dpd[q], v[6]);
-                        v[8] = fmaf(wgt, dp0[q], v[8]); v[9] = fmaf(wgt, dp1[q], v[9]); v[10] = fmaf(wgt, dp2[q], v[10]);
-                    }
-                }
+                v[0] = hsum(mdx2); v[1] = hsum(mdy2);
+                v[2] = dx * v[0];                                 // both pixels share dx
+                v[3] = hsum(mul2(mdx2, dy2)); v[4] = hsum(mul2(mdy2, dy2));
+                v[5] = hsum(m2);
+                v[6] = hsum(mul2(wgt2, dpd_2));
+                v[8] = hsum(mul2(wgt2, dp0_2)); v[9] = hsum(mul2(wgt2, dp1_2)); v[10] = hsum(mul2(wgt2, dp2_2));
                 v[7] = v[11] = v[12] = v[13] = v[14] = v[15] = 0.f;
                 if (vmask) {
                     float *row = acc + (size_t)lds32(a_id + j * 4) * ACC_STRIDE;

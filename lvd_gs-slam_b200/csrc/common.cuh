@@ -83,6 +83,17 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// ---- packed FP32 pairs (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issue slot).  A `bc(x)` operand
+// (both halves equal) costs nothing: ptxas folds it into the instruction's scalar-broadcast operand form.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 bc(float x) { return pk(x, x); }
+__device__ __forceinline__ float lo_of(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi_of(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ float hsum(f32x2 v) { return lo_of(v) + hi_of(v); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 constexpr float LOG2E = 1.4426950408889634f;
 // pixel x coordinate assigned to a finished / out-of-image pixel: every Gaussian then evaluates to alpha = 0, so the
 // hot loop needs no per-pixel "done" test (dx^2 ~ 1e36 stays finite in float)
