@@ -79,10 +79,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     const uint32_t *__restrict__ tile_order, const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
     const float *__restrict__ dL_dout_color, const float *__restrict__ dL_dout_depth,
     const float *__restrict__ dL_dout_opacity, float *__restrict__ acc) {
-    __shared__ uint32_t s_id[BB_BATCH];
-    __shared__ float2 s_xy[BB_BATCH];
-    __shared__ float4 s_co[BB_BATCH];
-    __shared__ float4 s_cd[BB_BATCH];
+    __shared__ BlendRec s_rec[BB_BATCH];
     __shared__ uint32_t s_mask[BB_BATCH / 32][BB_WARPS];     // [group of 32 staged entries][pixel block]
     __shared__ uint32_t s_top[BB_WARPS];
 
@@ -96,7 +93,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     const float tx0 = (float)(tile_x * TILE), ty0 = (float)(tile_y * TILE);
     const size_t HW = (size_t)H * W;
     const uint2 range = ranges[tile];
-    const uint32_t a_id = smem_u32(s_id), a_xy = smem_u32(s_xy), a_q = smem_u32(s_co), a_cd = smem_u32(s_cd);
+    const uint32_t a_rec = smem_u32(s_rec);
 
     // per-pixel state, packed (lo = row py0, hi = row py0 + 4)
     uint32_t last[2];
@@ -152,11 +149,11 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
             if (e < nb) {
                 const uint32_t id = __ldg(point_list + range.x + (uint32_t)(remaining - 1 - e));
                 const float4 m = __ldg(means2D + id);
-                s_id[e] = id;
-                s_xy[e] = make_float2(m.x, m.y);
                 const float4 co = __ldg(conic_opacity + id);
-                s_co[e] = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);   // as forward
-                s_cd[e] = __ldg(rgbd + id);
+                s_rec[e].xy = make_float2(m.x, m.y);
+                s_rec[e].id = id;
+                s_rec[e].co = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);   // as forward
+                s_rec[e].cd = __ldg(rgbd + id);
                 const float rx = m.x - tx0, ry = m.y - ty0;
                 uint32_t xb = 0, yb = 0;
                 if (!(rx + m.z < 0.f) && !(rx - m.z > 7.f)) xb |= 1u;
@@ -197,9 +194,10 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 mask &= mask - 1;
                 const int j = wp * 32 + b;
                 const uint32_t k = (uint32_t)(remaining - 1 - j);    // contributor index (0-based) of this entry
-                const float2 xy = lds64(a_xy + j * 8);
-                const float4 co = lds128(a_q + j * 16);
-                const float4 cd = lds128(a_cd + j * 16);
+                const uint32_t a_j = a_rec + (uint32_t)j * (uint32_t)sizeof(BlendRec);
+                const float2 xy = lds64(a_j);
+                const float4 co = lds128(a_j + 16);
+                const float4 cd = lds128(a_j + 32);
                 const float dx = xy.x - pfx;
                 // phase 1 (cheap): does either pixel blend the Gaussian at all?  The rest of the body is branch-free: a
                 // pixel that does not contributes with alpha = 0 and G = 0, which leaves its T / S recurrences untouched
@@ -237,7 +235,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 v[8] = hsum(mul2(wgt2, dp0_2)); v[9] = hsum(mul2(wgt2, dp1_2)); v[10] = hsum(mul2(wgt2, dp2_2));
                 v[7] = v[11] = v[12] = v[13] = v[14] = v[15] = 0.f;
                 if (vmask) {
-                    float *row = acc + (size_t)lds32(a_id + j * 4) * ACC_STRIDE;
+                    float *row = acc + (size_t)lds32(a_j + 8) * ACC_STRIDE;
                     if (__popc(vmask) <= BB_DIRECT_MAX) {
                         // a Gaussian's edge often reaches only one or two threads of the block: their partial sums go
                         // straight to the accumulator row (10 REDs) instead of through the 60-instruction reduction

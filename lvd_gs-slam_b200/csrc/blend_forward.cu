@@ -34,10 +34,7 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
                                                                    const float *__restrict__ bg, float *__restrict__ out_color, float *__restrict__ out_depth,
                                                                    float *__restrict__ out_opacity, float *__restrict__ final_T,
                                                                    uint32_t *__restrict__ n_contrib, int32_t *__restrict__ n_touched) {
-    __shared__ uint32_t s_id[BF_BATCH];
-    __shared__ float2 s_xy[BF_BATCH];
-    __shared__ float4 s_co[BF_BATCH];
-    __shared__ float4 s_cd[BF_BATCH];
+    __shared__ BlendRec s_rec[BF_BATCH];
     __shared__ uint32_t s_mask[BF_BATCH / 32][BF_WARPS];     // [group of 32 staged entries][pixel block]
 
     const int tile = tile_order ? (int)__ldg(tile_order + blockIdx.x) : (int)blockIdx.x;   // heaviest tiles first
@@ -49,7 +46,7 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
     const bool inside = px < W && py < H;
     float pfx = inside ? (float)px : PIX_PARKED;                   // parked pixels see alpha = 0 for every Gaussian
     const float pfy = (float)py;
-    const uint32_t a_id = smem_u32(s_id), a_xy = smem_u32(s_xy), a_q = smem_u32(s_co), a_cd = smem_u32(s_cd);
+    const uint32_t a_rec = smem_u32(s_rec);
     const float tx0 = (float)(tile_x * TILE), ty0 = (float)(tile_y * TILE);   // tile's first pixel centre
 
     // a speculative launch whose capacity hint was too small has no valid sorted list (the sort retires, see
@@ -57,14 +54,14 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
     if (n_dev && __ldg(n_dev) > capacity) return;
     const uint2 range = ranges[tile];
     int todo = (int)(range.y - range.x);
-    bool done = !inside;
+    // a pixel is done (terminated / outside the image) iff it is parked: pfx == PIX_PARKED
     float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
     uint32_t last_contributor = 0;
     uint32_t batch_first = 0;                                      // list position of the batch's first entry
-    bool warp_hi = true;     // some pixel of this warp may still satisfy T(1-alpha) > 0.5
+    int warp_hi = 1;         // some pixel of this warp may still satisfy T(1-alpha) > 0.5
 
     for (uint32_t base = range.x; todo > 0; base += BF_BATCH, todo -= BF_BATCH, batch_first += BF_BATCH) {
-        if (__syncthreads_count(done) == BF_THREADS) break;
+        if (__syncthreads_count(pfx == PIX_PARKED) == BF_THREADS) break;
 #pragma unroll
         for (int u = 0; u < BF_SPT; ++u) {
             const int e = u * BF_THREADS + (int)threadIdx.x;       // entry of the batch this thread stages
@@ -72,12 +69,12 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
             if (e < todo) {
                 const uint32_t id = __ldg(point_list + base + e);
                 const float4 m = __ldg(means2D + id);
-                s_id[e] = id;
-                s_xy[e] = make_float2(m.x, m.y);
                 const float4 co = __ldg(conic_opacity + id);
+                s_rec[e].xy = make_float2(m.x, m.y);
+                s_rec[e].id = id;
                 // exponent in base 2 with the -1/2 folded in: p2 = A' dx^2 + B' dx dy + C' dy^2, alpha = o 2^p2
-                s_co[e] = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);
-                s_cd[e] = __ldg(rgbd + id);
+                s_rec[e].co = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);
+                s_rec[e].cd = __ldg(rgbd + id);
                 const float rx = m.x - tx0, ry = m.y - ty0;
                 uint32_t xb = 0, yb = 0;
                 // block column bx spans pixel centres [8bx, 8bx+7]; keep it unless the box [rx-hx, rx+hx] misses it
@@ -99,17 +96,18 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
         __syncthreads();
         for (int wp = 0; wp < BF_BATCH / 32; ++wp) {
             uint32_t m = s_mask[wp][warp];
-            if (__all_sync(0xffffffffu, done)) break;
-            if (warp_hi) warp_hi = __any_sync(0xffffffffu, !done && T > 0.5f);
+            if (__all_sync(0xffffffffu, pfx == PIX_PARKED)) break;
+            if (warp_hi) warp_hi = __any_sync(0xffffffffu, pfx != PIX_PARKED && T > 0.5f);
             while (m) {
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
                 const int j = wp * 32 + b;
                 // branch-free body: a pixel that skips the Gaussian (alpha < 1/255, power > 0) or terminates on it
                 // blends with weight 0 and keeps its state; a terminated pixel is parked and sees alpha = 0 from then on
-                const float2 xy = lds64(a_xy + j * 8);
-                const float4 q = lds128(a_q + j * 16);
-                const float4 cd = lds128(a_cd + j * 16);
+                const uint32_t a_j = a_rec + (uint32_t)j * (uint32_t)sizeof(BlendRec);
+                const float2 xy = lds64(a_j);
+                const float4 q = lds128(a_j + 16);
+                const float4 cd = lds128(a_j + 32);
                 const float dx = xy.x - pfx, dy = xy.y - pfy;
                 const float p2 = fmaf(q.z * dy, dy, dx * fmaf(q.x, dx, q.y * dy));
                 const float alpha = fminf(0.99f, q.w * ex2_approx(p2));
@@ -122,11 +120,10 @@ __global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H,
                 T = contrib ? test_T : T;
                 last_contributor = contrib ? batch_first + (uint32_t)j + 1u : last_contributor;
                 pfx = term ? PIX_PARKED : pfx;
-                done |= term;
                 const bool hit = contrib && test_T > 0.5f;
                 if (warp_hi) {
                     const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                    if (bal && lane == 0) atomicAdd(n_touched + lds32(a_id + j * 4), __popc(bal));
+                    if (bal && lane == 0) atomicAdd(n_touched + lds32(a_j + 8), __popc(bal));
                 }
             }
         }

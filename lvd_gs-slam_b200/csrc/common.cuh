@@ -88,13 +88,23 @@ __device__ __forceinline__ float rcp_approx(float x) {
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ f32x2 bc(float x) { return pk(x, x); }
-__device__ __forceinline__ float lo_of(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-__device__ __forceinline__ float hi_of(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ float lo_of(f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi_of(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
 __device__ __forceinline__ float hsum(f32x2 v) { return lo_of(v) + hi_of(v); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 constexpr float LOG2E = 1.4426950408889634f;
+// One staged instance of a blend batch: the three loads of the hot loops share ONE address computation (immediate
+// offsets 0 / 16 / 32), and 48-byte records keep the staging stores (one record per lane) bank-conflict free.
+struct __align__(16) BlendRec {
+    float2 xy;          // pixel-space mean
+    uint32_t id;        // Gaussian index
+    uint32_t pad;
+    float4 co;          // conic prescaled to base 2 (-0.5 log2e A, -log2e B, -0.5 log2e C) + opacity
+    float4 cd;          // rgb + depth
+};
+static_assert(sizeof(BlendRec) == 48, "BlendRec layout");
 // pixel x coordinate assigned to a finished / out-of-image pixel: every Gaussian then evaluates to alpha = 0, so the
 // hot loop needs no per-pixel "done" test (dx^2 ~ 1e36 stays finite in float)
 constexpr float PIX_PARKED = 1.0e18f;
