@@ -325,8 +325,10 @@ def main():
         alg = {  # algorithmic work per view (SURVEY.md section 8d / DESIGN.md section 6)
             "preprocess_forward": ("hbm", 20.0 * (P - vis) + 131.0 * vis),
             "binning_count": ("hbm", 4.0 * P + 12.0 * vis),
-            "emit_keys": ("hbm", 12.0 * Rs + 20.0 * P),
-            "sort_onesweep": ("hbm", passes * 24.0 * Rs),
+            "emit_keys": ("hbm", 8.0 * Rs + 20.0 * P),            # one 8-byte (depth | Gaussian) word per instance
+            "tile_sort": ("hbm", 20.0 * Rs),                      # 8 B read + 12 B (key, value) written per instance;
+                                                                  # the network itself runs in shared memory (ALU-bound)
+            "sort_onesweep": ("hbm", passes * 24.0 * Rs),         # only with LVDGS_FLAG_GLOBAL_SORT
             "blend_forward": ("fp32", 28.0 * pairs),
             "blend_backward": ("fp32", 70.0 * pairs),
             "preprocess_backward": ("hbm", 190.0 * vis + 52.0 * (P - vis)),
