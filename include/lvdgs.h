@@ -58,7 +58,8 @@ typedef struct lvdgs_raster_params {
 } lvdgs_raster_params;
 
 /* Must return a device pointer to at least `bytes` bytes, 256-byte aligned, valid until the matching backward
- * has run.  Called once per buffer per forward (twice for LVDGS_BUF_BINNING when a capacity hint was too small),
+ * has run.  Called once per buffer per forward (twice for LVDGS_BUF_BINNING when a speculative launch has to be
+ * repeated: the capacity hint was too small, or a tile list was longer than the previous frame suggested),
  * from the calling thread; the latest pointer per buffer is the live one. */
 typedef void *(*lvdgs_resize_fn)(void *user, int32_t which, size_t bytes);
 

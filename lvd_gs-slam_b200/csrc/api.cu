@@ -175,11 +175,14 @@ int lvdgs_get_img_layout(int32_t W, int32_t H, lvdgs_img_layout *out) { if (!out
 // pinned slot + event for the asynchronous read-back of the instance count (one per host thread, created once)
 static thread_local uint32_t *t_pinned_R = nullptr;
 static thread_local cudaEvent_t t_R_event = nullptr;
+// longest tile list of this thread's previous forward (read back with R): decides whether the next forward launches
+// tile_sort's long-list class speculatively (a wrong guess costs time, never correctness)
+static thread_local uint32_t t_longest_list = 0xffffffffu;
 
 // everything after the instance count is known on the DEVICE: keys, sort, ranges, blend.  `capacity` sizes the
 // launches and the binning arena; the kernels clamp to min(R, capacity) read from device memory.
 static int launch_bin_and_blend(const lvdgs_raster_params &p, const GeomPtrs &g, const BinPtrs &b, const ImgPtrs &im,
-                                int64_t capacity, bool rerun, const float *background, float *out_color, float *out_depth,
+                                int64_t capacity, bool rerun, bool long_lists, const float *background, float *out_color, float *out_depth,
                                 float *out_opacity, int32_t *n_touched, cudaStream_t s) {
     const int W = p.width, H = p.height;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
@@ -196,7 +199,7 @@ static int launch_bin_and_blend(const lvdgs_raster_params &p, const GeomPtrs &g,
         // the cursors were zeroed together with the tile grid; a re-run after a failed speculative launch resets them
         if (rerun) LVDGS_CHECK(cudaMemsetAsync(im.tile_cursor, 0, sizeof(uint32_t) * CURSOR_STRIDE * (size_t)gx * gy, s));
         if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], nullptr, im.tile_cursor, im.ranges, s)) return 1;
-        if (launch_tile_sort(gx * gy, capacity, R_dev, im.ranges, im.tile_order, b.keys[0], b.keys[1], b.vals[1], s)) return 1;
+        if (launch_tile_sort(gx * gy, capacity, R_dev, im.ranges, im.tile_order, b.keys[0], b.keys[1], b.vals[1], long_lists, s)) return 1;
         sel = 1;
     }
     LVDGS_CHECK(cudaMemcpyAsync(b.sorted_sel, &sel, sizeof(int32_t), cudaMemcpyHostToDevice, s));
@@ -259,32 +262,36 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
                                   projmatrix, shs, campos, radii, g, im, s)) return 1;
     // block offsets, R, tile ranges and all digit histograms of the sort, from the block sums and per-tile counts
     if (launch_binning_prep(p.P, W, H, (p.flags & LVDGS_FLAG_GLOBAL_SORT) ? 32 + tile_bits((uint32_t)(gx * gy)) : 0, g, im, s)) return 1;
-    LVDGS_CHECK(cudaMemcpyAsync(t_pinned_R, g.num_instances, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    LVDGS_CHECK(cudaMemcpyAsync(t_pinned_R, g.num_instances, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     LVDGS_CHECK(cudaEventRecord(t_R_event, s));
 
     // Speculative launch: with a capacity hint the whole rest of the forward is queued BEFORE the host waits for R,
     // so the device never idles across the read-back.  If R turns out larger than the hint, the tail is re-run with
     // an exactly sized arena (the speculative results are simply overwritten).
     int64_t capacity = capacity_hint > 0 ? capacity_hint : 0;
-    bool launched = false;
+    bool launched = false, launched_long = false;
     if (capacity > 0) {
         lvdgs_binning_layout bl; binning_layout(capacity, bl);
         void *bin_base = resize(resize_user, LVDGS_BUF_BINNING, bl.total);
         if (!bin_base) { set_error("resize callback returned NULL (binning)"); return 1; }
-        if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, false, background, out_color, out_depth,
+        // guess from the previous forward, with hysteresis
+        launched_long = (p.flags & LVDGS_FLAG_GLOBAL_SORT) || t_longest_list >= (uint32_t)(tile_sort_long_threshold() * 3 / 4);
+        if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, false, launched_long, background, out_color, out_depth,
                                  out_opacity, n_touched, s)) return 1;
         launched = true;
     }
     LVDGS_CHECK(cudaEventSynchronize(t_R_event));
     if (profile_mark("(host: R read-back)", s)) return 1;
-    const int64_t R = *t_pinned_R;
+    const int64_t R = t_pinned_R[0];
+    t_longest_list = t_pinned_R[1];
     *num_rendered = R;
-    if (!launched || R > capacity) {
-        capacity = R > 0 ? R : 1;
+    const bool need_long = t_longest_list >= (uint32_t)tile_sort_long_threshold();      // exact: just read back
+    if (!launched || R > capacity || (need_long && !launched_long)) {
+        if (!launched || R > capacity) capacity = R > 0 ? R : 1;
         lvdgs_binning_layout bl; binning_layout(capacity, bl);
         void *bin_base = resize(resize_user, LVDGS_BUF_BINNING, bl.total);
         if (!bin_base) { set_error("resize callback returned NULL (binning)"); return 1; }
-        if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, launched, background, out_color, out_depth,
+        if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, launched, need_long, background, out_color, out_depth,
                                  out_opacity, n_touched, s)) return 1;
     }
     *binning_capacity = capacity;

@@ -183,7 +183,8 @@ int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, int64_t capacity, u
                      uint32_t *tile_cursor, const uint2 *ranges, cudaStream_t s);
 // tile-segment sort (tile_sort.cu): seg holds each tile's (depth bits << 32 | Gaussian) words in ranges[tile], unordered
 int launch_tile_sort(int tiles, int64_t capacity, const uint32_t *n_dev, const uint2 *ranges, const uint32_t *tile_order,
-                     uint64_t *seg, uint64_t *keys_out, uint32_t *vals_out, cudaStream_t s);
+                     uint64_t *seg, uint64_t *keys_out, uint32_t *vals_out, bool long_lists, cudaStream_t s);
+int tile_sort_long_threshold();
 
 size_t sort_workspace_bytes(int64_t n);
 // pre_hist: optional [passes][256] exclusive-scanned digit histograms (device); when given, the histogram pass over the

@@ -392,8 +392,10 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
     __shared__ uint32_t s_ws[32];
     __shared__ uint32_t s_carry;
     __shared__ uint32_t s_bucket[WORK_BUCKETS];
+    __shared__ uint32_t s_longest;
     const int gw = gx + 1, cells = gw * (gy + 1), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < WORK_BUCKETS) s_bucket[tid] = 0;
+    if (tid == 0) s_longest = 0;
     const bool in_smem = cells <= PREP_GRID_SMEM;
     int32_t *grid = in_smem ? s_grid : grid_g;
     for (int k = tid; k < SORT_MAX_PASSES * SORT_BINS; k += PREP_THREADS) s_h[k] = k < 4 * SORT_BINS ? hist[k] : 0u;
@@ -434,6 +436,7 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
         if (t < tiles) {
             ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
             atomicAdd(&s_bucket[work_bucket(c)], 1u);
+            if (c >= 1536u) atomicMax(&s_longest, c);       // only long lists matter to the reader (tile_sort's class choice)
             if (c) {
                 for (int q = 4; q < passes; ++q) {
                     const int shift = 8 * (q - 4), nb = min(8, end_bit - 8 * q);
@@ -450,6 +453,7 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
     if (tid == 0) {
         uint32_t run = 0;
         for (int b = 0; b < WORK_BUCKETS; ++b) { const uint32_t n = s_bucket[b]; s_bucket[b] = run; run += n; }
+        R_out[1] = s_longest;            // longest tile list (0 if below 1024), read back together with R
     }
     __syncthreads();
     for (int t = tid; t < tiles; t += PREP_THREADS) {

@@ -235,16 +235,24 @@ __device__ __forceinline__ void tile_sort_one(int tile, uint2 range, uint64_t *s
     }
 }
 
+// Lists of n_hi or more instances belong to the long-list launch.  passthrough: there is no such launch (the host
+// expected no long list) -- the list is then handed on UNSORTED, so that the speculatively queued blend reads valid
+// Gaussian indices; the host sees the longest list next to R and re-runs the tail with the long-list class.
 template <int THREADS, int CAP>
-__global__ void __launch_bounds__(THREADS) tile_sort_short_kernel(uint32_t n_hi, uint32_t capacity, const uint32_t *__restrict__ n_dev,
+__global__ void __launch_bounds__(THREADS) tile_sort_short_kernel(uint32_t n_hi, int passthrough, uint32_t capacity, const uint32_t *__restrict__ n_dev,
                                                                   const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_order,
                                                                   uint64_t *seg, uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
     __shared__ uint64_t s_words[ts_phys(CAP)];
     const int tile = (int)__ldg(tile_order + blockIdx.x);
     const uint2 range = ranges[tile];
     const uint32_t n = range.y - range.x;
-    if (n == 0 || n >= n_hi) return;
+    if (n == 0) return;
     if (n_dev && __ldg(n_dev) > capacity) return;       // speculative launch with too small an arena: the host re-runs
+    if (n >= n_hi) {
+        if (passthrough)
+            for (uint32_t i = threadIdx.x; i < n; i += THREADS) vals_out[range.x + i] = (uint32_t)seg[range.x + i];
+        return;
+    }
     tile_sort_one<THREADS, CAP, false>(tile, range, seg, keys_out, vals_out, s_words);
 }
 
@@ -269,8 +277,11 @@ __global__ void __launch_bounds__(THREADS) tile_sort_long_kernel(uint32_t n_lo, 
 constexpr int TS_SHORT_THREADS = LVDGS_TS_SHORT_THREADS, TS_SHORT_CAP = 2048;    // lists of 1 .. 2047 instances
 constexpr int TS_LONG_THREADS = 1024, TS_LONG_CAP = 16384;
 
+// long_lists: launch the long-list class (lists of TS_SHORT_CAP or more).  Without it such lists are NOT sorted: the
+// caller must check the longest list (binning_prep leaves it next to R) and re-run with long_lists = true.
+int tile_sort_long_threshold() { return TS_SHORT_CAP; }
 int launch_tile_sort(int tiles, int64_t capacity, const uint32_t *n_dev, const uint2 *ranges, const uint32_t *tile_order,
-                     uint64_t *seg, uint64_t *keys_out, uint32_t *vals_out, cudaStream_t s) {
+                     uint64_t *seg, uint64_t *keys_out, uint32_t *vals_out, bool long_lists, cudaStream_t s) {
     if (tiles <= 0) return 0;
     const uint32_t cap = (uint32_t)min(capacity, (int64_t)0xffffffffll);
     static int sm_count = 0;
@@ -281,11 +292,13 @@ int launch_tile_sort(int tiles, int64_t capacity, const uint32_t *n_dev, const u
         LVDGS_CHECK(cudaFuncSetAttribute(long_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts_smem_bytes(TS_LONG_CAP)));
         LVDGS_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
+    if (long_lists) {
+        LVDGS_PRE(s);
+        long_k<<<min(tiles, sm_count), TS_LONG_THREADS, ts_smem_bytes(TS_LONG_CAP), s>>>((uint32_t)TS_SHORT_CAP, tiles, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out);
+        LVDGS_LAUNCHED(s, "tile_sort_long");
+    }
     LVDGS_PRE(s);
-    long_k<<<min(tiles, sm_count), TS_LONG_THREADS, ts_smem_bytes(TS_LONG_CAP), s>>>((uint32_t)TS_SHORT_CAP, tiles, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out);
-    LVDGS_LAUNCHED(s, "tile_sort_long");
-    LVDGS_PRE(s);
-    tile_sort_short_kernel<TS_SHORT_THREADS, TS_SHORT_CAP><<<tiles, TS_SHORT_THREADS, 0, s>>>((uint32_t)TS_SHORT_CAP, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out);
+    tile_sort_short_kernel<TS_SHORT_THREADS, TS_SHORT_CAP><<<tiles, TS_SHORT_THREADS, 0, s>>>((uint32_t)TS_SHORT_CAP, long_lists ? 0 : 1, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out);
     LVDGS_LAUNCHED(s, "tile_sort");
     return 0;
 }

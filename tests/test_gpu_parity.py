@@ -355,3 +355,25 @@ def test_global_sort_flag_matches_default_with_gradients():
         np.testing.assert_array_equal(res[0][0][k], res[16][0][k])
     assert rel_err(res[0][2]["means3D"], res[16][2]["means3D"]) < 1e-4
     assert rel_err(res[0][2]["theta"], res[16][2]["theta"]) < 1e-4
+
+
+def test_tile_sort_unexpected_long_list_fallback():
+    """Speculative launches guess from the previous forward whether the long-list sort class is needed.  A frame whose
+    lists are unexpectedly long must still be sorted exactly (short-list kernel's chunked path), and so must the next
+    one (long-list kernel, now expected)."""
+    import diff_gaussian_rasterization as dgr
+    cam = synth.make_camera("vga")
+    bg = np.zeros(3, np.float32)
+    plain = synth.make_scene(20_000, cam, seed=2)
+    crowded = _crowded_scene(cam, 30_000, 5_000)
+    fwd, _ = run_oracle(crowded, cam, bg)
+    dev = torch.cuda.current_device()
+    dgr._capacity_hint.clear()
+    run_cuda(plain, cam, bg, debug=False)                       # longest list of the previous frame: short
+    for _ in range(2):                                          # 1st: guess "no long lists" is wrong; 2nd: guess is right
+        dgr._capacity_hint[dev] = 4_000_000                     # generous hint -> speculative launch, no re-run
+        out, internals, _ = run_cuda(crowded, cam, bg, debug=False)
+        np.testing.assert_array_equal(internals["keys_sorted"], fwd["keys_sorted"])
+        np.testing.assert_array_equal(internals["point_list"], fwd["point_list"])
+        ok = fwd["margin"] > 1e-5
+        assert np.abs(out["color"][:, ok] - fwd["color"][:, ok]).max() < 1e-5
