@@ -20,6 +20,10 @@
 // global memory (L2) and the narrow ones chunk by chunk in shared memory.
 #include "common.cuh"
 
+#ifndef LVDGS_TS_Q32
+#define LVDGS_TS_Q32 1        // short lists: 32-bit stand-ins + fix-up (0: the 64-bit network directly)
+#endif
+
 namespace lvdgs {
 
 __device__ __forceinline__ uint64_t lds_u64(uint32_t a) {
@@ -158,6 +162,209 @@ __device__ __forceinline__ void ts_sort_smem(uint32_t a_s, int n, int tid) {
     ts_levels_from<THREADS, 16, CAP>(a_s, n, tid);
 }
 
+// ---- 32-bit network for the short lists -------------------------------------------------------------------------
+// A 64-bit comparator is 6 ALU instructions; a 32-bit one is two (VIMNMX min / max).  For a list of n < 2048 instances
+// the sort therefore runs on 32-bit stand-ins  q << 11 | slot,  q = (depth bits - list minimum) >> shift  quantised to 21
+// bits (monotone, so the order by (q, slot) is the true order except INSIDE runs of equal q) and slot = the instance's
+// position in the unsorted segment (unique).  A fix-up pass then orders every run of equal q by the full 64-bit words
+// (runs are a handful of instances unless many depths coincide to within 2^-21 of the list's depth range; runs beyond
+// TS_MAXRUN send the whole list through the 64-bit network instead -- still exact, just slower).
+// Two stand-ins share one 64-bit shared-memory word (even element = low half), which keeps the word-level index maps,
+// the conflict-free layout and the immediate-offset addressing of the 64-bit network: a stage with stride j >= 2 is the
+// word-level stage j/2 applied to both halves, the stride-1 stage compares the halves of a word, and a flip compares a
+// word's halves with the opposite halves of its mirror word.  A thread holds 8 words = 16 elements.
+__device__ __forceinline__ void ce32(uint32_t &a, uint32_t &b) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo; b = hi;
+}
+struct PairWords {
+    uint32_t e[8], o[8];      // even / odd element of 8 words
+    __device__ __forceinline__ void load(int m, uint32_t addr) { const uint64_t w = lds_u64(addr); e[m] = (uint32_t)w; o[m] = (uint32_t)(w >> 32); }
+    __device__ __forceinline__ void store(int m, uint32_t addr) const { sts_u64(addr, (uint64_t)o[m] << 32 | e[m]); }
+    __device__ __forceinline__ void cew(int i, int j) { ce32(e[i], e[j]); ce32(o[i], o[j]); }         // word i below word j
+    __device__ __forceinline__ void inword(int i) { ce32(e[i], o[i]); }
+    __device__ __forceinline__ void flip(int a, int b) { ce32(e[a], o[b]); ce32(o[a], e[b]); }         // word a below its mirror b
+    __device__ __forceinline__ void inword_all() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) inword(i);
+    }
+};
+
+// element levels 2, 4, 8, 16 on 8 consecutive words
+template <int THREADS>
+__device__ __forceinline__ void tp_levels_2_to_16(uint32_t a_s, int nw, int tid) {
+    __syncthreads();
+    for (int g = tid; g * 8 < nw; g += THREADS) {
+        const uint32_t a0 = ts_addr(a_s, 8 * g);
+        PairWords w;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) w.load(m, a0 + 8 * m);
+        w.inword_all();
+        w.flip(0, 1); w.flip(2, 3); w.flip(4, 5); w.flip(6, 7);
+        w.inword_all();
+        w.flip(0, 3); w.flip(1, 2); w.flip(4, 7); w.flip(5, 6);
+        w.cew(0, 1); w.cew(2, 3); w.cew(4, 5); w.cew(6, 7);
+        w.inword_all();
+        w.flip(0, 7); w.flip(1, 6); w.flip(2, 5); w.flip(3, 4);
+        w.cew(0, 2); w.cew(1, 3); w.cew(4, 6); w.cew(5, 7);
+        w.cew(0, 1); w.cew(2, 3); w.cew(4, 5); w.cew(6, 7);
+        w.inword_all();
+#pragma unroll
+        for (int m = 0; m < 8; ++m) w.store(m, a0 + 8 * m);
+    }
+}
+
+// word-level flip of level KW (element level 2 KW) and the word stages KW/4, KW/8
+template <int THREADS, int KW>
+__device__ __forceinline__ void tp_flip_group(uint32_t a_s, int nw, int tid) {
+    constexpr int S = KW / 8;
+    const int G = ((nw + KW - 1) / KW) * S;
+    __syncthreads();
+    for (int g = tid; g < G; g += THREADS) {
+        const int r = g & (S - 1), base = (g / S) * KW;
+        const int il = base + r, iu = base + KW - 1 - r;
+        if (il >= nw) continue;
+        const uint32_t al = ts_addr(a_s, il), au = ts_addr(a_s, iu);
+        PairWords w;          // 0..3: lower words, ascending; 4..7: mirror words, DESCENDING
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { w.load(m, al + 8 * ts_phys(S * m)); w.load(4 + m, au - 8 * ts_phys(S * m)); }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) w.flip(m, 4 + m);
+        w.cew(0, 2); w.cew(1, 3); w.cew(6, 4); w.cew(7, 5);
+        w.cew(0, 1); w.cew(2, 3); w.cew(5, 4); w.cew(7, 6);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { w.store(m, al + 8 * ts_phys(S * m)); w.store(4 + m, au - 8 * ts_phys(S * m)); }
+    }
+}
+
+// the last CNT of the word stages 4S, 2S, S; S == 1 also ends the level with the in-word (element stride 1) stage
+template <int THREADS, int S, int CNT>
+__device__ __forceinline__ void tp_j_group(uint32_t a_s, int nw, int tid) {
+    const int G = ((nw + 8 * S - 1) / (8 * S)) * S;
+    __syncthreads();
+    for (int g = tid; g < G; g += THREADS) {
+        const int i0 = (g / S) * (8 * S) + (g & (S - 1));
+        if (i0 >= nw) continue;
+        const uint32_t a0 = ts_addr(a_s, i0);
+        PairWords w;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) w.load(m, a0 + 8 * ts_phys(S * m));
+        if (CNT >= 3) { w.cew(0, 4); w.cew(1, 5); w.cew(2, 6); w.cew(3, 7); }
+        if (CNT >= 2) { w.cew(0, 2); w.cew(1, 3); w.cew(4, 6); w.cew(5, 7); }
+        w.cew(0, 1); w.cew(2, 3); w.cew(4, 5); w.cew(6, 7);
+        if (S == 1) w.inword_all();
+#pragma unroll
+        for (int m = 0; m < 8; ++m) w.store(m, a0 + 8 * ts_phys(S * m));
+    }
+}
+
+template <int THREADS, int J>
+__device__ __forceinline__ void tp_j_stages_from(uint32_t a_s, int nw, int tid) {
+    if constexpr (J >= 1) {
+        constexpr int CNT = ts_ilog2(J) + 1 >= 3 ? 3 : ts_ilog2(J) + 1;
+        constexpr int S = J >> (CNT - 1);
+        if (S < nw || S == 1) tp_j_group<THREADS, S, CNT>(a_s, nw, tid);
+        tp_j_stages_from<THREADS, S / 2>(a_s, nw, tid);
+    }
+}
+
+template <int THREADS, int KW, int CAPW>
+__device__ __forceinline__ void tp_levels_from(uint32_t a_s, int nw, int tid) {
+    if constexpr (KW <= CAPW) {
+        if (KW / 2 < nw) {
+            tp_flip_group<THREADS, KW>(a_s, nw, tid);
+            tp_j_stages_from<THREADS, KW / 16>(a_s, nw, tid);
+            tp_levels_from<THREADS, KW * 2, CAPW>(a_s, nw, tid);
+        }
+    }
+}
+
+constexpr int TS_MAXRUN = 16;
+constexpr int TS_SLOT_BITS = 11, TS_Q_BITS = 32 - TS_SLOT_BITS;
+
+// Sorts the n < 2^TS_SLOT_BITS words of one tile.  s_words: ts_phys(CAP) words (the unsorted 64-bit words, by slot),
+// s_pairs: ts_phys(CAP / 2) pair words, s_red: 2 * THREADS / 32 + 1 words of scratch.
+template <int THREADS, int CAP>
+__device__ __forceinline__ void tile_sort_one_q32(int tile, uint2 range, const uint64_t *seg, uint64_t *__restrict__ keys_out,
+                                                  uint32_t *__restrict__ vals_out, uint64_t *s_words, uint64_t *s_pairs,
+                                                  uint32_t *s_red) {
+    static_assert(CAP <= (1 << TS_SLOT_BITS), "slot bits");
+    const int n = (int)(range.y - range.x), nw = (n + 1) >> 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t a_w = smem_u32(s_words), a_p = smem_u32(s_pairs);
+    const uint64_t *g = seg + range.x;
+    const uint64_t tile_hi = (uint64_t)(uint32_t)tile << 32;
+    // (1) stage the words, find the range of their depth bits
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
+    for (int i = tid; i < n; i += THREADS) {
+        const uint64_t w = g[i];
+        sts_u64(ts_addr(a_w, i), w);
+        const uint32_t d = (uint32_t)(w >> 32);
+        dmin = min(dmin, d); dmax = max(dmax, d);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, d));
+        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, d));
+    }
+    if (lane == 0) { s_red[2 * warp] = dmin; s_red[2 * warp + 1] = dmax; }
+    if (tid == 0) s_red[2 * (THREADS / 32)] = 0;          // "a run was too long" flag
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < THREADS / 32; ++k) { dmin = min(dmin, s_red[2 * k]); dmax = max(dmax, s_red[2 * k + 1]); }
+    const int span_bits = 32 - __clz(dmax - dmin);         // 0 when all depths coincide
+    const int shift = max(0, span_bits - TS_Q_BITS);
+    // (2) the 32-bit stand-ins, two per pair word; elements beyond n and words beyond nw are all-ones
+    {
+        const int npw = nw <= 8 ? 8 : 1 << (32 - __clz(nw - 1));
+        for (int w = tid; w < npw; w += THREADS) {
+            uint32_t k0 = 0xffffffffu, k1 = 0xffffffffu;
+            if (2 * w < n) k0 = (((uint32_t)(lds_u64(ts_addr(a_w, 2 * w)) >> 32) - dmin) >> shift) << TS_SLOT_BITS | (uint32_t)(2 * w);
+            if (2 * w + 1 < n) k1 = (((uint32_t)(lds_u64(ts_addr(a_w, 2 * w + 1)) >> 32) - dmin) >> shift) << TS_SLOT_BITS | (uint32_t)(2 * w + 1);
+            sts_u64(ts_addr(a_p, w), (uint64_t)k1 << 32 | k0);
+        }
+    }
+    // (3) sort them
+    tp_levels_2_to_16<THREADS>(a_p, nw, tid);
+    tp_levels_from<THREADS, 16, CAP / 2>(a_p, nw, tid);
+    __syncthreads();
+    // (4) fix-up: a stand-in alone in its run is in its final place; inside a run the full words decide
+    auto key_at = [&](int p) -> uint32_t {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ts_addr(a_p, p >> 1) + 4u * (uint32_t)(p & 1)) : "memory");
+        return v;
+    };
+    bool too_long = false;
+    for (int p = tid; p < n; p += THREADS) {
+        const uint32_t key = key_at(p), q = key >> TS_SLOT_BITS;
+        const uint64_t my = lds_u64(ts_addr(a_w, (int)(key & ((1u << TS_SLOT_BITS) - 1u))));
+        int pos = p;
+        const bool pe = p > 0 && (key_at(p - 1) >> TS_SLOT_BITS) == q, ne = p + 1 < n && (key_at(p + 1) >> TS_SLOT_BITS) == q;
+        if (pe || ne) {
+            int s = p, e = p + 1;
+            while (s > 0 && p - s < TS_MAXRUN && (key_at(s - 1) >> TS_SLOT_BITS) == q) --s;
+            while (e < n && e - p < TS_MAXRUN && (key_at(e) >> TS_SLOT_BITS) == q) ++e;
+            if (p - s >= TS_MAXRUN || e - p >= TS_MAXRUN) too_long = true;
+            int rank = 0;
+            for (int r = s; r < e; ++r)
+                rank += lds_u64(ts_addr(a_w, (int)(key_at(r) & ((1u << TS_SLOT_BITS) - 1u)))) < my ? 1 : 0;
+            pos = s + rank;
+        }
+        keys_out[range.x + pos] = tile_hi | (my >> 32);
+        vals_out[range.x + pos] = (uint32_t)my;
+    }
+    if (too_long) s_red[2 * (THREADS / 32)] = 1;
+    __syncthreads();
+    if (s_red[2 * (THREADS / 32)]) {        // block-uniform: the 64-bit network on the staged words
+        ts_sort_smem<THREADS, CAP>(a_w, n, tid);
+        __syncthreads();
+        for (int i = tid; i < n; i += THREADS) {
+            const uint64_t w = lds_u64(ts_addr(a_w, i));
+            keys_out[range.x + i] = tile_hi | (w >> 32);
+            vals_out[range.x + i] = (uint32_t)w;
+        }
+    }
+}
+
 __device__ __forceinline__ void ce_global(uint64_t *g, int lo, int hi) {
     const uint64_t a = g[lo], b = g[hi];
     if (a > b) { g[lo] = b; g[hi] = a; }
@@ -243,6 +450,10 @@ __global__ void __launch_bounds__(THREADS) tile_sort_short_kernel(uint32_t n_hi,
                                                                   const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_order,
                                                                   uint64_t *seg, uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
     __shared__ uint64_t s_words[ts_phys(CAP)];
+#if LVDGS_TS_Q32
+    __shared__ uint64_t s_pairs[ts_phys(CAP / 2)];
+    __shared__ uint32_t s_red[2 * (THREADS / 32) + 1];
+#endif
     const int tile = (int)__ldg(tile_order + blockIdx.x);
     const uint2 range = ranges[tile];
     const uint32_t n = range.y - range.x;
@@ -253,7 +464,11 @@ __global__ void __launch_bounds__(THREADS) tile_sort_short_kernel(uint32_t n_hi,
             for (uint32_t i = threadIdx.x; i < n; i += THREADS) vals_out[range.x + i] = (uint32_t)seg[range.x + i];
         return;
     }
+#if LVDGS_TS_Q32
+    tile_sort_one_q32<THREADS, CAP>(tile, range, seg, keys_out, vals_out, s_words, s_pairs, s_red);
+#else
     tile_sort_one<THREADS, CAP, false>(tile, range, seg, keys_out, vals_out, s_words);
+#endif
 }
 
 template <int THREADS, int CAP>
