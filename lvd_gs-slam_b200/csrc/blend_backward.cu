@@ -35,42 +35,47 @@ constexpr int BB_BATCH = BB_THREADS * BB_SPT;
 #endif
 constexpr int BB_DIRECT_MAX = LVDGS_BB_DIRECT_MAX;   // up to this many contributing threads: skip the warp reduction
 
-// After the call v[0] of lane L holds the warp-wide sum of slot ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
-__device__ __forceinline__ void transpose_reduce16(float (&v)[16], int lane) {
+// Transposing warp reduction of TEN values per lane: at every butterfly step a lane keeps half of its values and hands
+// the other half to its partner, so the value count halves while the lane span halves (5 + 3 + 2 + 1 + 1 = 12 shuffles
+// instead of 10 x 5).  Returns the warp-wide sum of value number red10_index(lane); lanes for which that is negative
+// hold nothing.  Value i of a lane: i = 5 g + k, group g = lane bit 4, k: see red10_index.
+__device__ __forceinline__ int red10_index(int lane) {
+    if (lane & 1) return -1;
+    const int b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
+    int k;
+    if (!b3) k = b2 ? (b1 ? -1 : 2) : b1;          // first three of the five: 0, 1 | 2
+    else k = b2 ? -1 : 3 + b1;                     // last two: 3, 4
+    return k < 0 ? -1 : 5 * ((lane >> 4) & 1) + k;
+}
+__device__ __forceinline__ float transpose_reduce10(const float (&v)[10], int lane) {
+    float w[5], x[3], y[2];
     {
         const bool up = lane & 16;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float send = up ? v[i] : v[i + 8];
-            const float keep = up ? v[i + 8] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        for (int i = 0; i < 5; ++i) {
+            const float send = up ? v[i] : v[i + 5];
+            const float keep = up ? v[i + 5] : v[i];
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
     }
     {
-        const bool up = lane & 8;
+        const bool up = lane & 8;      // lower lanes keep w0 w1 w2, upper lanes w3 w4
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = up ? v[i] : v[i + 4];
-            const float keep = up ? v[i + 4] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        for (int k = 0; k < 3; ++k) {
+            const float send = up ? w[k] : (k < 2 ? w[3 + k] : 0.f);
+            const float keep = up ? (k < 2 ? w[3 + k] : 0.f) : w[k];
+            x[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
         }
     }
     {
-        const bool up = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float send = up ? v[i] : v[i + 2];
-            const float keep = up ? v[i + 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
+        const bool up = lane & 4;      // lower lanes keep x0 x1, upper lanes x2
+        y[0] = (up ? x[2] : x[0]) + __shfl_xor_sync(0xffffffffu, up ? x[0] : x[2], 4);
+        y[1] = (up ? 0.f : x[1]) + __shfl_xor_sync(0xffffffffu, up ? x[1] : 0.f, 4);
     }
-    {
-        const bool up = lane & 2;
-        const float send = up ? v[0] : v[1];
-        const float keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    const bool up = lane & 2;
+    float z = (up ? y[1] : y[0]) + __shfl_xor_sync(0xffffffffu, up ? y[0] : y[1], 2);
+    z += __shfl_xor_sync(0xffffffffu, z, 1);
+    return z;
 }
 
 __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
@@ -134,9 +139,10 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     for (int k = 0; k < BB_WARPS; ++k) top = max(top, s_top[k]);
     top = min(top, range.y - range.x);
 
-    // slot of the transposing reduction this lane ends up holding, and whether it is a real accumulator slot
-    const int slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-    const bool commits = !(lane & 1) && slot < 11 && slot != 7;
+    // value of the transposing reduction this lane ends up holding -> its slot in the accumulator row
+    const int red_i = red10_index(lane);
+    const bool commits = red_i >= 0;
+    const int slot = red_i < 7 ? red_i : red_i + 1;           // values 0..6 -> slots 0..6, 7..9 -> rgb slots 8..10
 
     // entries are visited in decreasing contributor index k = top-1 ... 0
     for (int remaining = (int)top; remaining > 0; remaining -= BB_BATCH) {
@@ -226,14 +232,13 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 S2 = fma2(al2, cdp2, mul2(one_m2, S2));
                 const f32x2 m2 = mul2(G2, dL2);
                 const f32x2 mdx2 = mul2(m2, bc(dx)), mdy2 = mul2(m2, dy2);
-                float v[16];
+                float v[10];      // accumulator-row slots 0..6, 8..10 (ACC_STRIDE layout in common.cuh)
                 v[0] = hsum(mdx2); v[1] = hsum(mdy2);
                 v[2] = dx * v[0];                                 // both pixels share dx
                 v[3] = hsum(mul2(mdx2, dy2)); v[4] = hsum(mul2(mdy2, dy2));
                 v[5] = hsum(m2);
                 v[6] = hsum(mul2(wgt2, dpd_2));
-                v[8] = hsum(mul2(wgt2, dp0_2)); v[9] = hsum(mul2(wgt2, dp1_2)); v[10] = hsum(mul2(wgt2, dp2_2));
-                v[7] = v[11] = v[12] = v[13] = v[14] = v[15] = 0.f;
+                v[7] = hsum(mul2(wgt2, dp0_2)); v[8] = hsum(mul2(wgt2, dp1_2)); v[9] = hsum(mul2(wgt2, dp2_2));
                 if (vmask) {
                     float *row = acc + (size_t)lds32(a_j + 8) * ACC_STRIDE;
                     if (__popc(vmask) <= BB_DIRECT_MAX) {
@@ -242,11 +247,11 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                         if (valid) {
                             atomicAdd(row + 0, v[0]); atomicAdd(row + 1, v[1]); atomicAdd(row + 2, v[2]); atomicAdd(row + 3, v[3]);
                             atomicAdd(row + 4, v[4]); atomicAdd(row + 5, v[5]); atomicAdd(row + 6, v[6]);
-                            atomicAdd(row + 8, v[8]); atomicAdd(row + 9, v[9]); atomicAdd(row + 10, v[10]);
+                            atomicAdd(row + 8, v[7]); atomicAdd(row + 9, v[8]); atomicAdd(row + 10, v[9]);
                         }
                     } else {
-                        transpose_reduce16(v, lane);
-                        if (commits) atomicAdd(row + slot, v[0]);
+                        const float sum = transpose_reduce10(v, lane);
+                        if (commits) atomicAdd(row + slot, sum);
                     }
                 }
             }
