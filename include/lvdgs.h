@@ -204,6 +204,52 @@ int lvdgs_cub_sort_pairs(int64_t n, const uint64_t *keys_in, uint64_t *keys_out,
                          uint32_t *vals_out, int32_t end_bit, void *workspace, size_t workspace_bytes,
                          void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * The callers either side of the rasterizer (SURVEY.md section 8f "next" rows).  Same conventions as above.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+#define LVDGS_LOSS_OPACITY_WEIGHT 1       /* rgb term weighted by the rendered opacity (tracking: utils/slam_utils.py:60) */
+#define LVDGS_LOSS_DEPTH_NEEDS_OPAQUE 2   /* depth term only where opacity > 0.95 (tracking rgbd: utils/slam_utils.py:74) */
+
+/*
+ * Row N3.  Replaces the torch expression graphs of get_loss_tracking / get_loss_tracking_rgb / get_loss_tracking_rgbd
+ * (utils/slam_utils.py:42-83) and get_loss_mapping / _rgb / _rgbd (:86-121) together with their autograd backward:
+ *   loss = w_rgb * mean_{c,p} o | m (exp(a) I_c + b) - m gt_c |  +  w_depth * mean_p | md D - md gtD |
+ *   m = (sum_c gt_c > rgb_boundary_threshold) * grad_mask,  o = opacity or 1,  md = (gtD > 0.01) [* (opacity > 0.95)].
+ * color [3,H,W], depth / opacity / gt_depth / grad_mask [H,W] (gt_depth NULL or w_depth == 0: no depth term; grad_mask,
+ * opacity NULL: ones), exposure = device pointer to {a, b} or NULL (a = b = 0).
+ * Outputs: g_color [3,H,W] = dL/dI, g_depth [H,W] (NULL ok), g_opacity [H,W] (NULL ok),
+ *   out[4] (device) = {loss, dL/da, dL/db, 0}.  Deterministic (fixed summation order).
+ */
+size_t lvdgs_fused_loss_workspace_bytes(void);
+int lvdgs_fused_loss(int32_t width, int32_t height, const float *color, const float *depth, const float *opacity,
+                     const float *gt_color, const float *gt_depth, const float *grad_mask, const float *exposure,
+                     float rgb_boundary_threshold, float w_rgb, float w_depth, int32_t flags, float *g_color,
+                     float *g_depth, float *g_opacity, float *out, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Row N4.  Keyframe covisibility from per-Gaussian visibility (n_touched > 0), replacing the logical_and / logical_or
+ * + count_nonzero chains of utils/slam_frontend.py:1598-1603,1631-1639: out[4] (device, uint64) =
+ * {|a|, |b|, |a and b|, |a or b|}; an element is visible when non-zero; elem_bytes in {1, 4, 8} (bool / int32 / int64).
+ */
+int lvdgs_covis_counts(int64_t n, const void *a, const void *b, int32_t elem_bytes, uint64_t *out, void *stream);
+/* n_obs[i] = number of the K visibility arrays (device array of K device pointers) that are non-zero at i; replaces the
+ * CPU accumulation `n_obs += visibility.cpu()` of utils/slam_backend.py:322-325. */
+int lvdgs_n_obs(int64_t n, int32_t K, const void *const *masks, int32_t elem_bytes, int32_t *n_obs, void *stream);
+
+/*
+ * Row N1.  Stable compaction of up to 16 row-major float arrays by one keep mask (uint8, non-zero = keep): the
+ * parameter / Adam-moment surgery of GaussianModel.prune_points (callers utils/slam_backend.py:128-145,322-339).
+ * lvdgs_compact_count scans the mask and leaves the number of kept rows in *count_dev (a device uint32 inside the
+ * workspace) -- read it back to size the destinations; lvdgs_compact_move (same mask, same workspace, any number of
+ * calls) writes the kept rows of src[k] ([n, widths[k]]) to dst[k] in their original order.  dst must not alias src.
+ */
+size_t lvdgs_compact_workspace_bytes(int64_t n);
+int lvdgs_compact_count(int64_t n, const uint8_t *keep, void *workspace, size_t workspace_bytes, uint32_t **count_dev,
+                        void *stream);
+int lvdgs_compact_move(int64_t n, const uint8_t *keep, const void *workspace, int32_t n_arrays,
+                       const float *const *src, float *const *dst, const int32_t *widths, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -376,6 +376,45 @@ int lvdgs_adam_step(int64_t n, float *params, const float *grads, float *exp_avg
                             (cudaStream_t)stream);
 }
 
+size_t lvdgs_fused_loss_workspace_bytes(void) { return fused_loss_workspace_bytes(); }
+int lvdgs_fused_loss(int32_t width, int32_t height, const float *color, const float *depth, const float *opacity,
+                     const float *gt_color, const float *gt_depth, const float *grad_mask, const float *exposure,
+                     float rgb_boundary_threshold, float w_rgb, float w_depth, int32_t flags, float *g_color,
+                     float *g_depth, float *g_opacity, float *out, void *workspace, size_t workspace_bytes, void *stream) {
+    if (width <= 0 || height <= 0 || !color || !gt_color || !g_color || !out || !workspace) { set_error("fused_loss: bad arguments"); return 1; }
+    if (w_depth != 0.f && gt_depth && !depth) { set_error("fused_loss: depth term without a rendered depth"); return 1; }
+    if ((flags & (LVDGS_LOSS_OPACITY_WEIGHT | LVDGS_LOSS_DEPTH_NEEDS_OPAQUE)) && !opacity) { set_error("fused_loss: flags need the opacity image"); return 1; }
+    g_debug_sync = 0;
+    return launch_fused_loss(width, height, color, depth, opacity, gt_color, gt_depth, grad_mask, exposure,
+                             rgb_boundary_threshold, w_rgb, w_depth, flags, g_color, g_depth, g_opacity, out, workspace,
+                             workspace_bytes, (cudaStream_t)stream);
+}
+
+int lvdgs_covis_counts(int64_t n, const void *a, const void *b, int32_t elem_bytes, uint64_t *out, void *stream) {
+    if (n < 0 || !out || (n > 0 && (!a || !b))) { set_error("covis_counts: bad arguments"); return 1; }
+    g_debug_sync = 0;
+    return launch_covis(n, a, b, elem_bytes, (unsigned long long *)out, (cudaStream_t)stream);
+}
+int lvdgs_n_obs(int64_t n, int32_t K, const void *const *masks, int32_t elem_bytes, int32_t *n_obs, void *stream) {
+    if (n < 0 || K < 0 || (n > 0 && (!n_obs || (K > 0 && !masks)))) { set_error("n_obs: bad arguments"); return 1; }
+    g_debug_sync = 0;
+    return launch_n_obs(n, K, masks, elem_bytes, n_obs, (cudaStream_t)stream);
+}
+
+size_t lvdgs_compact_workspace_bytes(int64_t n) { return compact_workspace_bytes(n > 0 ? n : 0); }
+int lvdgs_compact_count(int64_t n, const uint8_t *keep, void *workspace, size_t workspace_bytes, uint32_t **count_dev,
+                        void *stream) {
+    if (n < 0 || !workspace || !count_dev || (n > 0 && !keep)) { set_error("compact_count: bad arguments"); return 1; }
+    g_debug_sync = 0;
+    return launch_compact_count(n, keep, workspace, workspace_bytes, count_dev, (cudaStream_t)stream);
+}
+int lvdgs_compact_move(int64_t n, const uint8_t *keep, const void *workspace, int32_t n_arrays,
+                       const float *const *src, float *const *dst, const int32_t *widths, void *stream) {
+    if (n < 0 || !workspace || (n_arrays > 0 && (!src || !dst || !widths)) || (n > 0 && !keep)) { set_error("compact_move: bad arguments"); return 1; }
+    g_debug_sync = 0;
+    return launch_compact_move(n, keep, workspace, n_arrays, src, dst, widths, (cudaStream_t)stream);
+}
+
 size_t lvdgs_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n > 0 ? n : 1); }
 int lvdgs_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1,
                      int32_t end_bit, void *workspace, size_t workspace_bytes, int32_t *selector, void *stream) {

@@ -229,6 +229,18 @@ int launch_adam_step(int64_t n, float *params, const float *grads, float *exp_av
                      const int64_t *group_end, const float *lr, double beta1, double beta2, double eps, int step,
                      cudaStream_t s);
 
+size_t fused_loss_workspace_bytes();
+int launch_fused_loss(int W, int H, const float *color, const float *depth, const float *opacity, const float *gt_color,
+                      const float *gt_depth, const float *grad_mask, const float *exposure, float thr, float w_rgb,
+                      float w_depth, int flags, float *g_color, float *g_depth, float *g_opacity, float *out, void *ws,
+                      size_t ws_bytes, cudaStream_t s);
+int launch_covis(int64_t n, const void *a, const void *b, int elem, unsigned long long *out, cudaStream_t s);
+int launch_n_obs(int64_t n, int K, const void *const *masks_dev, int elem, int32_t *n_obs, cudaStream_t s);
+size_t compact_workspace_bytes(int64_t n);
+int launch_compact_count(int64_t n, const uint8_t *keep, void *ws, size_t ws_bytes, uint32_t **count_dev, cudaStream_t s);
+int launch_compact_move(int64_t n, const uint8_t *keep, const void *ws, int n_arrays, const float *const *src,
+                        float *const *dst, const int32_t *widths, cudaStream_t s);
+
 size_t dist2_workspace_bytes(int P);
 int launch_dist2(int P, const float *points, float *mean_dists, void *ws, size_t ws_bytes, cudaStream_t s);
 

@@ -1,0 +1,324 @@
+// slam_ops.cu -- the callers either side of the rasterizer: the photometric +
+// depth losses that produce the rasterizer's upstream gradients, the keyframe-covisibility counts on n_touched masks,
+// and the row compaction behind prune_points.  All HBM-bound single passes; each replaces a chain of torch elementwise
+// kernels and their full-size temporaries in the reference.
+#include "common.cuh"
+
+namespace lvdgs {
+
+// ---------------------------------------------------------------------------------------------------------
+// N3: fused tracking / mapping loss (utils/slam_utils.py:42-121) with its gradient, in one pass over the pixels.
+//   loss = w_rgb * mean_{c,p} o(p) | m(p) (ea I_c(p) + eb) - m(p) gt_c(p) |  +  w_d * mean_p | md(p) D(p) - md(p) gtD(p) |
+//   ea = exp(exposure_a), eb = exposure_b (image_ab of get_loss_tracking / get_loss_mapping),
+//   m  = (sum_c gt_c > rgb_boundary_threshold) * grad_mask          (grad_mask only in the tracking loss, :59)
+//   o  = rendered opacity (tracking, :60) or 1 (mapping)
+//   md = (gtD > 0.01) * (opacity > 0.95 in the tracking rgbd loss, :73-74)
+// Outputs: dL/dI [3,H,W], dL/dD [H,W], dL/dopacity [H,W] (optional), and out[4] = {loss, dL/dexposure_a, dL/dexposure_b, 0}.
+// Deterministic: per-block partial sums, the last block adds them in block order.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LOSS_THREADS = 256;
+
+struct LossArgs {
+    int HW;
+    const float *color, *depth, *opacity, *gt_color, *gt_depth, *grad_mask, *exposure;
+    float thr, w_rgb, w_depth;
+    int flags;
+    float *g_color, *g_depth, *g_opacity, *out;
+    float *partials;          // [blocks][4]
+    unsigned int *ticket;
+};
+
+__device__ __forceinline__ float sgnf(float x) { return (float)(x > 0.f) - (float)(x < 0.f); }
+
+__global__ void __launch_bounds__(LOSS_THREADS) fused_loss_kernel(const LossArgs a) {
+    __shared__ float s_part[LOSS_THREADS / 32][4];
+    __shared__ bool s_last;
+    const float ea = a.exposure ? __expf(__ldg(a.exposure)) : 1.f;       // torch.exp in the reference; see tolerance in the tests
+    const float eb = a.exposure ? __ldg(a.exposure + 1) : 0.f;
+    const float k_rgb = a.w_rgb / (3.f * (float)a.HW), k_d = a.w_depth / (float)a.HW;
+    const bool use_opacity = a.flags & LVDGS_LOSS_OPACITY_WEIGHT, opaque_depth = a.flags & LVDGS_LOSS_DEPTH_NEEDS_OPAQUE;
+    float loss = 0.f, dea = 0.f, deb = 0.f;
+    for (int p = blockIdx.x * LOSS_THREADS + threadIdx.x; p < a.HW; p += gridDim.x * LOSS_THREADS) {
+        const float g0 = __ldg(a.gt_color + p), g1 = __ldg(a.gt_color + a.HW + p), g2 = __ldg(a.gt_color + 2 * a.HW + p);
+        float m = (g0 + g1 + g2 > a.thr) ? 1.f : 0.f;
+        if (a.grad_mask) m *= __ldg(a.grad_mask + p);
+        const float op = a.opacity ? __ldg(a.opacity + p) : 1.f;
+        const float o = use_opacity ? op : 1.f;
+        float abs_sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float I = __ldg(a.color + c * a.HW + p);
+            const float gt = c == 0 ? g0 : (c == 1 ? g1 : g2);
+            const float r = m * fmaf(ea, I, eb) - m * gt;       // the reference's own form: image * mask - gt * mask
+            const float s = sgnf(r) * m * o * k_rgb;
+            abs_sum += fabsf(r);
+            a.g_color[c * a.HW + p] = s * ea;
+            dea += s * ea * I;
+            deb += s;
+        }
+        loss += o * abs_sum * k_rgb;
+        if (a.g_opacity) a.g_opacity[p] = use_opacity ? abs_sum * k_rgb : 0.f;
+        float gd = 0.f;
+        if (a.w_depth != 0.f && a.gt_depth) {
+            const float gD = __ldg(a.gt_depth + p), D = __ldg(a.depth + p);
+            float md = gD > 0.01f ? 1.f : 0.f;
+            if (opaque_depth) md *= op > 0.95f ? 1.f : 0.f;
+            const float r = D * md - gD * md;
+            loss += fabsf(r) * k_d;
+            gd = sgnf(r) * md * k_d;
+        }
+        if (a.g_depth) a.g_depth[p] = gd;
+    }
+    float v[3] = {loss, dea, deb};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], d);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_part[warp][0] = v[0]; s_part[warp][1] = v[1]; s_part[warp][2] = v[2]; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float t = 0.f;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) t += s_part[w][threadIdx.x];
+        a.partials[blockIdx.x * 4 + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x < 3) {
+        float t = 0.f;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(a.partials + b * 4 + threadIdx.x);
+        // d/d(exposure_a) of exp(a) I + b is exp(a) I, already folded in above
+        a.out[threadIdx.x] = t;
+        if (threadIdx.x == 0) { a.out[3] = 0.f; *a.ticket = 0u; }
+    }
+}
+
+constexpr int LOSS_MAX_BLOCKS = 592;     // 4 per SM
+size_t fused_loss_workspace_bytes() { return align_up(LOSS_MAX_BLOCKS * 4 * sizeof(float)) + 256; }
+
+int launch_fused_loss(int W, int H, const float *color, const float *depth, const float *opacity, const float *gt_color,
+                      const float *gt_depth, const float *grad_mask, const float *exposure, float thr, float w_rgb,
+                      float w_depth, int flags, float *g_color, float *g_depth, float *g_opacity, float *out, void *ws,
+                      size_t ws_bytes, cudaStream_t s) {
+    if (ws_bytes < fused_loss_workspace_bytes()) { set_error("fused_loss: workspace too small"); return 1; }
+    LossArgs a;
+    a.HW = W * H;
+    a.color = color; a.depth = depth; a.opacity = opacity; a.gt_color = gt_color; a.gt_depth = gt_depth;
+    a.grad_mask = grad_mask; a.exposure = exposure; a.thr = thr; a.w_rgb = w_rgb; a.w_depth = w_depth; a.flags = flags;
+    a.g_color = g_color; a.g_depth = g_depth; a.g_opacity = g_opacity; a.out = out;
+    a.partials = (float *)ws;
+    a.ticket = (unsigned int *)((char *)ws + align_up(LOSS_MAX_BLOCKS * 4 * sizeof(float)));
+    const int blocks = min(LOSS_MAX_BLOCKS, ceil_div(a.HW, LOSS_THREADS));
+    LVDGS_PRE(s);
+    fused_loss_kernel<<<blocks, LOSS_THREADS, 0, s>>>(a);
+    LVDGS_LAUNCHED(s, "fused_loss");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// N4: covisibility of two keyframes from their per-Gaussian visibility (utils/slam_frontend.py:1598-1643:
+// logical_and / logical_or + count_nonzero, four temporaries and four reductions per pair).  One pass:
+// out[4] = {|a|, |b|, |a and b|, |a or b|}; an element counts as visible when non-zero.  elem = bytes per element (1, 4, 8).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) covis_kernel(int64_t n, const T *__restrict__ a, const T *__restrict__ b,
+                                                    unsigned long long *__restrict__ out) {
+    unsigned int ca = 0, cb = 0, ci = 0, cu = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const bool x = a[i] != 0, y = b[i] != 0;
+        ca += x; cb += y; ci += x && y; cu += x || y;
+    }
+    ca = __reduce_add_sync(0xffffffffu, ca); cb = __reduce_add_sync(0xffffffffu, cb);
+    ci = __reduce_add_sync(0xffffffffu, ci); cu = __reduce_add_sync(0xffffffffu, cu);
+    if ((threadIdx.x & 31) == 0) {
+        if (ca) atomicAdd(out + 0, (unsigned long long)ca);
+        if (cb) atomicAdd(out + 1, (unsigned long long)cb);
+        if (ci) atomicAdd(out + 2, (unsigned long long)ci);
+        if (cu) atomicAdd(out + 3, (unsigned long long)cu);
+    }
+}
+
+int launch_covis(int64_t n, const void *a, const void *b, int elem, unsigned long long *out, cudaStream_t s) {
+    LVDGS_CHECK(cudaMemsetAsync(out, 0, 4 * sizeof(unsigned long long), s));
+    if (n <= 0) return 0;
+    const int blocks = (int)min((int64_t)148 * 8, (n + 255) / 256);
+    LVDGS_PRE(s);
+    if (elem == 1) covis_kernel<uint8_t><<<blocks, 256, 0, s>>>(n, (const uint8_t *)a, (const uint8_t *)b, out);
+    else if (elem == 4) covis_kernel<int32_t><<<blocks, 256, 0, s>>>(n, (const int32_t *)a, (const int32_t *)b, out);
+    else if (elem == 8) covis_kernel<long long><<<blocks, 256, 0, s>>>(n, (const long long *)a, (const long long *)b, out);
+    else { set_error("covis: element size %d not in {1,4,8}", elem); return 1; }
+    LVDGS_LAUNCHED(s, "covis_counts");
+    return 0;
+}
+
+// n_obs[i] = number of the K masks that see Gaussian i (utils/slam_backend.py:322-325 does this on the CPU after K
+// device-to-host copies).  masks: device array of K device pointers.
+template <typename T>
+__global__ void __launch_bounds__(256) n_obs_kernel(int64_t n, int K, const T *const *__restrict__ masks, int32_t *__restrict__ n_obs) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        int c = 0;
+        for (int k = 0; k < K; ++k) c += masks[k][i] != 0;
+        n_obs[i] = c;
+    }
+}
+
+int launch_n_obs(int64_t n, int K, const void *const *masks_dev, int elem, int32_t *n_obs, cudaStream_t s) {
+    if (n <= 0) return 0;
+    const int blocks = (int)min((int64_t)148 * 8, (n + 255) / 256);
+    LVDGS_PRE(s);
+    if (elem == 1) n_obs_kernel<uint8_t><<<blocks, 256, 0, s>>>(n, K, (const uint8_t *const *)masks_dev, n_obs);
+    else if (elem == 4) n_obs_kernel<int32_t><<<blocks, 256, 0, s>>>(n, K, (const int32_t *const *)masks_dev, n_obs);
+    else if (elem == 8) n_obs_kernel<long long><<<blocks, 256, 0, s>>>(n, K, (const long long *const *)masks_dev, n_obs);
+    else { set_error("n_obs: element size %d not in {1,4,8}", elem); return 1; }
+    LVDGS_LAUNCHED(s, "n_obs");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// N1: stable row compaction of several row-major float arrays by one keep mask -- GaussianModel.prune_points /
+// _prune_optimizer (callers utils/slam_backend.py:128-145, 322-339) index every parameter and both Adam moments with
+// the same boolean mask, one torch index kernel + allocation per tensor.  Here: count per 1024-row block, scan the block
+// counts, then every block moves its kept rows of ALL arrays (destination rows are contiguous per block, so the
+// stores are coalesced).  dst must not alias src.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CP_THREADS = 256, CP_ROWS = 1024;
+constexpr int CP_MAX_ARRAYS = 16;
+
+__global__ void __launch_bounds__(CP_THREADS) compact_count_kernel(int64_t n, const uint8_t *__restrict__ keep, uint32_t *__restrict__ block_counts) {
+    __shared__ uint32_t s_w[CP_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * CP_ROWS;
+    uint32_t c = 0;
+#pragma unroll
+    for (int u = 0; u < CP_ROWS / CP_THREADS; ++u) {
+        const int64_t i = base + u * CP_THREADS + threadIdx.x;
+        c += i < n && keep[i] != 0;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < CP_THREADS / 32; ++w) t += s_w[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the block counts in place; total -> counts[nblocks]
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int nblocks, uint32_t *__restrict__ counts) {
+    __shared__ uint32_t s_ws[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int b = base + threadIdx.x;
+        const uint32_t c = b < nblocks ? counts[b] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_ws[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_ws[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += t; }
+            s_ws[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + (warp ? s_ws[warp - 1] : 0u) + incl - c;
+        if (b < nblocks) counts[b] = excl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += s_ws[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[nblocks] = s_carry;
+}
+
+struct CompactArrays {
+    const float *src[CP_MAX_ARRAYS];
+    float *dst[CP_MAX_ARRAYS];
+    int width[CP_MAX_ARRAYS];
+    int count;
+};
+
+__global__ void __launch_bounds__(CP_THREADS) compact_move_kernel(int64_t n, const uint8_t *__restrict__ keep, const uint32_t *__restrict__ block_offsets,
+                                                                  const CompactArrays arr) {
+    __shared__ uint32_t s_src[CP_ROWS];          // source rows of this block's kept rows, in order
+    __shared__ uint32_t s_wbase[CP_THREADS / 32];
+    __shared__ uint32_t s_total;
+    const int64_t base = (int64_t)blockIdx.x * CP_ROWS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // thread t owns rows base + 4t .. base + 4t + 3 (consecutive, so the kept order is the row order)
+    uint32_t flags = 0, c = 0;
+#pragma unroll
+    for (int u = 0; u < CP_ROWS / CP_THREADS; ++u) {
+        const int64_t i = base + (int64_t)threadIdx.x * (CP_ROWS / CP_THREADS) + u;
+        if (i < n && keep[i] != 0) { flags |= 1u << u; ++c; }
+    }
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_wbase[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int w = 0; w < CP_THREADS / 32; ++w) { const uint32_t t = s_wbase[w]; s_wbase[w] = run; run += t; }
+        s_total = run;
+    }
+    __syncthreads();
+    uint32_t pos = s_wbase[warp] + incl - c;
+#pragma unroll
+    for (int u = 0; u < CP_ROWS / CP_THREADS; ++u)
+        if (flags & (1u << u)) s_src[pos++] = (uint32_t)(threadIdx.x * (CP_ROWS / CP_THREADS) + u);
+    __syncthreads();
+    const uint32_t total = s_total;
+    const size_t dst_row0 = block_offsets[blockIdx.x];
+    for (int k = 0; k < arr.count; ++k) {
+        const int w = arr.width[k];
+        const float *__restrict__ src = arr.src[k] + (size_t)base * w;
+        float *__restrict__ dst = arr.dst[k] + dst_row0 * w;
+        for (uint32_t e = threadIdx.x; e < total * (uint32_t)w; e += CP_THREADS) {
+            const uint32_t r = e / (uint32_t)w, col = e - r * (uint32_t)w;
+            dst[e] = src[(size_t)s_src[r] * w + col];
+        }
+    }
+}
+
+size_t compact_workspace_bytes(int64_t n) { return align_up(((size_t)((n + CP_ROWS - 1) / CP_ROWS) + 2) * sizeof(uint32_t)); }
+
+int launch_compact_count(int64_t n, const uint8_t *keep, void *ws, size_t ws_bytes, uint32_t **count_dev, cudaStream_t s) {
+    if (ws_bytes < compact_workspace_bytes(n)) { set_error("compact: workspace too small"); return 1; }
+    uint32_t *counts = (uint32_t *)ws;
+    const int nblocks = (int)((n + CP_ROWS - 1) / CP_ROWS);
+    if (nblocks > 0) {
+        LVDGS_PRE(s);
+        compact_count_kernel<<<nblocks, CP_THREADS, 0, s>>>(n, keep, counts);
+        LVDGS_LAUNCHED(s, "compact_count");
+    }
+    LVDGS_PRE(s);
+    compact_scan_kernel<<<1, 1024, 0, s>>>(nblocks, counts);
+    LVDGS_LAUNCHED(s, "compact_scan");
+    *count_dev = counts + nblocks;
+    return 0;
+}
+
+int launch_compact_move(int64_t n, const uint8_t *keep, const void *ws, int n_arrays, const float *const *src,
+                        float *const *dst, const int32_t *widths, cudaStream_t s) {
+    if (n_arrays < 0 || n_arrays > CP_MAX_ARRAYS) { set_error("compact: at most %d arrays per call", CP_MAX_ARRAYS); return 1; }
+    const int nblocks = (int)((n + CP_ROWS - 1) / CP_ROWS);
+    if (nblocks == 0 || n_arrays == 0) return 0;
+    CompactArrays arr;
+    arr.count = n_arrays;
+    for (int k = 0; k < n_arrays; ++k) {
+        if (widths[k] <= 0 || !src[k] || !dst[k] || src[k] == dst[k]) { set_error("compact: bad array %d (in-place is not supported)", k); return 1; }
+        arr.src[k] = src[k]; arr.dst[k] = dst[k]; arr.width[k] = widths[k];
+    }
+    LVDGS_PRE(s);
+    compact_move_kernel<<<nblocks, CP_THREADS, 0, s>>>(n, keep, (const uint32_t *)ws, arr);
+    LVDGS_LAUNCHED(s, "compact_move");
+    return 0;
+}
+
+}  // namespace lvdgs

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC_DIR = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 SO_PATH = os.path.join(PKG_DIR, "liblvdgs.so")
-SOURCES = ["api.cu", "preprocess.cu", "radix_sort.cu", "tile_sort.cu", "blend_forward.cu", "blend_backward.cu",
+SOURCES = ["api.cu", "preprocess.cu", "radix_sort.cu", "tile_sort.cu", "slam_ops.cu", "blend_forward.cu", "blend_backward.cu",
            "preprocess_backward.cu", "knn.cu", "adam.cu", "cub_compare.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("LVDGS_NVCC_DEFS", "").split()
@@ -100,7 +100,9 @@ EXPORTS = ["lvdgs_version", "lvdgs_last_error", "lvdgs_set_device", "lvdgs_launc
            "lvdgs_get_geom_layout", "lvdgs_get_binning_layout", "lvdgs_get_img_layout", "lvdgs_rasterize_forward",
            "lvdgs_backward_scratch_bytes", "lvdgs_rasterize_backward", "lvdgs_mark_visible",
            "lvdgs_dist2_workspace_bytes", "lvdgs_dist2", "lvdgs_adam_step", "lvdgs_sort_workspace_bytes", "lvdgs_sort_pairs",
-           "lvdgs_cub_sort_workspace_bytes", "lvdgs_cub_sort_pairs"]
+           "lvdgs_cub_sort_workspace_bytes", "lvdgs_cub_sort_pairs",
+           "lvdgs_fused_loss_workspace_bytes", "lvdgs_fused_loss", "lvdgs_covis_counts", "lvdgs_n_obs",
+           "lvdgs_compact_workspace_bytes", "lvdgs_compact_count", "lvdgs_compact_move"]
 
 
 def lib():
@@ -140,6 +142,14 @@ def lib():
     L.lvdgs_cub_sort_workspace_bytes.argtypes = [i64, i32]
     L.lvdgs_cub_sort_workspace_bytes.restype = sz
     L.lvdgs_cub_sort_pairs.argtypes = [i64, vp, vp, vp, vp, i32, vp, sz, vp]
+    L.lvdgs_fused_loss_workspace_bytes.restype = sz
+    L.lvdgs_fused_loss.argtypes = [i32, i32] + [vp] * 7 + [f, f, f, i32] + [vp] * 5 + [sz, vp]
+    L.lvdgs_covis_counts.argtypes = [i64, vp, vp, i32, vp, vp]
+    L.lvdgs_n_obs.argtypes = [i64, i32, vp, i32, vp, vp]
+    L.lvdgs_compact_workspace_bytes.argtypes = [i64]
+    L.lvdgs_compact_workspace_bytes.restype = sz
+    L.lvdgs_compact_count.argtypes = [i64, vp, vp, sz, C.POINTER(vp), vp]
+    L.lvdgs_compact_move.argtypes = [i64, vp, vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp]
     _lib = L
     return L
 

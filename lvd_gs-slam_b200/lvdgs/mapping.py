@@ -124,6 +124,39 @@ class ShardedMapper:
                                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         _native.check(rc, "lvdgs_adam_step")
 
+    # ---- map maintenance ----
+    def prune(self, keep: torch.Tensor) -> int:
+        """GaussianModel.prune_points on the replicated block (callers utils/slam_backend.py:128-145,322-339): drops the
+        rows where `keep` is zero from every parameter group, both Adam moments and the densification statistics -- one
+        mask scan + two launches (lvdgs_compact_*) instead of one torch index kernel per tensor.  Every rank must call it
+        with the identical mask (it is derived from all-reduced statistics), so the replicas stay identical.
+        Returns the new number of Gaussians."""
+        if not self.param_flat.is_cuda:
+            raise RuntimeError("ShardedMapper.prune: parameters must live on a CUDA device (no CPU path)")
+        from .slam_ops import compact_rows
+        widths = group_widths(self.M)
+        srcs = []
+        for flat in (self.param_flat, self.exp_avg, self.exp_avg_sq):
+            srcs += [flat[self.slices[n]].view(self.P, widths[n]) for n in GROUPS]
+        srcs += [self.grad_norm_accum.view(self.P, 1), self.denom.view(self.P, 1), self.max_radii2D.view(self.P, 1)]
+        new = compact_rows(keep, srcs)
+        P2 = new[0].shape[0]
+        ng = len(GROUPS)
+        lr_of = {n: float(self.lr_flat[self.slices[n].start]) if self.P else 0.0 for n in GROUPS}
+        flats = [torch.cat([t.reshape(-1) for t in new[i * ng:(i + 1) * ng]]) if P2 else
+                 torch.zeros(0, dtype=torch.float32, device=self.device) for i in range(3)]
+        self.param_flat, self.exp_avg, self.exp_avg_sq = flats
+        self.grad_norm_accum, self.denom, self.max_radii2D = (t.reshape(-1) for t in new[3 * ng:])
+        self.lr_flat = torch.empty_like(self.param_flat)
+        self.P, off = P2, 0
+        for name in GROUPS:
+            n = widths[name] * P2
+            self.slices[name] = slice(off, off + n)
+            self.params[name] = self.param_flat[off:off + n]
+            self.lr_flat[off:off + n] = lr_of[name]
+            off += n
+        return P2
+
     # ---- one mapping iteration ----
     def step(self, n_views: int, render_and_grad: Callable[[int], None], grad_flat: torch.Tensor,
              zero: Optional[Callable[[], None]] = None, extra_views: Sequence[int] = ()):

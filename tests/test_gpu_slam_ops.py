@@ -1,0 +1,161 @@
+"""GPU parity of the SURVEY 8f "next" rows built so far (N3 fused losses, N4 covisibility counts, N1 prune compaction)
+against torch transcriptions of the reference code they replace (cited per test).  Losses: float32 sums in a different
+order -> 1e-5 relative on the loss, 1e-6 absolute on the (O(1/HW)) gradients; integer / row-move results exact."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+H, W = 37, 53
+
+
+def _viewpoint(rng, dev):
+    vp = types.SimpleNamespace()
+    gt = rng.uniform(0, 1, (3, H, W)).astype(np.float32)
+    gt[:, :5, :7] = 0.001                                       # below rgb_boundary_threshold
+    vp.original_image = torch.tensor(gt, device=dev)
+    md = rng.uniform(0.5, 40, (H, W)).astype(np.float32)
+    md[10:14, 20:30] = 0.0                                      # invalid mono depth
+    vp.mono_depth = md
+    vp.grad_mask = torch.tensor((rng.uniform(0, 1, (1, H, W)) > 0.3), device=dev)
+    vp.exposure_a = torch.tensor([0.07], device=dev, requires_grad=True)
+    vp.exposure_b = torch.tensor([-0.02], device=dev, requires_grad=True)
+    return vp
+
+
+# ---- the reference's losses, restated (utils/slam_utils.py:42-121) ----
+def ref_tracking_rgb(config, image, depth, opacity, vp):
+    gt = vp.original_image
+    mask = (gt.sum(dim=0) > config["Training"]["rgb_boundary_threshold"]).view(1, H, W) * vp.grad_mask
+    return (opacity * torch.abs(image * mask - gt * mask)).mean()
+
+
+def ref_tracking(config, image, depth, opacity, vp):
+    image_ab = torch.exp(vp.exposure_a) * image + vp.exposure_b
+    if config["Training"]["monocular"]:
+        return ref_tracking_rgb(config, image_ab, depth, opacity, vp)
+    alpha = config["Training"].get("alpha", 0.95)
+    gt_depth = torch.from_numpy(vp.mono_depth).to(image.device)[None]
+    dmask = (gt_depth > 0.01).view(*depth.shape) * (opacity > 0.95).view(*depth.shape)
+    l1_depth = torch.abs(depth * dmask - gt_depth * dmask)
+    return alpha * ref_tracking_rgb(config, image_ab, depth, opacity, vp) + (1 - alpha) * l1_depth.mean()
+
+
+def ref_mapping(config, image, vp, depth=None, initialization=False, monodepth=True):
+    image_ab = image if initialization else torch.exp(vp.exposure_a) * image + vp.exposure_b
+    gt = vp.original_image
+    mask = (gt.sum(dim=0) > config["Training"]["rgb_boundary_threshold"]).view(1, H, W)
+    l1_rgb = torch.abs(image_ab * mask - gt * mask)
+    if config["Training"]["monocular"] and not monodepth:
+        return l1_rgb.mean()
+    alpha = config["Training"].get("alpha", 0.95)
+    gt_depth = torch.from_numpy(vp.mono_depth).to(image.device)[None]
+    dmask = (gt_depth > 0.01).view(*depth.shape)
+    return alpha * l1_rgb.mean() + (1 - alpha) * torch.abs(depth * dmask - gt_depth * dmask).mean()
+
+
+def _inputs(rng, dev):
+    mk = lambda a: torch.tensor(a.astype(np.float32), device=dev, requires_grad=True)
+    image = mk(rng.uniform(0, 1, (3, H, W)))
+    depth = mk(rng.uniform(0.5, 40, (1, H, W)))
+    opacity = mk(rng.uniform(0.5, 1.0, (1, H, W)))
+    return image, depth, opacity
+
+
+def _grads(loss, leaves):
+    gs = torch.autograd.grad(loss * 1.7, leaves, allow_unused=True)     # a non-trivial grad_output
+    return [None if g is None else g.detach().cpu().numpy() for g in gs]
+
+
+@pytest.mark.parametrize("mode", ["track_mono", "track_rgbd", "map_rgbd", "map_rgb", "map_init"])
+def test_fused_losses_match_the_reference_expressions(mode):
+    from lvdgs import slam_ops
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(7)
+    vp = _viewpoint(rng, dev)
+    image, depth, opacity = _inputs(rng, dev)
+    config = {"Training": {"monocular": mode != "track_rgbd", "rgb_boundary_threshold": 0.01, "alpha": 0.9}, "Dataset": {"depth_loss": False}}
+    leaves = [image, depth, opacity, vp.exposure_a, vp.exposure_b]
+    if mode.startswith("track"):
+        ours = slam_ops.get_loss_tracking(config, image, depth, opacity, vp)
+        ref = ref_tracking(config, image, depth, opacity, vp)
+    else:
+        kw = dict(depth=depth, initialization=mode == "map_init", monodepth=mode != "map_rgb")
+        ours = slam_ops.get_loss_mapping(config, image, vp, **kw)
+        ref = ref_mapping(config, image, vp, **kw)
+    assert abs(float(ours) - float(ref)) <= 1e-5 * abs(float(ref))
+    for go, gr in zip(_grads(ours, leaves), _grads(ref, leaves)):
+        if gr is None:
+            assert go is None or np.abs(go).max() == 0
+        else:
+            assert go is not None
+            np.testing.assert_allclose(go, gr, rtol=2e-5, atol=1e-7 if gr.size > 1 else 1e-6)
+
+
+def test_fused_loss_is_deterministic_and_feeds_the_rasterizer_layout():
+    from lvdgs import slam_ops
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(9)
+    vp = _viewpoint(rng, dev)
+    image, depth, opacity = _inputs(rng, dev)
+    config = {"Training": {"monocular": True, "rgb_boundary_threshold": 0.01}}
+    vals = [float(slam_ops.get_loss_mapping(config, image, vp, depth=depth)) for _ in range(5)]
+    assert len(set(vals)) == 1
+    with pytest.raises(RuntimeError):
+        slam_ops.get_loss_mapping(config, image.cpu(), vp, depth=depth.cpu())
+
+
+def test_covisibility_and_n_obs():
+    """utils/slam_frontend.py:1598-1603,1631-1639 and utils/slam_backend.py:322-325."""
+    from lvdgs import slam_ops
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for n in (0, 1, 31, 1000, 300_001):
+        a = (torch.rand(n, generator=g) > 0.4).to(dev)
+        b = (torch.rand(n, generator=g) > 0.7).to(dev)
+        want = [int(a.count_nonzero()), int(b.count_nonzero()), int((a & b).count_nonzero()), int((a | b).count_nonzero())]
+        for conv in (lambda t: t, lambda t: t.to(torch.int32) * 5, lambda t: t.long()):      # bool, n_touched-like int32, .long()
+            assert slam_ops.covisibility(conv(a), conv(b)).tolist() == want
+    masks = [(torch.rand(5000, generator=g) > 0.5).long().to(dev) for _ in range(8)]
+    n_obs = slam_ops.accumulate_n_obs(masks)
+    assert torch.equal(n_obs.long(), torch.stack(masks).sum(0))
+
+
+@pytest.mark.parametrize("n", [0, 1, 1023, 1024, 1025, 200_000])
+def test_compact_rows_equals_boolean_indexing(n):
+    """GaussianModel.prune_points: every tensor indexed by the same mask (utils/slam_backend.py:128-145)."""
+    from lvdgs import slam_ops
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(n)
+    tensors = [torch.randn(n, w, generator=g).to(dev) for w in (3, 3, 1, 3, 4, 48)] + [torch.randn(n, 1, 3, generator=g).to(dev)]
+    for frac in (0.0, 0.3, 1.0):
+        keep = (torch.rand(n, generator=g) < frac).to(dev)
+        out = slam_ops.compact_rows(keep, tensors)
+        for t, o in zip(tensors, out):
+            assert torch.equal(o, t[keep])
+
+
+def test_mapper_prune_keeps_replica_state_consistent():
+    from lvdgs.mapping import ShardedMapper, GROUPS
+    dev = torch.device("cuda")
+    P = 5000
+    m = ShardedMapper(P, sh_coeffs=1, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    m.param_flat.copy_(torch.randn(m.param_flat.numel(), generator=g))
+    m.exp_avg.copy_(torch.randn(m.param_flat.numel(), generator=g))
+    m.exp_avg_sq.copy_(torch.rand(m.param_flat.numel(), generator=g))
+    m.denom.copy_(torch.rand(P, generator=g))
+    before = {n: m.view(n).clone() for n in GROUPS}
+    avg_before = m.exp_avg[m.slices["rotations"]].view(P, 4).clone()
+    denom_before = m.denom.clone()
+    keep = (torch.rand(P, generator=g) > 0.25).to(dev)
+    P2 = m.prune(keep)
+    assert P2 == int(keep.sum()) and m.P == P2 and m.param_flat.numel() == 14 * P2
+    for n in GROUPS:
+        assert torch.equal(m.view(n), before[n][keep])
+    assert torch.equal(m.exp_avg[m.slices["rotations"]].view(P2, 4), avg_before[keep])
+    assert torch.equal(m.denom, denom_before[keep])
+    m.adam_step(torch.ones_like(m.param_flat))          # the fused optimiser runs on the pruned block
