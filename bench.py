@@ -218,6 +218,7 @@ def main():
 
     # ---------------- e2e: plugin surface, host buffers ----------------
     import diff_gaussian_rasterization as dgr
+    from lvdgs import slam_ops
     params = [x.detach().clone().requires_grad_() for x in (means3D, opac, scales, rots, shs)]
     e2e_opt = torch.optim.Adam(params, lr=1e-8)
     rng = np.random.default_rng(2)
@@ -246,6 +247,8 @@ def main():
             st["cam"].copy_(hb["cam"], non_blocking=True)
             st["ready"].record(copy_stream)
 
+    torch_loss = os.environ.get("LVDGS_E2E_TORCH_LOSS", "0") == "1"
+
     def step_e2e():
         cur = torch.cuda.current_stream()
         e2e_opt.zero_grad(set_to_none=True)
@@ -265,8 +268,13 @@ def main():
             color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(rs)(
                 means3D=params[0], means2D=m2d, opacities=params[1], shs=params[4], scales=params[2], rotations=params[3],
                 theta=theta, rho=rho)
-            # mapping-style loss (utils/slam_utils.py:107-121): 0.9 L1 rgb + 0.1 L1 depth
-            loss = 0.9 * (color - img).abs().mean() + 0.1 * (depth - dep).abs().mean()
+            # mapping loss of utils/slam_utils.py:107-121 (0.9 L1 rgb + 0.1 L1 depth on the valid pixels) through the
+            # package's fused loss op (lvdgs.slam_ops); LVDGS_E2E_TORCH_LOSS=1 uses the torch expression
+            if torch_loss:
+                loss = 0.9 * (color - img).abs().mean() + 0.1 * (depth - dep).abs().mean()
+            else:
+                loss = slam_ops.fused_loss(color, depth, gt_image=img, gt_depth=dep, rgb_boundary_threshold=-1.0,
+                                           w_rgb=0.9, w_depth=0.1)
             loss.backward()
             st["free"].record(cur)
             res_host[j, 0:1].copy_(loss.detach().reshape(1), non_blocking=True)
@@ -388,7 +396,8 @@ def main():
                                  "of a step rewrite >300 MB of binning state between revisits",
                            "parallelism": f"keyframes sharded over {world} rank(s), NCCL SUM-allreduce of [P,14] grads" if world > 1 else "1 GPU"},
                 "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "path": "diff_gaussian_rasterization.GaussianRasterizer (autograd) + torch L1 loss + torch Adam; "
+                        "d2h_bytes_per_step": d2h, "path": "diff_gaussian_rasterization.GaussianRasterizer (autograd) + "
+                                + ("torch L1 loss" if torch_loss else "lvdgs.slam_ops.fused_loss (mapping rgbd loss)") + " + torch Adam; "
                                 "H2D of the next view prefetched on a copy stream"},
                 "gpu_launches": launches, "mapping_iters_per_s": 1e3 / ms, "clocks": clocks, "roofline": roof,
                 "kernels": kernels, "cpu_baseline": cpu}
