@@ -87,3 +87,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(d, f)).read()
                 assert not re.search(r"^\s*(import oracle|from oracle)", src, re.M), os.path.join(d, f)
+
+
+def test_slam_ops_reject_cpu_tensors():
+    """The ops either side of the rasterizer have no CPU path either."""
+    import torch
+    from lvdgs import slam_ops
+    from lvdgs.mapping import ShardedMapper
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        slam_ops.fused_loss(torch.zeros(3, 4, 4), gt_image=torch.zeros(3, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        slam_ops.covisibility(torch.zeros(8, dtype=torch.bool), torch.zeros(8, dtype=torch.bool))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        slam_ops.compact_rows(torch.ones(8, dtype=torch.bool), [torch.zeros(8, 3)])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ShardedMapper(8, device="cpu").prune(torch.ones(8, dtype=torch.bool))
