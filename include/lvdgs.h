@@ -250,6 +250,38 @@ int lvdgs_compact_count(int64_t n, const uint8_t *keep, void *workspace, size_t 
 int lvdgs_compact_move(int64_t n, const uint8_t *keep, const void *workspace, int32_t n_arrays,
                        const float *const *src, float *const *dst, const int32_t *widths, void *stream);
 
+/*
+ * Rows a15 / a16: the tail of one tracking iteration on the device.  lvdgs_pose_state is the camera's device-resident
+ * block; view / proj / campos are in the layout lvdgs_rasterize_* read (pass pointers into the block), so a tracking
+ * loop needs no host arithmetic between iterations.  lvdgs_pose_step = torch.optim.Adam.step on (cam_rot_delta,
+ * cam_trans_delta, exposure_a, exposure_b) with learning rates (lr_rot, lr_trans, lr_exposure) followed by update_pose
+ * (utils/slam_frontend.py:1466-1521, utils/pose_utils.py:70-87): T_w2c <- SE3_exp([trans_delta; rot_delta]) T_w2c, the
+ * three camera matrices refreshed, converged = |tau| < converged_threshold.  g_tau = (rho[3], theta[3]) as produced by
+ * lvdgs_rasterize_backward's dL_dtau_sum; g_exposure = {dL/da, dL/db} (lvdgs_fused_loss out + 1) or NULL (exposure
+ * fixed).  `step` is the 1-based iteration of this frame's optimiser (Adam bias correction); the host initialises the block
+ * (R, T, proj_raw, exposure; moments zero) and the matrices are valid after the first lvdgs_pose_step or when the host
+ * fills them too.
+ */
+typedef struct lvdgs_pose_state {
+    float view[16];       /* world_view_transform = [R T; 0 1]^T, flat row-major (utils/camera_utils.py:106-108) */
+    float proj[16];       /* full_proj_transform = world_view_transform @ projection_matrix (:110-116) */
+    float proj_raw[16];   /* projection_matrix (P^T), constant per camera */
+    float campos[4];      /* camera_center (:118-120), w unused */
+    float R[9];           /* world -> camera rotation, row-major */
+    float T[3];
+    float exposure[4];    /* exposure_a, exposure_b, unused, unused */
+    float adam_m[8];      /* first / second moments of (rot_delta[3], trans_delta[3], exposure_a, exposure_b) */
+    float adam_v[8];
+    int32_t step;         /* pose steps taken (device-side count) */
+    int32_t converged;    /* |tau| < threshold at the last step */
+    float tau_norm;
+    float pad;
+} lvdgs_pose_state;
+
+int lvdgs_pose_step(lvdgs_pose_state *state, const float *g_tau, const float *g_exposure, float lr_rot, float lr_trans,
+                    float lr_exposure, double beta1, double beta2, double eps, int32_t step, float converged_threshold,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

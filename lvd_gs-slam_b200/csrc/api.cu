@@ -415,6 +415,15 @@ int lvdgs_compact_move(int64_t n, const uint8_t *keep, const void *workspace, in
     return launch_compact_move(n, keep, workspace, n_arrays, src, dst, widths, (cudaStream_t)stream);
 }
 
+int lvdgs_pose_step(lvdgs_pose_state *state, const float *g_tau, const float *g_exposure, float lr_rot, float lr_trans,
+                    float lr_exposure, double beta1, double beta2, double eps, int32_t step, float converged_threshold,
+                    void *stream) {
+    if (!state || !g_tau || step < 1) { set_error("pose_step: bad arguments"); return 1; }
+    g_debug_sync = 0;
+    return launch_pose_step(state, g_tau, g_exposure, lr_rot, lr_trans, lr_exposure, beta1, beta2, eps, step,
+                            converged_threshold, (cudaStream_t)stream);
+}
+
 size_t lvdgs_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n > 0 ? n : 1); }
 int lvdgs_sort_pairs(int64_t n, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1,
                      int32_t end_bit, void *workspace, size_t workspace_bytes, int32_t *selector, void *stream) {

@@ -3,6 +3,7 @@
 // and the row compaction behind prune_points.  All HBM-bound single passes; each replaces a chain of torch elementwise
 // kernels and their full-size temporaries in the reference.
 #include "common.cuh"
+#include <cmath>
 
 namespace lvdgs {
 
@@ -318,6 +319,109 @@ int launch_compact_move(int64_t n, const uint8_t *keep, const void *ws, int n_ar
     LVDGS_PRE(s);
     compact_move_kernel<<<nblocks, CP_THREADS, 0, s>>>(n, keep, (const uint32_t *)ws, arr);
     LVDGS_LAUNCHED(s, "compact_move");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Rows a15 / a16 on the device: one tracking iteration's tail.  The reference runs torch.optim.Adam on
+// (cam_rot_delta, cam_trans_delta, exposure_a, exposure_b) and then update_pose (utils/slam_frontend.py:1466-1521,
+// utils/pose_utils.py:56-87): ~60 tiny torch kernels and two host synchronisations (`if angle < 1e-5`, `if converged`)
+// per iteration.  Here: one single-thread kernel on the camera's device-resident state block (lvdgs_pose_state):
+//   Adam step (the deltas are zero before every step, as update_pose resets them) -> tau = [trans_delta; rot_delta]
+//   -> T_w2c <- SE3_exp(tau) T_w2c -> world_view_transform, full_proj_transform, camera_center refreshed in the layout
+//   the rasterizer reads (utils/camera_utils.py:106-120) -> converged = |tau| < threshold.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void pose_step_kernel(lvdgs_pose_state *st, const float *__restrict__ g_tau, const float *__restrict__ g_exposure,
+                                 float lr_rot, float lr_trans, float lr_exp, float beta1, float beta2, float eps,
+                                 float bc1, float bc2_sqrt, float threshold) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // gradients in parameter order: rot_delta (theta), trans_delta (rho), exposure a, b
+    float g[8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { g[k] = g_tau[3 + k]; g[3 + k] = g_tau[k]; }
+    g[6] = g_exposure ? g_exposure[0] : 0.f;
+    g[7] = g_exposure ? g_exposure[1] : 0.f;
+    float delta[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float lr = k < 3 ? lr_rot : (k < 6 ? lr_trans : lr_exp);
+        const float m = beta1 * st->adam_m[k] + (1.f - beta1) * g[k];
+        const float v = beta2 * st->adam_v[k] + (1.f - beta2) * g[k] * g[k];
+        st->adam_m[k] = m; st->adam_v[k] = v;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;                 // torch.optim.Adam's order of operations
+        delta[k] = -(lr / bc1) * (m / denom);
+    }
+    if (g_exposure) { st->exposure[0] += delta[6]; st->exposure[1] += delta[7]; }
+    const float th[3] = {delta[0], delta[1], delta[2]}, rho[3] = {delta[3], delta[4], delta[5]};
+    // SE3_exp(tau), utils/pose_utils.py:22-68
+    const float W[9] = {0.f, -th[2], th[1], th[2], 0.f, -th[0], -th[1], th[0], 0.f};
+    float W2[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) W2[3 * i + j] = W[3 * i] * W[j] + W[3 * i + 1] * W[3 + j] + W[3 * i + 2] * W[6 + j];
+    const float angle = sqrtf(th[0] * th[0] + th[1] * th[1] + th[2] * th[2]);
+    float a1, a2, b1, b2;            // R = I + a1 W + a2 W2,  V = I + b1 W + b2 W2
+    if (angle < 1e-5f) { a1 = 1.f; a2 = 0.5f; b1 = 0.5f; b2 = 1.f / 6.f; }
+    else {
+        const float s = sinf(angle), c = cosf(angle);
+        a1 = s / angle; a2 = (1.f - c) / (angle * angle);
+        b1 = a2; b2 = (angle - s) / (angle * angle * angle);
+    }
+    float Rd[9], Vd[9], t[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float I = (k % 4 == 0) ? 1.f : 0.f;
+        Rd[k] = I + a1 * W[k] + a2 * W2[k];
+        Vd[k] = I + b1 * W[k] + b2 * W2[k];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = Vd[3 * i] * rho[0] + Vd[3 * i + 1] * rho[1] + Vd[3 * i + 2] * rho[2];
+    // new_w2c = SE3_exp(tau) @ T_w2c
+    float Rn[9], Tn[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Rn[3 * i + j] = Rd[3 * i] * st->R[j] + Rd[3 * i + 1] * st->R[3 + j] + Rd[3 * i + 2] * st->R[6 + j];
+        Tn[i] = Rd[3 * i] * st->T[0] + Rd[3 * i + 1] * st->T[1] + Rd[3 * i + 2] * st->T[2] + t[i];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) st->R[k] = Rn[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) st->T[k] = Tn[k];
+    // world_view_transform = [R T; 0 1]^T (flat row-major), full_proj = world_view_transform @ projection_matrix
+    float V4[16];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { V4[4 * r] = Rn[r]; V4[4 * r + 1] = Rn[3 + r]; V4[4 * r + 2] = Rn[6 + r]; V4[4 * r + 3] = 0.f; }
+    V4[12] = Tn[0]; V4[13] = Tn[1]; V4[14] = Tn[2]; V4[15] = 1.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) st->view[k] = V4[k];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc += V4[4 * i + k] * st->proj_raw[4 * k + j];
+            st->proj[4 * i + j] = acc;
+        }
+    // camera centre = -R^T T
+#pragma unroll
+    for (int j = 0; j < 3; ++j) st->campos[j] = -(Rn[j] * Tn[0] + Rn[3 + j] * Tn[1] + Rn[6 + j] * Tn[2]);
+    const float tn = sqrtf(th[0] * th[0] + th[1] * th[1] + th[2] * th[2] + rho[0] * rho[0] + rho[1] * rho[1] + rho[2] * rho[2]);
+    st->tau_norm = tn;
+    st->converged = tn < threshold ? 1 : 0;
+    st->step += 1;
+}
+
+int launch_pose_step(lvdgs_pose_state *state, const float *g_tau, const float *g_exposure, float lr_rot, float lr_trans,
+                     float lr_exp, double beta1, double beta2, double eps, int step, float threshold, cudaStream_t s) {
+    const float bc1 = (float)(1.0 - pow(beta1, (double)step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+    LVDGS_PRE(s);
+    pose_step_kernel<<<1, 32, 0, s>>>(state, g_tau, g_exposure, lr_rot, lr_trans, lr_exp, (float)beta1, (float)beta2,
+                                      (float)eps, bc1, bc2_sqrt, threshold);
+    LVDGS_LAUNCHED(s, "pose_step");
     return 0;
 }
 

@@ -24,7 +24,7 @@ import torch
 from . import _native
 from ._native import RasterParams, ptr
 
-FLAG_EXACT_PP, FLAG_OPACITY_GRAD, FLAG_ACCUMULATE = 1, 2, 4
+FLAG_EXACT_PP, FLAG_OPACITY_GRAD, FLAG_ACCUMULATE, FLAG_POSE_ONLY = 1, 2, 4, 8
 
 
 class ViewCamera:
@@ -134,11 +134,12 @@ class RasterEngine:
         return sl.R
 
     def backward(self, vc, means3D, opacities, scales, rotations, shs, dL_dcolor, dL_ddepth=None,
-                 dL_dopacity=None, accumulate=True, slot: int = 0, stream=None):
+                 dL_dopacity=None, accumulate=True, slot: int = 0, stream=None, pose_only: bool = False):
+        """pose_only (tracking): only slot.g_tau (and slot.g_means2D) are produced, no parameter gradients."""
         sl = self.slots[slot]
-        flags = self.flags | (FLAG_ACCUMULATE if accumulate else 0)
+        flags = self.flags | (FLAG_ACCUMULATE if accumulate and not pose_only else 0) | (FLAG_POSE_ONLY if pose_only else 0)
         prm = self._params(vc, flags)
-        g = self.grads
+        g = {k: None for k in self.grads} if pose_only else self.grads
         rc = self.L.lvdgs_rasterize_backward(
             C.byref(prm), ptr(vc.bg), ptr(means3D), ptr(sl.radii), None, ptr(opacities), ptr(scales), ptr(rotations),
             None, ptr(vc.view), ptr(vc.proj), ptr(vc.proj_raw), ptr(dL_dcolor), ptr(dL_ddepth), ptr(dL_dopacity), ptr(shs),
