@@ -280,15 +280,15 @@ __device__ __forceinline__ void tp_levels_from(uint32_t a_s, int nw, int tid) {
 }
 
 constexpr int TS_MAXRUN = 16;
-constexpr int TS_SLOT_BITS = 11, TS_Q_BITS = 32 - TS_SLOT_BITS;
 
-// Sorts the n < 2^TS_SLOT_BITS words of one tile.  s_words: ts_phys(CAP) words (the unsorted 64-bit words, by slot),
+// Sorts the n <= CAP = 2^TS_SLOT_BITS words of one tile.  s_words: ts_phys(CAP) words (the unsorted 64-bit words, by slot),
 // s_pairs: ts_phys(CAP / 2) pair words, s_red: 2 * THREADS / 32 + 1 words of scratch.
 template <int THREADS, int CAP>
 __device__ __forceinline__ void tile_sort_one_q32(int tile, uint2 range, const uint64_t *seg, uint64_t *__restrict__ keys_out,
                                                   uint32_t *__restrict__ vals_out, uint64_t *s_words, uint64_t *s_pairs,
                                                   uint32_t *s_red) {
-    static_assert(CAP <= (1 << TS_SLOT_BITS), "slot bits");
+    constexpr int TS_SLOT_BITS = ts_ilog2(CAP), TS_Q_BITS = 32 - TS_SLOT_BITS;
+    static_assert(CAP == (1 << TS_SLOT_BITS), "CAP must be a power of two");
     const int n = (int)(range.y - range.x), nw = (n + 1) >> 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t a_w = smem_u32(s_words), a_p = smem_u32(s_pairs);
     const uint64_t *g = seg + range.x;
@@ -471,6 +471,31 @@ __global__ void __launch_bounds__(THREADS) tile_sort_short_kernel(uint32_t n_hi,
 #endif
 }
 
+// Middle class: lists of n_lo <= n < n_hi instances, 32-bit stand-ins like the short class but with CAP = 8192 (13 slot bits,
+// 19 depth bits), persistent CTAs walking the head of tile_order (longer lists first, so they skip what the long class
+// owns and stop at the first short list).
+template <int THREADS, int CAP>
+__global__ void __launch_bounds__(THREADS) tile_sort_mid_kernel(uint32_t n_lo, uint32_t n_hi, int tiles, uint32_t capacity, const uint32_t *__restrict__ n_dev,
+                                                                const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_order,
+                                                                uint64_t *seg, uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+    extern __shared__ uint64_t s_dyn[];
+    uint64_t *s_words = s_dyn, *s_pairs = s_dyn + ts_phys(CAP);
+    uint32_t *s_red = reinterpret_cast<uint32_t *>(s_pairs + ts_phys(CAP / 2));
+    if (n_dev && __ldg(n_dev) > capacity) return;
+    for (int i = blockIdx.x; i < tiles; i += gridDim.x) {
+        const int tile = (int)__ldg(tile_order + i);
+        const uint2 range = ranges[tile];
+        const uint32_t n = range.y - range.x;
+        if (n < n_lo) break;                            // tile_order is sorted by length class: nothing longer follows
+        if (n >= n_hi) continue;                        // the long class's
+        __syncthreads();
+        tile_sort_one_q32<THREADS, CAP>(tile, range, seg, keys_out, vals_out, s_words, s_pairs, s_red);
+    }
+}
+constexpr size_t ts_mid_smem_bytes(int threads, int cap) {
+    return (size_t)(ts_phys(cap) + ts_phys(cap / 2)) * sizeof(uint64_t) + (2 * (threads / 32) + 1) * sizeof(uint32_t);
+}
+
 template <int THREADS, int CAP>
 __global__ void __launch_bounds__(THREADS) tile_sort_long_kernel(uint32_t n_lo, int tiles, uint32_t capacity, const uint32_t *__restrict__ n_dev,
                                                                  const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_order,
@@ -490,10 +515,11 @@ __global__ void __launch_bounds__(THREADS) tile_sort_long_kernel(uint32_t n_lo, 
 #define LVDGS_TS_SHORT_THREADS 256
 #endif
 constexpr int TS_SHORT_THREADS = LVDGS_TS_SHORT_THREADS, TS_SHORT_CAP = 2048;    // lists of 1 .. 2047 instances
-constexpr int TS_LONG_THREADS = 1024, TS_LONG_CAP = 16384;
+constexpr int TS_MID_THREADS = 512, TS_MID_CAP = 8192;                            // lists of 2048 .. 8191
+constexpr int TS_LONG_THREADS = 1024, TS_LONG_CAP = 16384;                        // 8192 and longer (beyond 16384: chunked)
 
-// long_lists: launch the long-list class (lists of TS_SHORT_CAP or more).  Without it such lists are NOT sorted: the
-// caller must check the longest list (binning_prep leaves it next to R) and re-run with long_lists = true.
+// long_lists: launch the middle and long classes (lists of TS_SHORT_CAP or more).  Without them such lists are NOT sorted:
+// the caller must check the longest list (binning_prep leaves it next to R) and re-run with long_lists = true.
 int tile_sort_long_threshold() { return TS_SHORT_CAP; }
 int launch_tile_sort(int tiles, int64_t capacity, const uint32_t *n_dev, const uint2 *ranges, const uint32_t *tile_order,
                      uint64_t *seg, uint64_t *keys_out, uint32_t *vals_out, bool long_lists, cudaStream_t s) {
@@ -501,16 +527,22 @@ int launch_tile_sort(int tiles, int64_t capacity, const uint32_t *n_dev, const u
     const uint32_t cap = (uint32_t)min(capacity, (int64_t)0xffffffffll);
     static int sm_count = 0;
     auto long_k = tile_sort_long_kernel<TS_LONG_THREADS, TS_LONG_CAP>;
+    auto mid_k = tile_sort_mid_kernel<TS_MID_THREADS, TS_MID_CAP>;
+    constexpr size_t mid_smem = ts_mid_smem_bytes(TS_MID_THREADS, TS_MID_CAP);
     if (!sm_count) {
         int dev = 0;
         LVDGS_CHECK(cudaGetDevice(&dev));
         LVDGS_CHECK(cudaFuncSetAttribute(long_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts_smem_bytes(TS_LONG_CAP)));
+        LVDGS_CHECK(cudaFuncSetAttribute(mid_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem));
         LVDGS_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     if (long_lists) {
         LVDGS_PRE(s);
-        long_k<<<min(tiles, sm_count), TS_LONG_THREADS, ts_smem_bytes(TS_LONG_CAP), s>>>((uint32_t)TS_SHORT_CAP, tiles, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out);
+        long_k<<<min(tiles, sm_count), TS_LONG_THREADS, ts_smem_bytes(TS_LONG_CAP), s>>>((uint32_t)TS_MID_CAP, tiles, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out);
         LVDGS_LAUNCHED(s, "tile_sort_long");
+        LVDGS_PRE(s);
+        mid_k<<<min(tiles, 2 * sm_count), TS_MID_THREADS, mid_smem, s>>>((uint32_t)TS_SHORT_CAP, (uint32_t)TS_MID_CAP, tiles, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out);
+        LVDGS_LAUNCHED(s, "tile_sort_mid");
     }
     LVDGS_PRE(s);
     tile_sort_short_kernel<TS_SHORT_THREADS, TS_SHORT_CAP><<<tiles, TS_SHORT_THREADS, 0, s>>>((uint32_t)TS_SHORT_CAP, long_lists ? 0 : 1, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out);
