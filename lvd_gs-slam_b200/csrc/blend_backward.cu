@@ -3,15 +3,18 @@
 //
 // The reference issues ten global float atomicAdds per (pixel, Gaussian) pair.  Here:
 //  * a CTA of 4 warps owns a 16x16 tile, a warp an 8x8 pixel block, a thread TWO pixels (rows y and y+4), so one
-//    warp-level reduction serves 64 pairs;
-//  * instances are staged 128 at a time through shared memory, rearmost first, together with a per-block mask from
-//    the same conservative {alpha >= 1/255} bounding-box test as the forward: a warp only visits instances that can
-//    reach its block, and the traversal starts at the tile's largest n_contrib instead of the end of the list;
-//  * per pixel the recurrences are those of A.4 (T <- T/(1-alpha); colour/depth accumulated behind the current
-//    Gaussian), evaluated eagerly;
-//  * per (warp, Gaussian) the twelve partial sums (six geometric moments of m = G dL/dalpha, depth, rgb -- see
-//    ACC_STRIDE in common.cuh) are reduced with a transposing butterfly: 16 shuffles in total instead of 5 per value,
-//    after which sixteen lanes each hold one finished slot and commit it with a single warp-wide RED instruction.
+//    warp-level reduction serves 64 pairs, and the two pixels' arithmetic runs as packed FP32 pairs (FFMA2 / FMUL2 /
+//    FADD2: one issue slot for both);
+//  * instances are staged 256 at a time through shared memory (one 48-byte record each), rearmost first, together
+//    with a per-block mask from the same conservative {alpha >= 1/255} bounding-box test as the forward plus an exact
+//    ellipse-vs-block test: a warp only visits instances that can reach its block, and the traversal starts at the
+//    tile's largest n_contrib instead of the end of the list;
+//  * per pixel the recurrences are those of A.4 (T <- T/(1-alpha); what is blended behind the current Gaussian enters
+//    only as the scalar S = <B, dL/dpixel>), branch-free: a pixel that does not blend the Gaussian runs the same
+//    instructions with alpha = G = 0;
+//  * per (warp, Gaussian) the ten partial sums (six geometric moments of m = G dL/dalpha, depth, rgb -- see
+//    ACC_STRIDE in common.cuh) are reduced with a transposing butterfly (12 shuffles instead of 5 per value), after
+//    which ten lanes each hold one finished sum and commit it with a single warp-wide RED instruction.
 #include "common.cuh"
 
 namespace lvdgs {

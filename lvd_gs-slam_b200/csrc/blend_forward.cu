@@ -5,12 +5,14 @@
 // One CTA per tile, one thread per pixel, each WARP owns an 8x4-pixel block of the tile.  The tile's depth-sorted
 // instance list is streamed in batches of 256: each thread gathers one instance's 48 bytes (xy + bounding-box half
 // extents, conic + opacity, rgb + depth -- three 128-bit loads from the SoA geometry arrays, which are
-// L2-resident) into shared memory and tests the instance's {alpha >= 1/255} bounding box against the eight pixel
+// L2-resident) into one shared-memory record and tests the instance's {alpha >= 1/255} bounding box against the eight pixel
 // blocks; a ballot per block turns the result into eight 32-bit masks per staging warp.  Each warp then walks only
 // the set bits of ITS block's masks, in list order, so an instance that cannot reach a block costs that warp
 // nothing (the reference evaluates the exponent for all 256 pixels and discards it).  The test is conservative, so
 // every (pixel, Gaussian) pair that passes the reference's two skips is still evaluated and the result is
-// unchanged; n_contrib keeps counting list positions.
+// unchanged; n_contrib keeps counting list positions.  The per-pair body is branch-free: a pixel that skips the
+// Gaussian or terminates on it blends with weight 0, and a finished pixel is "parked" at x = 1e18 (alpha = 0 from then
+// on) -- that coordinate doubles as its done flag.
 // FP32 FMA/MUFU bound; no tensor cores (there is no dense contraction on this path).
 // n_touched is aggregated per warp with a ballot, and only while some pixel of the warp still has T > 0.5
 // (T only decreases, so the test T*(1-alpha) > 0.5 can never fire afterwards).

@@ -16,8 +16,12 @@
 // the lower index, elements beyond n behave like +inf without being stored: comparators whose upper index is >= n are
 // skipped, and with the index maps below the live comparators of a stage are a PREFIX [0, cnt) -- the work is
 // proportional to n, not to the next power of two.
-// Lists longer than the shared-memory capacity are handled by the same network with the wide stages run in place in
-// global memory (L2) and the narrow ones chunk by chunk in shared memory.
+// Three size classes (tile_order lists the tiles by decreasing length, so each class is a contiguous run of it):
+//   n < 2048        one 256-thread CTA per tile; sorts 32-bit stand-ins (quantised depth | slot), fixes up ties;
+//   2048 .. 8191    the same with 13 slot bits, persistent 512-thread CTAs;
+//   >= 8192         64-bit network, persistent 1024-thread CTAs, 16384 words of shared memory; longer lists run the wide
+//                   stages in place in global memory (L2) and the narrow ones chunk by chunk in shared memory.
+// The two upper classes are launched only when the previous frame's longest list calls for them (api.cu).
 #include "common.cuh"
 
 #ifndef LVDGS_TS_Q32
