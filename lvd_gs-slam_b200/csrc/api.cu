@@ -341,8 +341,11 @@ int lvdgs_rasterize_backward(const lvdgs_raster_params *prm, const float *backgr
         const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
         const int passes = (32 + tile_bits((uint32_t)(gx * gy)) + 7) / 8;
         const int sel = (p.flags & LVDGS_FLAG_GLOBAL_SORT) ? (passes & 1) : 1;
+        // tracking: the pose gradient needs neither the colour sums (colours do not depend on the pose at SH degree 0 /
+        // with precomputed colours) nor, without a depth loss, the depth sum -> the six geometric moments only
+        const bool moments_only = (p.flags & LVDGS_FLAG_POSE_ONLY) && !dL_dout_depth && (p.sh_degree == 0 || colors_precomp);
         if (launch_blend_backward(p.P, W, H, R, im.ranges, b.vals[sel], im.tile_order, g, background, im.final_T, im.n_contrib,
-                                  dL_dout_color, dL_dout_depth, dL_dout_opacity, p.flags, bg, s)) return 1;
+                                  dL_dout_color, dL_dout_depth, dL_dout_opacity, p.flags, moments_only, bg, s)) return 1;
     }
     if (launch_preprocess_backward(p, means3D, radii, shs, scales, rotations, cov3D_precomp, viewmatrix, projmatrix,
                                    projmatrix_raw, campos, g, bg, colors_precomp != nullptr, dL_dmeans2D, dL_dcolors,

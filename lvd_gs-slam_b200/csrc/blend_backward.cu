@@ -81,6 +81,36 @@ __device__ __forceinline__ float transpose_reduce10(const float (&v)[10], int la
     return z;
 }
 
+// The same for the six geometric moments alone (3 + 2 + 1 + 1 + 1 = 8 shuffles): value 3 g + k, g = lane bit 4.
+__device__ __forceinline__ int red6_index(int lane) {
+    if (lane & 3) return -1;
+    const int b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
+    const int k = b3 ? (b2 ? -1 : 2) : b2;
+    return k < 0 ? -1 : 3 * ((lane >> 4) & 1) + k;
+}
+__device__ __forceinline__ float transpose_reduce6(const float (&v)[10], int lane) {
+    float w[3];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) w[i] = (up ? v[i + 3] : v[i]) + __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 3], 16);
+    }
+    float x0, x1;
+    {
+        const bool up = lane & 8;      // lower lanes keep w0 w1, upper lanes w2
+        x0 = (up ? w[2] : w[0]) + __shfl_xor_sync(0xffffffffu, up ? w[0] : w[2], 8);
+        x1 = (up ? 0.f : w[1]) + __shfl_xor_sync(0xffffffffu, up ? w[1] : 0.f, 8);
+    }
+    const bool up = lane & 4;
+    float y = (up ? x1 : x0) + __shfl_xor_sync(0xffffffffu, up ? x0 : x1, 4);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    return y;
+}
+
+// MOMENTS_ONLY: the colour and depth sums are not needed (pose-only backward at SH degree 0 without a depth gradient --
+// the tracking loop): six values per (warp, Gaussian) instead of ten.
+template <bool MOMENTS_ONLY>
 __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     int W, int H, int gx, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
     const float4 *__restrict__ means2D, const float4 *__restrict__ conic_opacity, const float4 *__restrict__ rgbd,
@@ -143,7 +173,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
     top = min(top, range.y - range.x);
 
     // value of the transposing reduction this lane ends up holding -> its slot in the accumulator row
-    const int red_i = red10_index(lane);
+    const int red_i = MOMENTS_ONLY ? red6_index(lane) : red10_index(lane);
     const bool commits = red_i >= 0;
     const int slot = red_i < 7 ? red_i : red_i + 1;           // values 0..6 -> slots 0..6, 7..9 -> rgb slots 8..10
 
@@ -226,7 +256,6 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 const f32x2 one_m2 = fma2(al2, bc(-1.f), bc(1.f));
                 const f32x2 inv2 = pk(rcp_approx(lo_of(one_m2)), rcp_approx(hi_of(one_m2)));   // 1 - alpha >= 0.01
                 T2 = mul2(T2, inv2);
-                const f32x2 wgt2 = mul2(al2, T2);
                 // the colour / depth blended BEHIND this Gaussian enters only through its dot product with dL/dpixel:
                 // S = <B, dp> obeys the same recurrence as B itself (S <- alpha <c, dp> + (1 - alpha) S)
                 const f32x2 cdp2 = fma2(bc(cd.w), dpd_2, fma2(bc(cd.z), dp2_2, fma2(bc(cd.y), dp1_2, mul2(bc(cd.x), dp0_2))));
@@ -240,8 +269,13 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 v[2] = dx * v[0];                                 // both pixels share dx
                 v[3] = hsum(mul2(mdx2, dy2)); v[4] = hsum(mul2(mdy2, dy2));
                 v[5] = hsum(m2);
-                v[6] = hsum(mul2(wgt2, dpd_2));
-                v[7] = hsum(mul2(wgt2, dp0_2)); v[8] = hsum(mul2(wgt2, dp1_2)); v[9] = hsum(mul2(wgt2, dp2_2));
+                if (!MOMENTS_ONLY) {
+                    const f32x2 wgt2 = mul2(al2, T2);
+                    v[6] = hsum(mul2(wgt2, dpd_2));
+                    v[7] = hsum(mul2(wgt2, dp0_2)); v[8] = hsum(mul2(wgt2, dp1_2)); v[9] = hsum(mul2(wgt2, dp2_2));
+                } else {
+                    v[6] = v[7] = v[8] = v[9] = 0.f;
+                }
                 if (vmask) {
                     float *row = acc + (size_t)lds32(a_j + 8) * ACC_STRIDE;
                     if (__popc(vmask) <= BB_DIRECT_MAX) {
@@ -249,11 +283,14 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                         // straight to the accumulator row (10 REDs) instead of through the 60-instruction reduction
                         if (valid) {
                             atomicAdd(row + 0, v[0]); atomicAdd(row + 1, v[1]); atomicAdd(row + 2, v[2]); atomicAdd(row + 3, v[3]);
-                            atomicAdd(row + 4, v[4]); atomicAdd(row + 5, v[5]); atomicAdd(row + 6, v[6]);
-                            atomicAdd(row + 8, v[7]); atomicAdd(row + 9, v[8]); atomicAdd(row + 10, v[9]);
+                            atomicAdd(row + 4, v[4]); atomicAdd(row + 5, v[5]);
+                            if (!MOMENTS_ONLY) {
+                                atomicAdd(row + 6, v[6]);
+                                atomicAdd(row + 8, v[7]); atomicAdd(row + 9, v[8]); atomicAdd(row + 10, v[9]);
+                            }
                         }
                     } else {
-                        const float sum = transpose_reduce10(v, lane);
+                        const float sum = MOMENTS_ONLY ? transpose_reduce6(v, lane) : transpose_reduce10(v, lane);
                         if (commits) atomicAdd(row + slot, sum);
                     }
                 }
@@ -265,15 +302,20 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
 int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, const uint32_t *point_list,
                           const uint32_t *tile_order, const GeomPtrs &g, const float *bg, const float *final_T, const uint32_t *n_contrib,
                           const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_opacity,
-                          int flags, const BlendGradPtrs &o, cudaStream_t s) {
+                          int flags, bool moments_only, const BlendGradPtrs &o, cudaStream_t s) {
     (void)P;
     if (R <= 0) return 0;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const float *dop = (flags & LVDGS_FLAG_OPACITY_GRAD) ? dL_dout_opacity : nullptr;
     LVDGS_PRE(s);
-    blend_backward_kernel<<<gx * gy, BB_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
-                                                               g.rgbd, tile_order, bg, final_T, n_contrib, dL_dout_color,
-                                                               dL_dout_depth, dop, o.acc);
+    if (moments_only)
+        blend_backward_kernel<true><<<gx * gy, BB_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
+                                                                         g.rgbd, tile_order, bg, final_T, n_contrib, dL_dout_color,
+                                                                         nullptr, dop, o.acc);
+    else
+        blend_backward_kernel<false><<<gx * gy, BB_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
+                                                                          g.rgbd, tile_order, bg, final_T, n_contrib, dL_dout_color,
+                                                                          dL_dout_depth, dop, o.acc);
     LVDGS_LAUNCHED(s, "blend_backward");
     return 0;
 }

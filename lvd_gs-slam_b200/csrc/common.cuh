@@ -212,7 +212,7 @@ struct BlendGradPtrs {
 int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, const uint32_t *point_list,
                           const uint32_t *tile_order, const GeomPtrs &g, const float *bg, const float *final_T, const uint32_t *n_contrib,
                           const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_opacity,
-                          int flags, const BlendGradPtrs &o, cudaStream_t s);
+                          int flags, bool moments_only, const BlendGradPtrs &o, cudaStream_t s);
 
 int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3D, const int32_t *radii,
                                const float *shs, const float *scales, const float *rotations,

@@ -87,16 +87,26 @@ __global__ void __launch_bounds__(LOSS_THREADS) fused_loss_kernel(const LossArgs
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (s_last && threadIdx.x < 3) {
+    if (s_last) {
+        // fixed-order sum of the per-block partials by the whole block: thread t adds the blocks b = t/4, t/4 + 64, ...
+        // of component t%4, then a fixed tree over the 64 strands -- deterministic, and not 600 dependent loads
+        __shared__ float s_fin[LOSS_THREADS];
+        const int c = threadIdx.x & 3, j = threadIdx.x >> 2;
         float t = 0.f;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(a.partials + b * 4 + threadIdx.x);
-        // d/d(exposure_a) of exp(a) I + b is exp(a) I, already folded in above
-        a.out[threadIdx.x] = t;
-        if (threadIdx.x == 0) { a.out[3] = 0.f; *a.ticket = 0u; }
+        if (c < 3)
+            for (unsigned b = j; b < gridDim.x; b += LOSS_THREADS / 4) t += __ldcg(a.partials + b * 4 + c);
+        s_fin[threadIdx.x] = t;
+        __syncthreads();
+        for (int h = LOSS_THREADS / 8; h >= 1; h >>= 1) {
+            if (j < h) s_fin[threadIdx.x] += s_fin[threadIdx.x + 4 * h];
+            __syncthreads();
+        }
+        if (threadIdx.x < 3) a.out[threadIdx.x] = s_fin[threadIdx.x];
+        if (threadIdx.x == 3) { a.out[3] = 0.f; *a.ticket = 0u; }
     }
 }
 
-constexpr int LOSS_MAX_BLOCKS = 592;     // 4 per SM
+constexpr int LOSS_MAX_BLOCKS = 296;     // 2 per SM
 size_t fused_loss_workspace_bytes() { return align_up(LOSS_MAX_BLOCKS * 4 * sizeof(float)) + 256; }
 
 int launch_fused_loss(int W, int H, const float *color, const float *depth, const float *opacity, const float *gt_color,
