@@ -250,19 +250,23 @@ def main():
     torch_loss = os.environ.get("LVDGS_E2E_TORCH_LOSS", "0") == "1"
 
     def step_e2e():
+        """One mapping iteration the way utils/slam_backend.py:167-306 runs it: render every view of the window, sum the
+        per-view losses (`loss_mapping +=`), ONE backward through all of them, one optimiser step."""
         cur = torch.cuda.current_stream()
         e2e_opt.zero_grad(set_to_none=True)
         prefetch(0)
+        total, poses = None, []
         for j, k in enumerate(my_views):
             if j + 1 < len(my_views):
                 prefetch(j + 1)                                 # overlaps with this view's render
             st = stage[j % 2]
             cur.wait_event(st["ready"])
             img, dep, cm = st["img"], st["dep"], st["cam"]
+            cmv = cm.clone()                                    # the staging slot is reused two views later; the backward reads the camera
             rs = dgr.GaussianRasterizationSettings(
                 image_height=H, image_width=W, tanfovx=cams[k].tanfovx, tanfovy=cams[k].tanfovy, bg=bgt, scale_modifier=1.0,
-                viewmatrix=cm[0:16].view(4, 4), projmatrix=cm[16:32].view(4, 4), projmatrix_raw=cm[32:48].view(4, 4),
-                sh_degree=0, campos=cm[48:51], prefiltered=False, debug=False)
+                viewmatrix=cmv[0:16].view(4, 4), projmatrix=cmv[16:32].view(4, 4), projmatrix_raw=cmv[32:48].view(4, 4),
+                sh_degree=0, campos=cmv[48:51], prefiltered=False, debug=False)
             theta = torch.zeros(3, device=dev, requires_grad=True); rho = torch.zeros(3, device=dev, requires_grad=True)
             m2d = torch.zeros_like(params[0], requires_grad=True)
             color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(rs)(
@@ -275,8 +279,11 @@ def main():
             else:
                 loss = slam_ops.fused_loss(color, depth, gt_image=img, gt_depth=dep, rgb_boundary_threshold=-1.0,
                                            w_rgb=0.9, w_depth=0.1)
-            loss.backward()
-            st["free"].record(cur)
+            st["free"].record(cur)                              # the loss forward has consumed the targets (autograd keeps its own tensors)
+            total = loss if total is None else total + loss
+            poses.append((loss, rho, theta, st))
+        total.backward()
+        for j, (loss, rho, theta, st) in enumerate(poses):
             res_host[j, 0:1].copy_(loss.detach().reshape(1), non_blocking=True)
             res_host[j, 1:4].copy_(rho.grad, non_blocking=True)
             res_host[j, 4:7].copy_(theta.grad, non_blocking=True)
@@ -397,7 +404,7 @@ def main():
                            "parallelism": f"keyframes sharded over {world} rank(s), NCCL SUM-allreduce of [P,14] grads" if world > 1 else "1 GPU"},
                 "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "path": "diff_gaussian_rasterization.GaussianRasterizer (autograd) + "
-                                + ("torch L1 loss" if torch_loss else "lvdgs.slam_ops.fused_loss (mapping rgbd loss)") + " + torch Adam; "
+                                + ("torch L1 loss" if torch_loss else "lvdgs.slam_ops.fused_loss (mapping rgbd loss)") + ", losses summed over the window and one backward (as utils/slam_backend.py:167-306) + torch Adam; "
                                 "H2D of the next view prefetched on a copy stream"},
                 "gpu_launches": launches, "mapping_iters_per_s": 1e3 / ms, "clocks": clocks, "roofline": roof,
                 "kernels": kernels, "cpu_baseline": cpu}
