@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
                 // pixel that does not contributes with alpha = 0 and G = 0, which leaves its T / S recurrences untouched
                 // (rcp(1) = 1 exactly) and adds zeros to the warp's sums.
                 const f32x2 dy2 = add2(bc(xy.y), npfy2);
-                const f32x2 p2 = fma2(mul2(bc(co.z), dy2), dy2, mul2(bc(dx), add2(bc(co.x * dx), mul2(bc(co.y), dy2))));
+                const f32x2 p2 = fma2(mul2(bc(co.z), dy2), dy2, mul2(bc(dx), fma2(bc(co.y), dy2, bc(co.x * dx))));
                 const float p2a = lo_of(p2), p2b = hi_of(p2);
                 const float ga = ex2_approx(p2a), gb = ex2_approx(p2b);
                 const float aa = fminf(0.99f, co.w * ga), ab = fminf(0.99f, co.w * gb);
