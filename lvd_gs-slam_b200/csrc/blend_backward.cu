@@ -110,8 +110,11 @@ __device__ __forceinline__ float transpose_reduce6(const float (&v)[10], int lan
 
 // MOMENTS_ONLY: the colour and depth sums are not needed (pose-only backward at SH degree 0 without a depth gradient --
 // the tracking loop): six values per (warp, Gaussian) instead of ten.
+#ifndef LVDGS_BB_MINBLOCKS
+#define LVDGS_BB_MINBLOCKS 1
+#endif
 template <bool MOMENTS_ONLY>
-__global__ void __launch_bounds__(BB_THREADS) blend_backward_kernel(
+__global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward_kernel(
     int W, int H, int gx, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
     const float4 *__restrict__ means2D, const float4 *__restrict__ conic_opacity, const float4 *__restrict__ rgbd,
     const uint32_t *__restrict__ tile_order, const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,

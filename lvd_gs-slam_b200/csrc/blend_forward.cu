@@ -28,7 +28,10 @@ namespace lvdgs {
 #endif
 constexpr int BF_WARPS = 4, BF_THREADS = BF_WARPS * 32, BF_SPT = 2, BF_BATCH = BF_THREADS * BF_SPT;
 
-__global__ void __launch_bounds__(BF_THREADS) blend_forward_kernel(int W, int H, int gx, uint32_t capacity, const uint32_t *__restrict__ n_dev, const uint2 *__restrict__ ranges,
+#ifndef LVDGS_BF_MINBLOCKS
+#define LVDGS_BF_MINBLOCKS 8      // <= 64 registers: 132.6 us against 139 us for 1, 4, 6, 9, 10, 12 (measured)
+#endif
+__global__ void __launch_bounds__(BF_THREADS, LVDGS_BF_MINBLOCKS) blend_forward_kernel(int W, int H, int gx, uint32_t capacity, const uint32_t *__restrict__ n_dev, const uint2 *__restrict__ ranges,
                                                                      const uint32_t *__restrict__ point_list,
                                                                      const float4 *__restrict__ means2D,
                                                                      const float4 *__restrict__ conic_opacity,
