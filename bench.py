@@ -393,6 +393,36 @@ def main():
                "sample": "3 of the 8 views (k=0,3,6), full 1241x376 fwd+bwd each, median; C oracle with OpenMP",
                "seconds_per_view": tv}
 
+    # ---------------- BASELINE configs[1]: the tracking loop, device-resident (rank 0, N=1; extra key, not the metric) ----------------
+    tracking = None
+    if rank == 0 and world == 1:
+        try:
+            from lvdgs.tracking import PoseTracker
+            NT, iters_t = 300_000, 100
+            sct = synth.make_scene(NT, cams[0], seed=0)
+            tt = lambda a: torch.tensor(a, dtype=torch.float32, device=dev).contiguous()
+            gm, go, gs, gr, gsh = tt(sct["means3D"]), tt(sct["opacities"]), tt(sct["scales"]), tt(sct["rotations"]), tt(sct["shs"])
+            eng_t = RasterEngine(NT, W, H, sh_coeffs=1, sh_degree=0, device=dev, slots=1)
+            eng_t.forward(ViewCamera(cams[0], dev), gm, go, gs, gr, gsh)
+            target = eng_t.color.clone()
+            del eng_t
+            trk_ = PoseTracker(NT, W, H, cams[0].tanfovx, cams[0].tanfovy, device=dev, lr_rot=0.003, lr_trans=0.001,
+                               rgb_boundary_threshold=-1.0)
+            R1, T1 = cams[1].R, cams[1].T                       # start from the neighbouring keyframe's pose
+            ts_ = []
+            for rep in range(3):
+                trk_.set_camera(R1, T1, cams[0].projection_matrix)
+                torch.cuda.synchronize(); t0_ = time.perf_counter()
+                out_t = trk_.track(gm, go, gs, gr, gsh, target, iters=iters_t, stop_when_converged=False)
+                torch.cuda.synchronize(); ts_.append(time.perf_counter() - t0_)
+            tsec = float(np.median(ts_[1:]))
+            tracking = {"workload": "kitti_tracking_300k (BASELINE configs[1])", "iters_per_frame": iters_t,
+                        "ms_per_iter": 1e3 * tsec / iters_t, "iters_per_s": iters_t / tsec,
+                        "mpix_per_s": iters_t * H * W / tsec / 1e6,
+                        "path": "lvdgs.tracking.PoseTracker: rasterizer fwd + fused tracking loss + pose-only bwd + lvdgs_pose_step, host wall clock"}
+        except Exception as e:                                   # never let the extra measurement break the metric line
+            tracking = {"error": repr(e)[:200]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
@@ -407,7 +437,7 @@ def main():
                                 + ("torch L1 loss" if torch_loss else "lvdgs.slam_ops.fused_loss (mapping rgbd loss)") + ", losses summed over the window and one backward (as utils/slam_backend.py:167-306) + torch Adam; "
                                 "H2D of the next view prefetched on a copy stream"},
                 "gpu_launches": launches, "mapping_iters_per_s": 1e3 / ms, "clocks": clocks, "roofline": roof,
-                "kernels": kernels, "cpu_baseline": cpu}
+                "kernels": kernels, "cpu_baseline": cpu, "tracking": tracking}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

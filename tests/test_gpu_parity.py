@@ -22,6 +22,8 @@ CASES = {
     # BASELINE.json's full sizes: the headline configuration and the nuScenes-shaped one (configs[3])
     "kitti500k": dict(cam="kitti", N=500_000, sh=0, bg=(0.0, 0.0, 0.0)),
     "nuscenes2m": dict(cam="nuscenes", N=2_000_000, sh=0, bg=(0.0, 0.0, 0.0)),
+    # the scale sweep's image shape (configs[4]: 1920x1080, 8160 tiles -> 13 tile bits in the keys)
+    "hd1m": dict(cam="hd", N=1_000_000, sh=0, bg=(0.0, 0.0, 0.0)),
 }
 
 
@@ -377,3 +379,37 @@ def test_tile_sort_unexpected_long_list_fallback():
         np.testing.assert_array_equal(internals["point_list"], fwd["point_list"])
         ok = fwd["margin"] > 1e-5
         assert np.abs(out["color"][:, ok] - fwd["color"][:, ok]).max() < 1e-5
+
+
+def test_full_size_properties_without_the_oracle():
+    """Size-independent properties at BASELINE's headline size (500k Gaussians, 1241x376): the binning output is a
+    partition of [0, R) into per-tile runs, every run is ordered by (depth bits, Gaussian index), the keys carry their
+    tile, the forward is idempotent bit for bit (atomics only choose slots, never results), and the backward is linear in
+    the upstream gradient."""
+    cam = synth.make_camera("kitti", k=5)
+    sc = synth.make_scene(500_000, cam, seed=0)
+    bg = np.zeros(3, np.float32)
+    H, W = cam.image_height, cam.image_width
+    rng = np.random.default_rng(1)
+    gc = rng.normal(0, 1, (3, H, W)).astype(np.float32)
+    gd = rng.normal(0, 1, (1, H, W)).astype(np.float32)
+    out1, int1, g1 = run_cuda(sc, cam, bg, grads=(gc, gd, None), debug=False)
+    out2, int2, g2 = run_cuda(sc, cam, bg, grads=(2 * gc, 2 * gd, None), debug=False)
+    R = int1["R"]
+    keys, pl, ranges = int1["keys_sorted"], int1["point_list"], int1["ranges"].astype(np.int64)
+    assert R > 1_000_000 and keys.shape == (R,)
+    nz = ranges[:, 1] > ranges[:, 0]
+    starts, ends = ranges[nz, 0], ranges[nz, 1]
+    assert starts[0] == 0 and ends[-1] == R and np.array_equal(starts[1:], ends[:-1])          # a partition, in tile order
+    tile_of = (keys >> np.uint64(32)).astype(np.int64)
+    assert np.array_equal(tile_of, np.repeat(np.nonzero(nz)[0], (ends - starts)))              # every key carries its tile
+    assert np.all(keys[1:] >= keys[:-1])                                                        # (tile | depth) ascending
+    same = keys[1:] == keys[:-1]
+    assert np.all(pl[1:][same] > pl[:-1][same])                                                 # ties: ascending Gaussian index
+    assert np.array_equal((keys & np.uint64(0xffffffff)).astype(np.uint32), int1["depths"].view(np.uint32)[pl])
+    for k in ("color", "depth", "opacity", "radii", "n_touched"):                               # idempotent, bitwise
+        np.testing.assert_array_equal(out1[k], out2[k])
+    np.testing.assert_array_equal(int1["keys_sorted"], int2["keys_sorted"])
+    np.testing.assert_array_equal(int1["point_list"], int2["point_list"])
+    for k in ("means3D", "scales", "rotations", "opacities", "shs", "theta", "rho"):            # linear in the upstream gradient
+        assert rel_err(g2[k], 2.0 * g1[k]) < 1e-4, k
