@@ -175,9 +175,16 @@ int lvdgs_get_img_layout(int32_t W, int32_t H, lvdgs_img_layout *out) { if (!out
 // pinned slot + event for the asynchronous read-back of the instance count (one per host thread, created once)
 static thread_local uint32_t *t_pinned_R = nullptr;
 static thread_local cudaEvent_t t_R_event = nullptr;
-// longest tile list of this thread's previous forward (read back with R): decides whether the next forward launches
-// tile_sort's long-list class speculatively (a wrong guess costs time, never correctness)
-static thread_local uint32_t t_longest_list = 0xffffffffu;
+// longest tile lists of this thread's last forwards (read back with R): decide whether the next forward launches
+// tile_sort's long-list classes speculatively (a wrong guess costs time, never correctness).  The maximum over the last
+// eight forwards is used, so cameras with and without long lists rendered in turn (a mapping window) never re-run.
+static thread_local uint32_t t_longest_hist[8] = {0xffffffffu, 0, 0, 0, 0, 0, 0, 0};
+static thread_local int t_longest_pos = 0;
+static uint32_t longest_recent() {
+    uint32_t m = 0;
+    for (uint32_t v : t_longest_hist) m = v > m ? v : m;
+    return m;
+}
 
 // everything after the instance count is known on the DEVICE: keys, sort, ranges, blend.  `capacity` sizes the
 // launches and the binning arena; the kernels clamp to min(R, capacity) read from device memory.
@@ -275,7 +282,7 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
         void *bin_base = resize(resize_user, LVDGS_BUF_BINNING, bl.total);
         if (!bin_base) { set_error("resize callback returned NULL (binning)"); return 1; }
         // guess from the previous forward, with hysteresis
-        launched_long = (p.flags & LVDGS_FLAG_GLOBAL_SORT) || t_longest_list >= (uint32_t)(tile_sort_long_threshold() * 3 / 4);
+        launched_long = (p.flags & LVDGS_FLAG_GLOBAL_SORT) || longest_recent() >= (uint32_t)(tile_sort_long_threshold() * 3 / 4);
         if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, false, launched_long, background, out_color, out_depth,
                                  out_opacity, n_touched, s)) return 1;
         launched = true;
@@ -283,9 +290,11 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     LVDGS_CHECK(cudaEventSynchronize(t_R_event));
     if (profile_mark("(host: R read-back)", s)) return 1;
     const int64_t R = t_pinned_R[0];
-    t_longest_list = t_pinned_R[1];
+    const uint32_t longest = t_pinned_R[1];
+    t_longest_pos = (t_longest_pos + 1) & 7;
+    t_longest_hist[t_longest_pos] = longest;
     *num_rendered = R;
-    const bool need_long = t_longest_list >= (uint32_t)tile_sort_long_threshold();      // exact: just read back
+    const bool need_long = longest >= (uint32_t)tile_sort_long_threshold();      // exact: just read back
     if (!launched || R > capacity || (need_long && !launched_long)) {
         if (!launched || R > capacity) capacity = R > 0 ? R : 1;
         lvdgs_binning_layout bl; binning_layout(capacity, bl);

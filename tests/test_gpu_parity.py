@@ -371,7 +371,8 @@ def test_tile_sort_unexpected_long_list_fallback():
     fwd, _ = run_oracle(crowded, cam, bg)
     dev = torch.cuda.current_device()
     dgr._capacity_hint.clear()
-    run_cuda(plain, cam, bg, debug=False)                       # longest list of the previous frame: short
+    for _ in range(8):                                          # the guess looks at the last eight forwards: all short lists
+        run_cuda(plain, cam, bg, debug=False)
     for _ in range(2):                                          # 1st: guess "no long lists" is wrong; 2nd: guess is right
         dgr._capacity_hint[dev] = 4_000_000                     # generous hint -> speculative launch, no re-run
         out, internals, _ = run_cuda(crowded, cam, bg, debug=False)
