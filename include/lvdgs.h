@@ -251,6 +251,15 @@ int lvdgs_compact_move(int64_t n, const uint8_t *keep, const void *workspace, in
                        const float *const *src, float *const *dst, const int32_t *widths, void *stream);
 
 /*
+ * Row N1, densification half: dst[k][j, :] = src[k][idx[j], :] for up to 16 row-major float arrays ([n_src_rows,
+ * widths[k]]) in one launch -- the row copies behind GaussianModel.densify_and_clone / densify_and_split
+ * (reached from utils/slam_backend.py:359-376), whose new rows are appended to every parameter tensor.  idx: device
+ * int64 [n_idx]; out-of-range indices leave the destination row untouched.  dst may not overlap the rows it reads.
+ */
+int lvdgs_gather_rows(int64_t n_idx, const int64_t *idx, int64_t n_src_rows, int32_t n_arrays, const float *const *src,
+                      float *const *dst, const int32_t *widths, void *stream);
+
+/*
  * Rows a15 / a16: the tail of one tracking iteration on the device.  lvdgs_pose_state is the camera's device-resident
  * block; view / proj / campos are in the layout lvdgs_rasterize_* read (pass pointers into the block), so a tracking
  * loop needs no host arithmetic between iterations.  lvdgs_pose_step = torch.optim.Adam.step on (cam_rot_delta,

@@ -427,6 +427,13 @@ int lvdgs_compact_move(int64_t n, const uint8_t *keep, const void *workspace, in
     return launch_compact_move(n, keep, workspace, n_arrays, src, dst, widths, (cudaStream_t)stream);
 }
 
+int lvdgs_gather_rows(int64_t n_idx, const int64_t *idx, int64_t n_src_rows, int32_t n_arrays, const float *const *src,
+                      float *const *dst, const int32_t *widths, void *stream) {
+    if (n_idx < 0 || n_src_rows < 0 || (n_idx > 0 && (!idx || (n_arrays > 0 && (!src || !dst || !widths))))) { set_error("gather_rows: bad arguments"); return 1; }
+    g_debug_sync = 0;
+    return launch_gather_rows(n_idx, idx, n_src_rows, n_arrays, src, dst, widths, (cudaStream_t)stream);
+}
+
 int lvdgs_pose_step(lvdgs_pose_state *state, const float *g_tau, const float *g_exposure, float lr_rot, float lr_trans,
                     float lr_exposure, double beta1, double beta2, double eps, int32_t step, float converged_threshold,
                     void *stream) {

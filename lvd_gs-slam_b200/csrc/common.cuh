@@ -241,6 +241,8 @@ int launch_compact_count(int64_t n, const uint8_t *keep, void *ws, size_t ws_byt
 int launch_compact_move(int64_t n, const uint8_t *keep, const void *ws, int n_arrays, const float *const *src,
                         float *const *dst, const int32_t *widths, cudaStream_t s);
 
+int launch_gather_rows(int64_t n_idx, const int64_t *idx, int64_t n_src_rows, int n_arrays, const float *const *src,
+                       float *const *dst, const int32_t *widths, cudaStream_t s);
 int launch_pose_step(lvdgs_pose_state *state, const float *g_tau, const float *g_exposure, float lr_rot, float lr_trans,
                      float lr_exp, double beta1, double beta2, double eps, int step, float threshold, cudaStream_t s);
 

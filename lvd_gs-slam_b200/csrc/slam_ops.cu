@@ -436,3 +436,45 @@ int launch_pose_step(lvdgs_pose_state *state, const float *g_tau, const float *g
 }
 
 }  // namespace lvdgs
+
+namespace lvdgs {
+
+// ---------------------------------------------------------------------------------------------------------
+// N1, densification half: rows idx[j] of several row-major float arrays -> row j of the destinations (dst may be the tail
+// of the same allocation as src: densify_and_clone / densify_and_split append copies of the selected Gaussians to every
+// parameter tensor, utils/slam_backend.py:359-376 via GaussianModel.densify_and_prune).  One launch for all arrays;
+// consecutive threads move consecutive floats of a destination row (coalesced stores, row-granular gathers).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_rows_kernel(int64_t n_idx, const int64_t *__restrict__ idx, int64_t n_src_rows, const CompactArrays arr) {
+    for (int k = 0; k < arr.count; ++k) {
+        const int w = arr.width[k];
+        const int64_t total = n_idx * w;
+        for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+            const int64_t r = e / w;
+            const int col = (int)(e - r * w);
+            const int64_t s = idx[r];
+            if (s >= 0 && s < n_src_rows) arr.dst[k][e] = arr.src[k][s * w + col];
+        }
+    }
+}
+
+int launch_gather_rows(int64_t n_idx, const int64_t *idx, int64_t n_src_rows, int n_arrays, const float *const *src,
+                       float *const *dst, const int32_t *widths, cudaStream_t s) {
+    if (n_arrays < 0 || n_arrays > CP_MAX_ARRAYS) { set_error("gather_rows: at most %d arrays per call", CP_MAX_ARRAYS); return 1; }
+    if (n_idx <= 0 || n_arrays == 0) return 0;
+    CompactArrays arr;
+    arr.count = n_arrays;
+    int wmax = 1;
+    for (int k = 0; k < n_arrays; ++k) {
+        if (widths[k] <= 0 || !src[k] || !dst[k]) { set_error("gather_rows: bad array %d", k); return 1; }
+        arr.src[k] = src[k]; arr.dst[k] = dst[k]; arr.width[k] = widths[k];
+        wmax = max(wmax, widths[k]);
+    }
+    const int blocks = (int)min((int64_t)148 * 8, (n_idx * wmax + 255) / 256);
+    LVDGS_PRE(s);
+    gather_rows_kernel<<<blocks, 256, 0, s>>>(n_idx, idx, n_src_rows, arr);
+    LVDGS_LAUNCHED(s, "gather_rows");
+    return 0;
+}
+
+}  // namespace lvdgs

@@ -102,7 +102,7 @@ EXPORTS = ["lvdgs_version", "lvdgs_last_error", "lvdgs_set_device", "lvdgs_launc
            "lvdgs_dist2_workspace_bytes", "lvdgs_dist2", "lvdgs_adam_step", "lvdgs_sort_workspace_bytes", "lvdgs_sort_pairs",
            "lvdgs_cub_sort_workspace_bytes", "lvdgs_cub_sort_pairs",
            "lvdgs_fused_loss_workspace_bytes", "lvdgs_fused_loss", "lvdgs_covis_counts", "lvdgs_n_obs",
-           "lvdgs_compact_workspace_bytes", "lvdgs_compact_count", "lvdgs_compact_move", "lvdgs_pose_step"]
+           "lvdgs_compact_workspace_bytes", "lvdgs_compact_count", "lvdgs_compact_move", "lvdgs_pose_step", "lvdgs_gather_rows"]
 
 
 def lib():
@@ -150,6 +150,7 @@ def lib():
     L.lvdgs_compact_workspace_bytes.restype = sz
     L.lvdgs_compact_count.argtypes = [i64, vp, vp, sz, C.POINTER(vp), vp]
     L.lvdgs_compact_move.argtypes = [i64, vp, vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp]
+    L.lvdgs_gather_rows.argtypes = [i64, vp, i64, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp]
     L.lvdgs_pose_step.argtypes = [vp, vp, vp, f, f, f, C.c_double, C.c_double, C.c_double, i32, f, vp]
     _lib = L
     return L

@@ -157,6 +157,47 @@ class ShardedMapper:
             off += n
         return P2
 
+    def densify_clone(self, index: torch.Tensor, overrides: Optional[Dict[str, torch.Tensor]] = None) -> int:
+        """Appends copies of the Gaussians `index` (int64) to the replicated block -- GaussianModel.densify_and_clone, and
+        with `overrides` = {"means3D": new positions, "scales": new scales} the append half of densify_and_split (callers
+        utils/slam_backend.py:359-376).  New rows get zero Adam moments and zero densification statistics, like
+        densification_postfix.  The rows of all groups are gathered in one launch (lvdgs_gather_rows) straight into the new
+        block.  Every rank must call it with identical arguments.  Returns the new number of Gaussians."""
+        if not self.param_flat.is_cuda:
+            raise RuntimeError("ShardedMapper.densify_clone: parameters must live on a CUDA device (no CPU path)")
+        from .slam_ops import gather_rows
+        widths = group_widths(self.M)
+        k = int(index.numel())
+        P2 = self.P + k
+        lr_of = {n: float(self.lr_flat[self.slices[n].start]) if self.P else 0.0 for n in GROUPS}
+        new_flat = torch.empty(sum(widths.values()) * P2, dtype=torch.float32, device=self.device)
+        new_m, new_v = torch.zeros_like(new_flat), torch.zeros_like(new_flat)
+        new_slices, off, tails, srcs = {}, 0, [], []
+        for name in GROUPS:
+            w = widths[name]
+            new_slices[name] = slice(off, off + w * P2)
+            old = slice(self.slices[name].start, self.slices[name].stop)
+            new_flat[off:off + w * self.P] = self.param_flat[old]
+            new_m[off:off + w * self.P] = self.exp_avg[old]
+            new_v[off:off + w * self.P] = self.exp_avg_sq[old]
+            tails.append(new_flat[off + w * self.P:off + w * P2].view(k, w))
+            srcs.append(self.param_flat[old].view(self.P, w))
+            off += w * P2
+        gather_rows(index, srcs, out=tails)
+        for name, t in (overrides or {}).items():
+            tails[GROUPS.index(name)].copy_(t.reshape(k, widths[name]))
+        pad = torch.zeros(k, dtype=torch.float32, device=self.device)
+        self.grad_norm_accum = torch.cat([self.grad_norm_accum, pad])
+        self.denom = torch.cat([self.denom, pad])
+        self.max_radii2D = torch.cat([self.max_radii2D, pad])
+        self.param_flat, self.exp_avg, self.exp_avg_sq = new_flat, new_m, new_v
+        self.lr_flat = torch.empty_like(new_flat)
+        self.P, self.slices = P2, new_slices
+        for name in GROUPS:
+            self.params[name] = self.param_flat[self.slices[name]]
+            self.lr_flat[self.slices[name]] = lr_of[name]
+        return P2
+
     # ---- one mapping iteration ----
     def step(self, n_views: int, render_and_grad: Callable[[int], None], grad_flat: torch.Tensor,
              zero: Optional[Callable[[], None]] = None, extra_views: Sequence[int] = ()):

@@ -7,6 +7,8 @@
   and utils/slam_backend.py:322-325 without temporaries or host copies.
 * `compact_rows(keep, tensors)`: the boolean-mask indexing of every parameter / Adam-moment tensor that
   GaussianModel.prune_points performs (utils/slam_backend.py:128-145,322-339), for all tensors in one launch.
+* `gather_rows(index, tensors, out)`: the row copies of densify_and_clone / densify_and_split (utils/slam_backend.py:359-376),
+  for all tensors in one launch, written where the caller wants them (e.g. the tail of a larger buffer).
 
 CUDA only: there is no CPU path (a CPU tensor raises).
 """
@@ -222,4 +224,37 @@ def compact_rows(keep, tensors, out=None):
         dp = (C.c_void_p * m)(*[dsts[i].data_ptr() for i in chunk])
         wd = (C.c_int32 * m)(*[max(1, srcs[i][0].numel()) if n else 1 for i in chunk])
         _native.check(L.lvdgs_compact_move(n, _native.ptr(k8), _native.ptr(ws), m, sp, dp, wd, stream), "lvdgs_compact_move")
+    return dsts
+
+
+# ---- densify ----
+def gather_rows(index, tensors, out=None):
+    """out[k][j] = tensors[k][index[j]] for every tensor (each [n, ...], float32), one launch per 16 tensors -- what
+    `t[index]` gives for each.  `out`: optional destinations with at least len(index) rows (e.g. views of the tail of a
+    preallocated parameter buffer); returns the list of filled [len(index), ...] tensors."""
+    _need_cuda(index, "gather_rows")
+    L = _native.lib()
+    dev = index.device
+    idx = index.contiguous().to(torch.int64)
+    m = idx.numel()
+    srcs = [_f32(t) for t in tensors]
+    n = srcs[0].shape[0] if srcs else 0
+    if any(t.shape[0] != n for t in srcs):
+        raise ValueError("gather_rows: every tensor needs the same number of rows")
+    dsts = []
+    for i, t in enumerate(srcs):
+        d = out[i][:m] if out is not None else torch.empty((m,) + tuple(t.shape[1:]), dtype=torch.float32, device=dev)
+        if d.shape[0] < m or not d.is_contiguous():
+            raise ValueError("gather_rows: destination too small or not contiguous")
+        dsts.append(d)
+    if m == 0 or n == 0:
+        return dsts
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for lo in range(0, len(srcs), 16):
+        chunk = list(range(lo, min(lo + 16, len(srcs))))
+        k = len(chunk)
+        sp = (C.c_void_p * k)(*[srcs[i].data_ptr() for i in chunk])
+        dp = (C.c_void_p * k)(*[dsts[i].data_ptr() for i in chunk])
+        wd = (C.c_int32 * k)(*[max(1, srcs[i][0].numel()) for i in chunk])
+        _native.check(L.lvdgs_gather_rows(m, _native.ptr(idx), n, k, sp, dp, wd, stream), "lvdgs_gather_rows")
     return dsts

@@ -159,3 +159,34 @@ def test_mapper_prune_keeps_replica_state_consistent():
     assert torch.equal(m.exp_avg[m.slices["rotations"]].view(P2, 4), avg_before[keep])
     assert torch.equal(m.denom, denom_before[keep])
     m.adam_step(torch.ones_like(m.param_flat))          # the fused optimiser runs on the pruned block
+
+
+def test_gather_rows_and_mapper_densify():
+    """densify_and_clone / densify_and_split's row copies (utils/slam_backend.py:359-376): exact against t[index]."""
+    from lvdgs import slam_ops
+    from lvdgs.mapping import ShardedMapper, GROUPS
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    n = 10_000
+    tensors = [torch.randn(n, w, generator=g).to(dev) for w in (3, 3, 1, 3, 4)] + [torch.randn(n, 16, 3, generator=g).to(dev)]
+    for m in (0, 1, 777, 25_000):
+        idx = torch.randint(0, n, (m,), generator=g).to(dev)
+        for t, o in zip(tensors, slam_ops.gather_rows(idx, tensors)):
+            assert torch.equal(o, t[idx])
+    P = 4000
+    mp = ShardedMapper(P, sh_coeffs=1, device=dev)
+    mp.param_flat.copy_(torch.randn(mp.param_flat.numel(), generator=g))
+    mp.exp_avg.copy_(torch.randn(mp.param_flat.numel(), generator=g))
+    before = {k: mp.view(k).clone() for k in GROUPS}
+    avg_before = mp.exp_avg[mp.slices["scales"]].view(P, 3).clone()
+    idx = torch.randint(0, P, (900,), generator=g).to(dev)
+    new_means = torch.randn(900, 3, generator=g).to(dev)
+    P2 = mp.densify_clone(idx, overrides={"means3D": new_means})
+    assert P2 == P + 900 and mp.param_flat.numel() == 14 * P2 and mp.denom.numel() == P2
+    for k in GROUPS:
+        v = mp.view(k)
+        assert torch.equal(v[:P], before[k])
+        assert torch.equal(v[P:], new_means if k == "means3D" else before[k][idx])
+    assert torch.equal(mp.exp_avg[mp.slices["scales"]].view(P2, 3)[:P], avg_before)
+    assert float(mp.exp_avg[mp.slices["scales"]].view(P2, 3)[P:].abs().max()) == 0.0
+    mp.adam_step(torch.ones_like(mp.param_flat))
