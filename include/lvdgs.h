@@ -73,7 +73,9 @@ typedef struct lvdgs_geom_layout {
     size_t tiles_touched;  /* uint32 [P] */
     size_t point_offsets;  /* uint32 [P]    inclusive scan of tiles_touched (written by the key emission) */
     size_t clamped;        /* uint8  [P]    bit c set: channel c clamped at 0 */
-    size_t scan_state;     /* uint32 [ceil(P/256)] instances per preprocess block (-> exclusive offsets) + the R word */
+    size_t scan_state;     /* uint32 [ceil(P/256)] instances per preprocess block (-> exclusive offsets), then 256 bytes of
+                              counters: [0] R, [1] longest tile list, [2] number of visible Gaussians */
+    size_t visible_list;   /* uint32 [P]    indices of the Gaussians with tiles_touched > 0, [0, counters[2]) valid */
     size_t total;
 } lvdgs_geom_layout;
 

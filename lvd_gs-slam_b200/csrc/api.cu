@@ -57,7 +57,8 @@ static void geom_layout(int32_t P, lvdgs_geom_layout &l) {
     l.tiles_touched = o; o += align_up(n * sizeof(uint32_t));
     l.point_offsets = o; o += align_up(n * sizeof(uint32_t));
     l.clamped = o; o += align_up(n * sizeof(uint8_t));
-    l.scan_state = o; o += align_up(((n + 255) / 256) * sizeof(uint32_t)) + 256;   // block sums + R word
+    l.scan_state = o; o += align_up(((n + 255) / 256) * sizeof(uint32_t)) + 256;   // block sums + counters
+    l.visible_list = o; o += align_up(n * sizeof(uint32_t));
     l.total = o;
 }
 static void binning_layout(int64_t R, lvdgs_binning_layout &l) {
@@ -93,7 +94,8 @@ static GeomPtrs geom_ptrs(void *base, int32_t P) {
     g.rect = (short4 *)(b + l.rect); g.tiles_touched = (uint32_t *)(b + l.tiles_touched);
     g.point_offsets = (uint32_t *)(b + l.point_offsets); g.clamped = (uint8_t *)(b + l.clamped);
     g.block_sums = (uint32_t *)(b + l.scan_state);
-    g.num_instances = (uint32_t *)(b + l.total - 256);
+    g.num_instances = (uint32_t *)(b + l.visible_list - 256);
+    g.visible_list = (uint32_t *)(b + l.visible_list);
     return g;
 }
 static BinPtrs bin_ptrs(void *base, int64_t R) {
@@ -196,14 +198,16 @@ static int launch_bin_and_blend(const lvdgs_raster_params &p, const GeomPtrs &g,
     const uint32_t *R_dev = g.num_instances;
     LVDGS_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * (size_t)p.P, s));
     int sel = 0;
+    // a re-run after a failed speculative launch: the emission counts the visible list (and claims tile slots) again
+    if (rerun) LVDGS_CHECK(cudaMemsetAsync(g.num_instances + 2, 0, sizeof(uint32_t), s));
     if (p.flags & LVDGS_FLAG_GLOBAL_SORT) {
         if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], b.vals[0], nullptr, nullptr, s)) return 1;
         const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
         if (launch_sort_pairs(capacity, R_dev, b.keys[0], b.keys[1], b.vals[0], b.vals[1], end_bit, b.sort_ws,
                               sort_workspace_bytes(capacity), im.sort_hist, &sel, s)) return 1;
     } else {
-        // instances go straight into their tile's segment of keys[0]; one CTA per tile sorts it into keys[1] / vals[1]
-        // the cursors were zeroed together with the tile grid; a re-run after a failed speculative launch resets them
+        // instances go straight into their tile's segment of keys[0]; one CTA per tile sorts it into keys[1] / vals[1].
+        // The cursors were zeroed together with the tile grid
         if (rerun) LVDGS_CHECK(cudaMemsetAsync(im.tile_cursor, 0, sizeof(uint32_t) * CURSOR_STRIDE * (size_t)gx * gy, s));
         if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], nullptr, im.tile_cursor, im.ranges, s)) return 1;
         if (launch_tile_sort(gx * gy, capacity, R_dev, im.ranges, im.tile_order, b.keys[0], b.keys[1], b.vals[1], long_lists, s)) return 1;

@@ -154,7 +154,9 @@ struct GeomPtrs {
     float *depths; float4 *means2D; float4 *conic_opacity; float4 *rgbd; short4 *rect;
     uint32_t *tiles_touched; uint32_t *point_offsets; uint8_t *clamped;
     uint32_t *block_sums;             // [ceil(P/256)] instances per preprocess block -> exclusive offsets (binning_prep)
-    uint32_t *num_instances;          // R, written by binning_prep
+    uint32_t *num_instances;          // [0] R, [1] longest tile list (binning_prep), [2] visible Gaussians (key emission)
+    uint32_t *visible_list;           // [P] indices of the Gaussians with tiles_touched > 0 (written by the key emission, in
+                                      // block order): the preprocess backward of the accumulate / pose-only modes walks it
 };
 struct BinPtrs {
     uint64_t *keys[2]; uint32_t *vals[2]; void *sort_ws; int32_t *sorted_sel;
@@ -221,7 +223,7 @@ int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3
                                const BlendGradPtrs &bgp, bool colors_are_precomp, float *dL_dmeans2D,
                                float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D, float *dL_dcov3D,
                                float *dL_dsh, float *dL_dscales, float *dL_drots, float *dL_dtau,
-                               float *dL_dtau_sum, cudaStream_t s);
+                               float *dL_dtau_sum, cudaStream_t s);     // uses g.visible_list when no output needs the culled rows
 
 int launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t s);
 

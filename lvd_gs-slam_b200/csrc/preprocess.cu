@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
         uint32_t run = 0;
         for (int b = 0; b < WORK_BUCKETS; ++b) { const uint32_t n = s_bucket[b]; s_bucket[b] = run; run += n; }
         R_out[1] = s_longest;            // longest tile list (0 if below 1024), read back together with R
+        R_out[2] = 0u;                   // visible-Gaussian counter of the key emission that follows
     }
     __syncthreads();
     for (int t = tid; t < tiles; t += PREP_THREADS) {
@@ -517,8 +518,11 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
                                                                  const short4 *__restrict__ rects,
                                                                  const float *__restrict__ depths,
                                                                  uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                                                                 uint32_t *__restrict__ tile_cursor, const uint2 *__restrict__ ranges) {
+                                                                 uint32_t *__restrict__ tile_cursor, const uint2 *__restrict__ ranges,
+                                                                 uint32_t *__restrict__ visible_list, uint32_t *__restrict__ num_visible) {
     __shared__ uint32_t s_end[EMIT_THREADS];      // inclusive offsets of this block's Gaussians
+    __shared__ uint32_t s_vcnt[EMIT_THREADS / 32];
+    __shared__ uint32_t s_vbase;
     __shared__ short4 s_rect[EMIT_THREADS];
     __shared__ uint32_t s_depth[EMIT_THREADS];
     __shared__ uint32_t s_wsum[EMIT_THREADS / 32];
@@ -528,13 +532,24 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
     // K2, second half: inclusive scan of this block's tile counts
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t incl = i < P ? tiles_touched[i] : 0u;
+    // the visible Gaussians (at least one tile) are also listed compactly for the preprocess backward: ranks inside the
+    // block by ballot, the block's base by one atomic (block order is arbitrary, the backward does not care)
+    const uint32_t vis_ballot = __ballot_sync(0xffffffffu, incl != 0u);
+    const bool is_vis = incl != 0u;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += n;
     }
     if (lane == 31) s_wsum[warp] = incl;
+    if (lane == 0) s_vcnt[warp] = __popc(vis_ballot);
     __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int k = 0; k < EMIT_THREADS / 32; ++k) { const uint32_t c = s_vcnt[k]; s_vcnt[k] = t; t += c; }
+        s_vbase = t ? atomicAdd(num_visible, t) : 0u;
+    }
     uint32_t wbase = 0;
 #pragma unroll
     for (int k = 0; k < EMIT_THREADS / 32; ++k) wbase += k < warp ? s_wsum[k] : 0u;
@@ -548,6 +563,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
         s_end[threadIdx.x] = 0xffffffffu;
     }
     __syncthreads();
+    if (is_vis) visible_list[s_vbase + s_vcnt[warp] + __popc(vis_ballot & ((1u << lane) - 1u))] = (uint32_t)i;
     const int last = min(EMIT_THREADS, P - g0) - 1;
     const uint32_t span_end = BUCKET ? s_end[last] : min(s_end[last], capacity);      // never write past the arena the launch was sized for
     for (uint32_t r = span_begin + threadIdx.x; r < span_end; r += EMIT_THREADS) {
@@ -580,9 +596,9 @@ int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, int64_t capacity, u
     const uint32_t cap = (uint32_t)min(capacity, (int64_t)0xffffffffll);
     LVDGS_PRE(s);
     if (tile_cursor)
-        emit_keys_kernel<true><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, tile_cursor, ranges);
+        emit_keys_kernel<true><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, tile_cursor, ranges, g.visible_list, g.num_instances + 2);
     else
-        emit_keys_kernel<false><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, nullptr, nullptr);
+        emit_keys_kernel<false><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, nullptr, nullptr, g.visible_list, g.num_instances + 2);
     LVDGS_LAUNCHED(s, "emit_keys");
     return 0;
 }

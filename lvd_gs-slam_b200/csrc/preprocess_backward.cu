@@ -34,6 +34,10 @@ struct PbArgs {
     const float *acc;
     float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drots,
         *dL_dtau, *dL_dtau_sum;
+    // compact mode (accumulate / pose-only, no per-Gaussian tau): thread j handles Gaussian visible_list[j], j < *num_visible.
+    // Only ~40-60 % of a map is in view, so the kernel runs that fraction of the warps, all lanes live; culled rows are
+    // never touched (accumulate mode leaves them as they are; dL_dmeans2D is zeroed by the launcher)
+    const uint32_t *visible_list, *num_visible;
 };
 
 __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
@@ -55,8 +59,13 @@ __global__ void __launch_bounds__(PB_THREADS, LVDGS_PB_MINBLOCKS) preprocess_bac
     else if (threadIdx.x < 32) cam.proj[threadIdx.x - 16] = __ldg(a.proj + threadIdx.x - 16);
     else if (threadIdx.x < 35) cam.campos[threadIdx.x - 32] = __ldg(a.campos + threadIdx.x - 32);
     else if (threadIdx.x >= 64 && threadIdx.x < 80) s_praw[threadIdx.x - 64] = __ldg(a.proj_raw + threadIdx.x - 64);
+    int i = blockIdx.x * PB_THREADS + threadIdx.x;
+    if (a.visible_list) {
+        const uint32_t nv = __ldg(a.num_visible);
+        if ((uint32_t)(blockIdx.x * PB_THREADS) >= nv) return;               // block-uniform
+        i = (uint32_t)i < nv ? (int)__ldg(a.visible_list + i) : a.P;          // a.P: out of range, the lane idles
+    }
     __syncthreads();
-    const int i = blockIdx.x * PB_THREADS + threadIdx.x;
     const float *V = cam.view, *Pj = cam.proj;
 
     float dmean[3] = {0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, tau[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -366,6 +375,11 @@ int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3
     a.dL_dcov3D = dL_dcov3D; a.dL_dsh = colors_are_precomp ? nullptr : dL_dsh; a.dL_dscales = dL_dscales;
     a.dL_drots = dL_drots; a.dL_dtau = dL_dtau; a.dL_dtau_sum = dL_dtau_sum;
     if (dL_dtau_sum) LVDGS_CHECK(cudaMemsetAsync(dL_dtau_sum, 0, 6 * sizeof(float), s));
+    // the culled rows matter only when something dense is written for them: parameter gradients in store mode, dL_dtau
+    const bool compact = ((p.flags & LVDGS_FLAG_ACCUMULATE) || (p.flags & LVDGS_FLAG_POSE_ONLY)) && !dL_dtau;
+    a.visible_list = compact ? g.visible_list : nullptr;
+    a.num_visible = g.num_instances + 2;
+    if (compact && dL_dmeans2D) LVDGS_CHECK(cudaMemsetAsync(dL_dmeans2D, 0, 3 * sizeof(float) * (size_t)p.P, s));
     LVDGS_PRE(s);
     preprocess_backward_kernel<<<ceil_div(p.P, PB_THREADS), PB_THREADS, 0, s>>>(a);
     LVDGS_LAUNCHED(s, "preprocess_backward");

@@ -81,7 +81,7 @@ class RasterParams(C.Structure):
 
 class GeomLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("depths", "means2D", "conic_opacity", "rgbd", "rect", "tiles_touched",
-                                          "point_offsets", "clamped", "scan_state", "total")]
+                                          "point_offsets", "clamped", "scan_state", "visible_list", "total")]
 
 
 class BinningLayout(C.Structure):

@@ -135,7 +135,7 @@ class RasterEngine:
 
     def backward(self, vc, means3D, opacities, scales, rotations, shs, dL_dcolor, dL_ddepth=None,
                  dL_dopacity=None, accumulate=True, slot: int = 0, stream=None, pose_only: bool = False):
-        """pose_only (tracking): only slot.g_tau (and slot.g_means2D) are produced, no parameter gradients."""
+        """pose_only (tracking): only slot.g_tau is produced, no parameter gradients and no screen-space gradients."""
         sl = self.slots[slot]
         flags = self.flags | (FLAG_ACCUMULATE if accumulate and not pose_only else 0) | (FLAG_POSE_ONLY if pose_only else 0)
         prm = self._params(vc, flags)
@@ -144,7 +144,7 @@ class RasterEngine:
             C.byref(prm), ptr(vc.bg), ptr(means3D), ptr(sl.radii), None, ptr(opacities), ptr(scales), ptr(rotations),
             None, ptr(vc.view), ptr(vc.proj), ptr(vc.proj_raw), ptr(dL_dcolor), ptr(dL_ddepth), ptr(dL_dopacity), ptr(shs),
             ptr(vc.campos), ptr(sl.arena[0]), C.c_int64(sl.R), C.c_int64(sl.capacity), ptr(sl.arena[1]),
-            ptr(sl.arena[2]), ptr(sl.scratch), C.c_size_t(sl.scratch.numel()), ptr(sl.g_means2D), None, ptr(g["opacity"]),
+            ptr(sl.arena[2]), ptr(sl.scratch), C.c_size_t(sl.scratch.numel()), None if pose_only else ptr(sl.g_means2D), None, ptr(g["opacity"]),
             ptr(g["means3D"]), None, ptr(g["shs"]), ptr(g["scales"]), ptr(g["rotations"]), None,
             ptr(sl.g_tau), self._stream(stream))
         _native.check(rc, "lvdgs_rasterize_backward")

@@ -21,10 +21,11 @@ def test_pipelined_views_match_sequential_plugin():
     gds = [rng.normal(0, 1, (1, H, W)).astype(np.float32) for _ in cams]
     # reference: plugin surface, one view at a time, gradients summed in float64
     ref = {k: 0.0 for k in ("means3D", "opacities", "scales", "rotations", "shs")}
-    outs = []
+    outs, per_view = [], []
     for cam, gc, gd in zip(cams, gcs, gds):
         out, _, g = run_cuda(sc, cam, np.zeros(3, np.float32), grads=(gc, gd, None), debug=False)
         outs.append(out)
+        per_view.append((g["means2D"], np.concatenate([g["rho"].reshape(-1), g["theta"].reshape(-1)])))
         for k in ref:
             ref[k] = ref[k] + g[k].astype(np.float64)
     t = lambda a: torch.tensor(a, device=dev)
@@ -48,6 +49,12 @@ def test_pipelined_views_match_sequential_plugin():
         assert rel_err(got["scales"].reshape(P, 3), ref["scales"]) < 1e-4
         assert rel_err(got["rotations"].reshape(P, 4), ref["rotations"]) < 1e-4
         assert rel_err(got["shs"].reshape(P, 1, 3), ref["shs"]) < 1e-4
+        # per-view outputs of the last view of slot 0 (view 4): the backward walks the visible list only, the rows of
+        # culled Gaussians must still read as zero
+        assert rel_err(eng.slots[0].g_means2D.cpu().numpy(), per_view[4][0]) < 1e-4
+        assert rel_err(eng.slots[0].g_tau.cpu().numpy(), per_view[4][1]) < 1e-4
+        culled = outs[4]["radii"] == 0
+        assert culled.any() and float(eng.slots[0].g_means2D[torch.tensor(culled, device=dev)].abs().max()) == 0.0
         for k, out in enumerate(outs):
             np.testing.assert_array_equal(seen[k][0].cpu().numpy(), out["color"])
             np.testing.assert_array_equal(seen[k][1].cpu().numpy(), out["radii"])
