@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) fused_loss_kernel(const LossArgs
     }
 }
 
-constexpr int LOSS_MAX_BLOCKS = 1184;    // 8 per SM: the pass is latency-bound, more warps in flight (14.7 -> ? us measured at 296)
+constexpr int LOSS_MAX_BLOCKS = 592;     // 4 per SM (296 and 1184 measured the same: the pass is short, its tail is the ticket + final sum)
 size_t fused_loss_workspace_bytes() { return align_up(LOSS_MAX_BLOCKS * 4 * sizeof(float)) + 256; }
 
 int launch_fused_loss(int W, int H, const float *color, const float *depth, const float *opacity, const float *gt_color,
