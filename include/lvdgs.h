@@ -40,6 +40,9 @@ extern "C" {
                                       sorted keys / point list are bit-identical either way.  Must be the same in the
                                       forward and its backward. */
 
+#define LVDGS_FLAG_ZEROED_OUTPUTS 32 /* backward: the caller has zero-filled every gradient output; rows of culled Gaussians are
+                                      then left alone and the backward walks only the visible Gaussians */
+
 /* which buffer a resize callback is asked for */
 #define LVDGS_BUF_GEOM 0
 #define LVDGS_BUF_BINNING 1

@@ -34,7 +34,7 @@ struct PbArgs {
     const float *acc;
     float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drots,
         *dL_dtau, *dL_dtau_sum;
-    // compact mode (accumulate / pose-only, no per-Gaussian tau): thread j handles Gaussian visible_list[j], j < *num_visible.
+    // compact mode (accumulate / pose-only / pre-zeroed outputs, no per-Gaussian tau): thread j handles Gaussian visible_list[j], j < *num_visible.
     // Only ~40-60 % of a map is in view, so the kernel runs that fraction of the warps, all lanes live; culled rows are
     // never touched (accumulate mode leaves them as they are; dL_dmeans2D is zeroed by the launcher)
     const uint32_t *visible_list, *num_visible;
@@ -376,10 +376,11 @@ int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3
     a.dL_drots = dL_drots; a.dL_dtau = dL_dtau; a.dL_dtau_sum = dL_dtau_sum;
     if (dL_dtau_sum) LVDGS_CHECK(cudaMemsetAsync(dL_dtau_sum, 0, 6 * sizeof(float), s));
     // the culled rows matter only when something dense is written for them: parameter gradients in store mode, dL_dtau
-    const bool compact = ((p.flags & LVDGS_FLAG_ACCUMULATE) || (p.flags & LVDGS_FLAG_POSE_ONLY)) && !dL_dtau;
+    const bool zeroed = (p.flags & LVDGS_FLAG_ZEROED_OUTPUTS) != 0;
+    const bool compact = ((p.flags & LVDGS_FLAG_ACCUMULATE) || (p.flags & LVDGS_FLAG_POSE_ONLY) || zeroed) && !dL_dtau;
     a.visible_list = compact ? g.visible_list : nullptr;
     a.num_visible = g.num_instances + 2;
-    if (compact && dL_dmeans2D) LVDGS_CHECK(cudaMemsetAsync(dL_dmeans2D, 0, 3 * sizeof(float) * (size_t)p.P, s));
+    if (compact && dL_dmeans2D && !zeroed) LVDGS_CHECK(cudaMemsetAsync(dL_dmeans2D, 0, 3 * sizeof(float) * (size_t)p.P, s));
     LVDGS_PRE(s);
     preprocess_backward_kernel<<<ceil_div(p.P, PB_THREADS), PB_THREADS, 0, s>>>(a);
     LVDGS_LAUNCHED(s, "preprocess_backward");
