@@ -92,7 +92,8 @@ class RasterEngine:
         for name, k in sizes:
             self.grads[name] = self.grad_flat[off:off + k * P]
             off += k * P
-        self.s_fwd = torch.cuda.Stream(self.dev, priority=-1)     # short latency-bound kernels get SM slots first
+        import os
+        self.s_fwd = torch.cuda.Stream(self.dev, priority=int(os.environ.get("LVDGS_FWD_PRIORITY", "-1")))   # short latency-bound kernels get SM slots first
         self.s_bwd = torch.cuda.Stream(self.dev)
         if self.dev.index is not None:
             self.L.lvdgs_set_device(self.dev.index)
