@@ -102,3 +102,40 @@ def test_slam_ops_reject_cpu_tensors():
         slam_ops.compact_rows(torch.ones(8, dtype=torch.bool), [torch.zeros(8, 3)])
     with pytest.raises(RuntimeError, match="no CPU path"):
         ShardedMapper(8, device="cpu").prune(torch.ones(8, dtype=torch.bool))
+
+
+def _header():
+    return open(os.path.join(ROOT, "include", "lvdgs.h")).read()
+
+
+def test_ctypes_prototypes_have_the_headers_arity():
+    """Every bound function takes as many arguments as include/lvdgs.h declares (a silent mismatch would corrupt the
+    call frame instead of raising)."""
+    L = _native.lib()
+    text = re.sub(r"/\*.*?\*/", "", _header(), flags=re.S)
+    protos = dict(re.findall(r"\b(lvdgs_\w+)\s*\(([^;{]*?)\)\s*;", text))
+    assert set(_native.EXPORTS) <= set(protos)
+    for name in _native.EXPORTS:
+        params = protos[name].strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        fn = getattr(L, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
+
+
+def test_pose_state_offsets_match_the_header():
+    """lvdgs.tracking addresses fields of lvdgs_pose_state by float offset."""
+    from lvdgs import tracking as trk
+    text = re.sub(r"/\*.*?\*/", "", _header(), flags=re.S)
+    body = re.search(r"typedef struct lvdgs_pose_state \{(.*?)\} lvdgs_pose_state;", text, re.S).group(1)
+    off, offsets = 0, {}
+    for typ, name, dim in re.findall(r"(float|int32_t)\s+(\w+)(?:\[(\d+)\])?\s*;", body):
+        offsets[name] = off
+        off += int(dim) if dim else 1
+    want = dict(view=trk._VIEW, proj=trk._PROJ, proj_raw=trk._PRAW, campos=trk._CAMPOS, R=trk._R, T=trk._T,
+                exposure=trk._EXPO, adam_m=trk._M, adam_v=trk._V, step=trk._STEP, converged=trk._CONV, tau_norm=trk._TAUN)
+    for k, v in want.items():
+        assert offsets[k] == v, (k, offsets[k], v)
+    assert off == trk._SIZE
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        trk.PoseTracker(8, 32, 32, 1.0, 1.0, device="cpu")
