@@ -46,6 +46,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if nvcc is None:
         raise RuntimeError("liblvdgs.so is missing/stale and nvcc was not found; there is no CPU fallback")
     os.makedirs(BUILD_DIR, exist_ok=True)
+    # one builder at a time (torchrun starts one process per GPU against the same tree); the others wait, then find
+    # the library fresh
+    import fcntl
+    lock = open(os.path.join(BUILD_DIR, ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not _stale():
+            return SO_PATH
+        return _build_locked(nvcc, force, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc, force, verbose):
     hdrs = [os.path.join(SRC_DIR, f) for f in os.listdir(SRC_DIR) if f.endswith((".cuh", ".h"))] + \
            [os.path.join(os.path.dirname(PKG_DIR), "include", "lvdgs.h")]
     hdr_t = max(os.path.getmtime(h) for h in hdrs)
