@@ -25,7 +25,9 @@ _ws = {}
 
 
 def _workspace(dev, nbytes):
-    key = (dev.index, "ws")
+    # one workspace per (device, stream): the loss kernel keeps per-block partials and a ticket in it, so two launches
+    # that may run concurrently must not share one
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     buf = _ws.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.zeros(int(nbytes), dtype=torch.uint8, device=dev)      # zeroed: holds the loss kernel's ticket
