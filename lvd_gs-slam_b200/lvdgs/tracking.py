@@ -76,7 +76,7 @@ class PoseTracker:
         st[_CAMPOS:_CAMPOS + 3] = -R.T @ T
         st[_R:_R + 9] = R.reshape(-1)
         st[_T:_T + 3] = T
-        st[_EXPO], st[_EXPO + 1] = exposure_a, exposure_b
+        st[_EXPO], st[_EXPO + 1] = float(exposure_a), float(exposure_b)      # python floats or 1-element tensors (Camera.exposure_a/b)
         self.state.copy_(torch.from_numpy(st))
 
     @property
