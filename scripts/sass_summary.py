@@ -24,7 +24,7 @@ for f in sorted(os.listdir(SRC)):
         m = re.match(r"\s+Function : (\S+)", line)
         if m:
             cur = m.group(1); mix[cur] = collections.Counter(); continue
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", line)
+        m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", line)
         if m and cur:
             mix[cur][m.group(1)] += 1
     for fn, c in mix.items():
