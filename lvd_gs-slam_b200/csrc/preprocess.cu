@@ -1,5 +1,6 @@
-// preprocess.cu -- K1 preprocess forward (with the K2 tile-count scan fused in), binning_prep (K5 tile ranges + sort
-// histograms from per-tile counts), K3 key emission, K10 markVisible.
+// preprocess.cu -- K1 preprocess forward (with the first half of the K2 tile-count scan fused in), binning_count /
+// binning_prep (K2 + K5: per-tile counts -> tile ranges, key offsets, R; digit histograms for the onesweep path),
+// K3 key emission (into per-tile segments, or in emission order for the onesweep path), K10 markVisible.
 //
 // Behaviour follows SURVEY.md Appendix A.1 / A.2 (the reference's `preprocessCUDA`, `duplicateWithKeys`,
 // `identifyTileRanges`, `checkFrustum`, reached from utils/slam_frontend.py:1493 and utils/slam_backend.py:184
@@ -7,9 +8,10 @@
 //  * the [P,3] AoS inputs are staged through shared memory with fully coalesced loads, quaternions are
 //    one 128-bit load, all intermediate state is SoA with 8/16-byte vector stores;
 //  * every operation on the chain to an integer output is an explicit IEEE intrinsic (canonical arithmetic);
-//  * key emission is block-cooperative: a block owns 256 consecutive Gaussians, and its threads write the
-//    block's contiguous span of (key,value) instances with coalesced stores (binary search in shared memory)
-//    instead of one thread looping over its own tile rectangle.
+//  * key emission is block-cooperative: a block owns 256 consecutive Gaussians, and its threads walk the block's
+//    contiguous span of instances (binary search in shared memory) instead of one thread looping over its own tile
+//    rectangle; an instance either claims a slot of its tile's segment (tile_sort.cu) or, for the global onesweep
+//    sort, is stored at its emission position with coalesced stores.
 #include "common.cuh"
 
 namespace lvdgs {
@@ -300,16 +302,15 @@ int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// binning_prep: one CTA.  Integrates the 2-D difference array into per-tile instance counts, turns them into the
-// tile ranges (K5 -- no pass over the sorted keys is needed: range(t) = [sum of counts before t, + count(t))),
-// derives the histograms of the key digits that hold the tile id, and exclusive-scans all digit histograms for the
-// onesweep passes (replaces the sort's own histogram kernel: the keys are never read for counting).
-// ---------------------------------------------------------------------------------------------------------
-// ---------------------------------------------------------------------------------------------------------
-// binning_count: per-tile instance counts and the histograms of the four depth digits of the sort keys, WITHOUT
-// touching the instances: every visible Gaussian contributes its tile rect as a 2-D difference (4 corner updates
-// instead of one update per covered tile) and `tiles_touched` to the bin of each depth byte.  A few large CTAs with
-// shared-memory-privatised tables, flushed once, so global atomics are ~1 per table cell per CTA.
+// binning_count: per-tile instance counts (and, for the onesweep path only, the histograms of the four depth digits
+// of the sort keys) WITHOUT touching the instances: every visible Gaussian contributes its tile rect as a 2-D
+// difference (4 corner updates instead of one update per covered tile) and `tiles_touched` to the bin of each depth
+// byte.  A few large CTAs with shared-memory-privatised tables, flushed once, so global atomics are ~1 per table
+// cell per CTA.
+// binning_prep (below): one CTA.  Scans the preprocess blocks' instance counts (-> per-block key offsets, R),
+// integrates the difference array into per-tile instance counts, turns them into the tile ranges (K5 -- no pass over
+// the sorted keys is needed: range(t) = [sum of counts before t, + count(t))), records the longest list, orders the
+// tiles by decreasing list length, and -- onesweep path -- derives and exclusive-scans the digit histograms.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int COUNT_THREADS = 1024;
 constexpr int PREP_GRID_SMEM = 10240;     // difference-array cells kept in shared memory (covers 1920x1080: 121 x 69)
