@@ -36,6 +36,8 @@ if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "fwd+bwd render Mpix/s at 1241x376, 500k Gaussians"
+CPU_BASELINE_DETAIL = ("C/OpenMP restatement of the reference's algorithm (oracle/raster_oracle.c), not the pure-torch "
+                       "transcription BASELINE.md mentions -- a stronger baseline; the reference's own CUDA sources are absent")
 WORKLOADS = {"kitti_window8_500k": dict(N=500_000, cam="kitti", views=8),
              "kitti_window8_1m": dict(N=1_000_000, cam="kitti", views=8)}
 
@@ -108,14 +110,31 @@ def cpu_oracle_view(sc, cam, gc, gd):
     return time.perf_counter() - t0
 
 
+def bench_config(args, wl, W, H, world, views_per_rank):
+    """`config` of the JSON line -- the SAME keys and values in both arms (the driver compares them)."""
+    return {"workload": args.workload, "gaussians": wl["N"], "image": [W, H], "views_per_step": wl["views"], "sh_degree": 0,
+            "l2": "inputs larger than L2: each view streams its own sorted instance list, and the 8 views of a step "
+                  "rewrite >300 MB of binning state between revisits"}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, wl):
     """Reference arm: the reference's algorithm on the host cores (oracle port; the reference's own CUDA build is
-    impossible here -- its sources are absent), same metric/config, one view of the window per step."""
+    impossible here -- its sources are absent), same metric/config; each step is a bounded sample of the workload: one
+    view of the 8-view window (fwd+bwd, full resolution), Mpix/s normalises."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
     from lvdgs import synth
+    oracle.build()
+    cores = oracle.set_num_threads(host_cores())            # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
     cams = [synth.make_camera(wl["cam"], k) for k in range(wl["views"])]
     sc = synth.make_scene(wl["N"], cams[0], seed=0)
     gc, gd = synth.make_upstream_grads(cams[0])
@@ -127,17 +146,37 @@ def run_reference(args, wl):
         t += cpu_oracle_view(sc, cams[i % len(cams)], gc, gd)
     ms = 1e3 * t / max(args.steps, 1)
     val = H * W / (ms * 1e-3) / 1e6
-    cores = oracle.num_threads()
+    sample = "one keyframe view (fwd+bwd, full 1241x376) of the 8-view window per step, OpenMP over tiles / Gaussians"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "gaussians": wl["N"], "image": [W, H],
-                       "sample": "one keyframe view (fwd+bwd) of the 8-view window per step"},
-            "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                             "sample": "one full 1241x376 view, fwd+bwd, per step (OpenMP over tiles / Gaussians)"},
+            "config": bench_config(args, wl, W, H, 1, 1),
+            "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample,
+                             "detail": CPU_BASELINE_DETAIL},
             "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def measure_fp32_peak(L, dev, n_sm):
+    """Measured FP32 FMA-pipe peak: one launch of n_sm x 8 blocks x 256 threads x 4096 x 16 independent FMAs, scalar and
+    packed, best of 5, CUDA events on the launching stream."""
+    import ctypes as C
+    import torch
+    out = torch.zeros(4, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    res = {}
+    for packed, key in ((0, "ffma_tflops"), (1, "ffma2_tflops")):
+        best = 0.0
+        for _ in range(6):
+            fmas = C.c_double(0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.lvdgs_fp32_peak(n_sm * 8, 4096, packed, C.c_void_p(out.data_ptr()), C.byref(fmas), stream)
+            e1.record(); e1.synchronize()
+            best = max(best, 2.0 * fmas.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        res[key] = best
+    return res
 
 
 def main():
@@ -167,33 +206,67 @@ def main():
     sc = synth.make_scene(wl["N"], cams[0], seed=0)            # identical replicated map on every rank
     H, W = cams[0].image_height, cams[0].image_width
     t = lambda a: torch.tensor(a, dtype=torch.float32, device=dev).contiguous()
-    # the replicated map lives in ONE flat parameter block (lvdgs.mapping.ShardedMapper) updated by the fused Adam kernel;
-    # learning rates are scaled down 1e-4 so that the synthetic workload stays stationary over the timed steps
+    # the replicated map lives in ONE flat block of RAW parameters (lvdgs.mapping.ShardedMapper: logit opacity, log scale,
+    # un-normalised rotations, like the reference's GaussianModel) updated by the fused Adam kernel.  The learning rates
+    # are scaled down 1e-4 only because the upstream gradients of this workload are fixed random images: at the real rates
+    # 25 steps of Adam along them would random-walk the map and the timed steps would not see the same workload
+    # (tests/test_gpu_slam_ops.py::test_mapper_optimises_raw_parameters_like_gaussian_model runs the real rates)
     base_lr = {"means3D": 1.6e-4, "shs": 2.5e-3, "opacity": 5e-2, "scales": 1e-3, "rotations": 1e-3}
-    mapper = ShardedMapper(P := wl["N"], sh_coeffs=1, device=dev, lrs={k: v * 1e-4 for k, v in base_lr.items()})
-    mapper.load(means3D=sc["means3D"], shs=sc["shs"], opacity=sc["opacities"], scales=sc["scales"], rotations=sc["rotations"])
-    means3D, opac, scales, rots, shs = (mapper.view(k) for k in ("means3D", "opacity", "scales", "rotations", "shs"))
     gc_np, gd_np = synth.make_upstream_grads(cams[0])
     gc, gd = t(gc_np), t(gd_np)
     vcs = {k: ViewCamera(cams[k], dev) for k in my_views}
-    eng = RasterEngine(P, W, H, sh_coeffs=1, sh_degree=0, device=dev, slots=int(os.environ.get("LVDGS_SLOTS", "2")))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- value: device-resident, C-ABI engine ----------------
-    my_vcs = [vcs[k] for k in my_views]
+    def build_job(scene, n_gauss):
+        """Mapper (replicated raw parameter block + sharded Adam) and engine (persistent arenas, two-stream view pipeline)."""
+        mp_ = ShardedMapper(n_gauss, sh_coeffs=1, device=dev, lrs={k: v * 1e-4 for k, v in base_lr.items()})
+        mp_.load(means3D=scene["means3D"], shs=scene["shs"], opacity=scene["opacities"], scales=scene["scales"], rotations=scene["rotations"])
+        eng_ = RasterEngine(n_gauss, W, H, sh_coeffs=1, sh_degree=0, device=dev, slots=int(os.environ.get("LVDGS_SLOTS", "2")),
+                            grad_flat=mp_.new_grad_block())
+        return mp_, eng_
+
     fixed_upstream = lambda k, slot: (gc, gd, None)           # fixed synthetic dL/dcolor, dL/ddepth (SURVEY 8d)
+    my_vcs = [vcs[k] for k in my_views]
 
-    def step_resident():
-        eng.zero_grads()
-        # forward of view k+1 overlaps the backward of view k (two streams, two buffer slots); gradients accumulate
-        eng.run_views(my_vcs, means3D, opac, scales, rots, shs, fixed_upstream)
-        mapper.reduce_gradients(eng.grad_flat)                 # SUM over keyframe shards (NCCL / NVLink); no-op at N=1
-        mapper.adam_step(eng.grad_flat)                        # identical fused Adam update on every rank
+    def make_step(mp_, eng_):
+        def step():
+            args_ = [mp_.view(k) for k in ("means3D", "opacity", "scales", "rotations", "shs")]
+            # forward of view k+1 overlaps the backward of view k (two streams, two buffer slots); gradients accumulate
+            eng_.run_views(my_vcs, *args_, fixed_upstream)
+            # chain rule to the raw parameters, SUM over the keyframe shards (NCCL reduce-scatter), Adam on this rank's
+            # slice, all-gather of the parameters, activations; leaves the gradient block zeroed
+            mp_.exchange_and_update(eng_.grad_flat)
+        return step
 
+    def time_steps(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        barrier()
+        e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0_.record()
+        for _ in range(steps):
+            step()
+        e1_.record()
+        barrier()
+        mine = e0_.elapsed_time(e1_) / steps
+        tms_ = torch.tensor([mine], device=dev)
+        per_rank = [mine]
+        if world > 1:
+            allr = [torch.zeros(1, device=dev) for _ in range(world)]
+            dist.all_gather(allr, tms_)
+            per_rank = [float(x.item()) for x in allr]
+            dist.all_reduce(tms_, op=dist.ReduceOp.MAX)
+        return float(tms_.item()), per_rank
+
+    # ---------------- value: device-resident, C-ABI engine ----------------
+    mapper, eng = build_job(sc, P := wl["N"])
+    means3D, opac, scales, rots, shs = (mapper.view(k) for k in ("means3D", "opacity", "scales", "rotations", "shs"))
+    step_resident = make_step(mapper, eng)
     for _ in range(args.warmup):
         step_resident()
     barrier()
@@ -201,20 +274,38 @@ def main():
     if rank == 0:
         sampler.start()
     L.lvdgs_reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step_resident()
-    e1.record()
-    barrier()
+    ms, ms_per_rank = time_steps(step_resident, args.steps, 0)
     launches = int(L.lvdgs_launch_count())
-    ms = e0.elapsed_time(e1) / args.steps
-    tms = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
     value = wl["views"] * H * W / (ms * 1e-3) / 1e6
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # SURVEY 8(d)'s per-view figure beside the pipelined window: H*W / (t_fwd + t_bwd) of ONE view at a time on one stream
+    per_view = None
+    if rank == 0:
+        ts_ = []
+        for k in my_views[:4]:
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                eng.forward(vcs[k], means3D, opac, scales, rots, shs)
+                eng.backward(vcs[k], means3D, opac, scales, rots, shs, gc, gd, accumulate=True)
+            e1.record(); e1.synchronize()
+            ts_.append(e0.elapsed_time(e1) / 5)
+        eng.zero_grads()
+        per_view = {"ms_fwd_bwd": float(np.median(ts_)), "mpix_per_s": H * W / (float(np.median(ts_)) * 1e-3) / 1e6,
+                    "what": "one view at a time on one stream (no overlap between views), median over this rank's first views"}
+
+    # BASELINE configs[2] names 1 M Gaussians for the mapping window: the same step on that map (extra key; the headline
+    # metric is quoted at 500 k)
+    mapping_1m = None
+    if args.workload == "kitti_window8_500k" and os.environ.get("LVDGS_BENCH_1M", "1") != "0":
+        sc1 = synth.make_scene(1_000_000, cams[0], seed=0)
+        m1, e1m = build_job(sc1, 1_000_000)
+        ms1, ms1_ranks = time_steps(make_step(m1, e1m), max(5, args.steps // 2), 3)
+        mapping_1m = {"workload": "kitti_window8_1m (BASELINE configs[2])", "ms_per_step": ms1, "iters_per_s": 1e3 / ms1,
+                      "mpix_per_s": wl["views"] * H * W / (ms1 * 1e-3) / 1e6, "ms_per_step_by_rank": ms1_ranks}
+        del m1, e1m, sc1
+        torch.cuda.empty_cache()
 
     # ---------------- e2e: plugin surface, host buffers ----------------
     import diff_gaussian_rasterization as dgr
@@ -322,7 +413,9 @@ def main():
         hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         sm_max = peaks.get("sm_max_mhz", 1965.0)
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        fp32_peak = n_sm * 128 * 2 * sm_max * 1e6 / 1e12        # TFLOP/s at max clock; no measured FP32 peak exists
+        fp32_computed = n_sm * 128 * 2 * sm_max * 1e6 / 1e12    # TFLOP/s at max clock
+        fp32_meas = measure_fp32_peak(L, dev, n_sm)             # FFMA / FFMA2 micro-kernel, CUDA events, best of 5
+        fp32_peak = max(fp32_meas["ffma_tflops"], fp32_meas["ffma2_tflops"])
         stream = torch.cuda.current_stream().cuda_stream
         agg, pairs, Rs, vis = {}, 0, 0, 0
         reps = 3
@@ -374,8 +467,10 @@ def main():
                     "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic,
                     "ms_per_launch": dom["ms_per_view"] / dom["launches_per_view"],
                     "peak_source": hbm_src if dom["bound"] == "hbm" else
-                    f"computed {n_sm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (no measured FP32 peak in MEASURED_PEAKS.json; "
-                    "tensor cores unused: the blend is FP32 FMA/MUFU issue-bound, not a dense contraction)",
+                    f"measured in this run: lvdgs_fp32_peak micro-kernel, FFMA {fp32_meas['ffma_tflops']:.1f} / FFMA2 {fp32_meas['ffma2_tflops']:.1f} "
+                    f"TFLOP/s (computed {n_sm} SMs x 128 lanes x 2 x {sm_max:.0f} MHz = {fp32_computed:.1f}; MEASURED_PEAKS.json has no FP32 "
+                    "figure; tensor cores unused: the blend is FP32 FMA/MUFU issue-bound, not a dense contraction)",
+                    "fp32_peak_measured": fp32_meas,
                     "algorithmic": {"pairs_per_view": pairs, "instances_per_view": Rs, "visible_per_view": vis},
                     "ncu": ncu,
                     "note": "frac counts only the FLOPs of the A.3/A.4 blend math; the kernel's issue slots (ncu "
@@ -389,7 +484,7 @@ def main():
         cpu_oracle_view(sc, cams[0], gc_np, gd_np)               # warm (page-in, OpenMP pool)
         ts = [cpu_oracle_view(sc, cams[k], gc_np, gd_np) for k in (0, 3, 6)]
         tv = float(np.median(ts))
-        cpu = {"value": H * W / tv / 1e6, "unit": "Mpix/s", "cores": oracle.num_threads(), "kind": "port",
+        cpu = {"value": H * W / tv / 1e6, "unit": "Mpix/s", "cores": oracle.set_num_threads(host_cores()), "kind": "port", "detail": CPU_BASELINE_DETAIL,
                "sample": "3 of the 8 views (k=0,3,6), full 1241x376 fwd+bwd each, median; C oracle with OpenMP",
                "seconds_per_view": tv}
 
@@ -427,16 +522,15 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload, "gaussians": P, "image": [W, H], "views_per_step": wl["views"],
-                           "views_per_rank": len(my_views), "sh_degree": 0,
-                           "l2": "inputs larger than L2: each view streams its own sorted instance list, and the 8 views "
-                                 "of a step rewrite >300 MB of binning state between revisits",
-                           "parallelism": f"keyframes sharded over {world} rank(s), NCCL SUM-allreduce of [P,14] grads" if world > 1 else "1 GPU"},
+                "config": bench_config(args, wl, W, H, world, len(my_views)),
+                "layout": {"views_per_rank": len(my_views),
+                           "parallelism": f"keyframes sharded over {world} rank(s), NCCL reduce-scatter of the [P,14] gradients + Adam on the shard + all-gather" if world > 1 else "1 GPU"},
                 "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "path": "diff_gaussian_rasterization.GaussianRasterizer (autograd) + "
                                 + ("torch L1 loss" if torch_loss else "lvdgs.slam_ops.fused_loss (mapping rgbd loss)") + ", losses summed over the window and one backward (as utils/slam_backend.py:167-306) + torch Adam; "
                                 "H2D of the next view prefetched on a copy stream"},
-                "gpu_launches": launches, "mapping_iters_per_s": 1e3 / ms, "clocks": clocks, "roofline": roof,
+                "gpu_launches": launches, "mapping_iters_per_s": 1e3 / ms, "ms_per_step_by_rank": ms_per_rank,
+                "per_view_unpipelined": per_view, "mapping_1m": mapping_1m, "clocks": clocks, "roofline": roof,
                 "kernels": kernels, "cpu_baseline": cpu, "tracking": tracking}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -209,6 +209,16 @@ int lvdgs_cub_sort_pairs(int64_t n, const uint64_t *keys_in, uint64_t *keys_out,
                          uint32_t *vals_out, int32_t end_bit, void *workspace, size_t workspace_bytes,
                          void *stream);
 
+/*
+ * Measurement aid for bench.py (not a product path): one launch of `blocks` x 256 threads, each running iters x 16
+ * independent register-only operations.  mode 0: scalar FFMA, mode 1: packed FFMA2 (two fp32 FMAs per instruction);
+ * modes 2..7: instruction-mix probes (FMUL2, FADD2, FFMA2 + FFMA, FFMA2 + select, select alone, FFMA + select; see
+ * csrc/peak.cu and scripts/pipe_probe.py).  *fmas (host) receives the number of FMAs (modes 0, 1, 4) or instructions of the
+ * launch; time it with CUDA events -> the device's measured FP32 FMA-pipe peak, the denominator of the blend kernels'
+ * roofline fraction.  out: any device float (never written).
+ */
+int lvdgs_fp32_peak(int32_t blocks, int32_t iters, int32_t mode, float *out, double *fmas, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * The callers either side of the rasterizer (SURVEY.md section 8f "next" rows).  Same conventions as above.
  * ------------------------------------------------------------------------------------------------------------ */
@@ -263,6 +273,19 @@ int lvdgs_compact_move(int64_t n, const uint8_t *keep, const void *workspace, in
  */
 int lvdgs_gather_rows(int64_t n_idx, const int64_t *idx, int64_t n_src_rows, int32_t n_arrays, const float *const *src,
                       float *const *dst, const int32_t *widths, void *stream);
+
+/*
+ * Row N1, parametrisation.  GaussianModel optimises RAW parameters and hands the rasterizer their activations
+ * (get_opacity = sigmoid(_opacity), get_scaling = exp(_scaling), get_rotation = normalize(_rotation); used by render() at
+ * utils/slam_backend.py:98,184,277,407).  lvdgs_gaussian_activate: raw [P], [P,3], [P,4] -> activated arrays of the same
+ * shapes.  lvdgs_gaussian_activation_backward: turns the gradients with respect to the ACTIVATED values (the outputs of
+ * lvdgs_rasterize_backward, possibly summed over views) into gradients with respect to the RAW parameters, in place --
+ * the chain rule torch autograd applies in the reference.  rotations / raw_rotations / g_rotations 16-byte aligned.
+ */
+int lvdgs_gaussian_activate(int64_t P, const float *raw_opacity, const float *raw_scales, const float *raw_rotations, float *opacity,
+                            float *scales, float *rotations, void *stream);
+int lvdgs_gaussian_activation_backward(int64_t P, const float *opacity, const float *scales, const float *rotations,
+                                       const float *raw_rotations, float *g_opacity, float *g_scales, float *g_rotations, void *stream);
 
 /*
  * Rows a15 / a16: the tail of one tracking iteration on the device.  lvdgs_pose_state is the camera's device-resident

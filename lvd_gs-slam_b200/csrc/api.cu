@@ -438,6 +438,21 @@ int lvdgs_gather_rows(int64_t n_idx, const int64_t *idx, int64_t n_src_rows, int
     return launch_gather_rows(n_idx, idx, n_src_rows, n_arrays, src, dst, widths, (cudaStream_t)stream);
 }
 
+int lvdgs_gaussian_activate(int64_t P, const float *raw_opacity, const float *raw_scales, const float *raw_rotations, float *opacity,
+                            float *scales, float *rotations, void *stream) {
+    if (P < 0 || (P > 0 && (!raw_opacity || !raw_scales || !raw_rotations || !opacity || !scales || !rotations))) { set_error("gaussian_activate: bad arguments"); return 1; }
+    if (((uintptr_t)raw_rotations | (uintptr_t)rotations) & 15) { set_error("gaussian_activate: rotations must be 16-byte aligned"); return 1; }
+    g_debug_sync = 0;
+    return launch_gaussian_activate(P, raw_opacity, raw_scales, raw_rotations, opacity, scales, rotations, (cudaStream_t)stream);
+}
+int lvdgs_gaussian_activation_backward(int64_t P, const float *opacity, const float *scales, const float *rotations,
+                                       const float *raw_rotations, float *g_opacity, float *g_scales, float *g_rotations, void *stream) {
+    if (P < 0 || (P > 0 && (!opacity || !scales || !rotations || !raw_rotations || !g_opacity || !g_scales || !g_rotations))) { set_error("gaussian_activation_backward: bad arguments"); return 1; }
+    if (((uintptr_t)raw_rotations | (uintptr_t)rotations | (uintptr_t)g_rotations) & 15) { set_error("gaussian_activation_backward: rotations must be 16-byte aligned"); return 1; }
+    g_debug_sync = 0;
+    return launch_gaussian_activation_backward(P, opacity, scales, rotations, raw_rotations, g_opacity, g_scales, g_rotations, (cudaStream_t)stream);
+}
+
 int lvdgs_pose_step(lvdgs_pose_state *state, const float *g_tau, const float *g_exposure, float lr_rot, float lr_trans,
                     float lr_exposure, double beta1, double beta2, double eps, int32_t step, float converged_threshold,
                     void *stream) {
@@ -445,6 +460,12 @@ int lvdgs_pose_step(lvdgs_pose_state *state, const float *g_tau, const float *g_
     g_debug_sync = 0;
     return launch_pose_step(state, g_tau, g_exposure, lr_rot, lr_trans, lr_exposure, beta1, beta2, eps, step,
                             converged_threshold, (cudaStream_t)stream);
+}
+
+int lvdgs_fp32_peak(int32_t blocks, int32_t iters, int32_t mode, float *out, double *fmas, void *stream) {
+    if (blocks <= 0 || iters <= 0 || !out) { set_error("fp32_peak: bad arguments"); return 1; }
+    g_debug_sync = 0;
+    return launch_fp32_peak(blocks, iters, mode, out, fmas, (cudaStream_t)stream);
 }
 
 size_t lvdgs_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n > 0 ? n : 1); }

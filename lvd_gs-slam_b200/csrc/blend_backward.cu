@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
 
     // per-pixel state, packed (lo = row py0, hi = row py0 + 4)
     uint32_t last[2];
-    f32x2 npfy2, T2, nTfbgd2, dp0_2, dp1_2, dp2_2, dpd_2, S2 = bc(0.f);
+    f32x2 npfy2, T2, Tfbgd2, dp0_2, dp1_2, dp2_2, dpd_2, S2 = bc(0.f);
     {
         float pfy[2], Tf[2], dp0[2], dp1[2], dp2[2], dpd[2], bgd[2];
         const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
         }
         npfy2 = pk(-pfy[0], -pfy[1]);
         T2 = pk(Tf[0], Tf[1]);
-        nTfbgd2 = pk(-Tf[0] * bgd[0], -Tf[1] * bgd[1]);
+        Tfbgd2 = pk(Tf[0] * bgd[0], Tf[1] * bgd[1]);
         dp0_2 = pk(dp0[0], dp0[1]); dp1_2 = pk(dp1[0], dp1[1]); dp2_2 = pk(dp2[0], dp2[1]); dpd_2 = pk(dpd[0], dpd[1]);
     }
     // warp-wide and tile-wide max of n_contrib: nothing at or beyond it contributes
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
                 const float4 co = __ldg(conic_opacity + id);
                 s_rec[e].xy = make_float2(m.x, m.y);
                 s_rec[e].id = id;
-                s_rec[e].co = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);   // as forward
+                s_rec[e].co = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, -co.w);   // as forward
                 s_rec[e].cd = __ldg(rgbd + id);
                 const float rx = m.x - tx0, ry = m.y - ty0;
                 uint32_t xb = 0, yb = 0;
@@ -248,32 +248,35 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
                 const f32x2 p2 = fma2(mul2(bc(co.z), dy2), dy2, mul2(bc(dx), fma2(bc(co.y), dy2, bc(co.x * dx))));
                 const float p2a = lo_of(p2), p2b = hi_of(p2);
                 const float ga = ex2_approx(p2a), gb = ex2_approx(p2b);
-                const float aa = fminf(0.99f, co.w * ga), ab = fminf(0.99f, co.w * gb);
-                const bool oka = k < last[0] && p2a <= 0.f && aa >= 1.f / 255.f;
-                const bool okb = k < last[1] && p2b <= 0.f && ab >= 1.f / 255.f;
+                // co.w = -opacity; the recurrences below are written in -alpha, and every sum of this visit comes out
+                // NEGATED (m = G dL/dalpha and the blend weight both carry the sign), which the commit undoes for free
+                const float naa = fmaxf(-0.99f, co.w * ga), nab = fmaxf(-0.99f, co.w * gb);
+                const bool oka = k < last[0] && p2a <= 0.f && naa <= -1.f / 255.f;
+                const bool okb = k < last[1] && p2b <= 0.f && nab <= -1.f / 255.f;
                 const bool valid = oka || okb;
                 const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
                 if (!vmask) continue;
                 const f32x2 G2 = pk(oka ? ga : 0.f, okb ? gb : 0.f);
-                const f32x2 al2 = pk(oka ? aa : 0.f, okb ? ab : 0.f);
-                const f32x2 one_m2 = fma2(al2, bc(-1.f), bc(1.f));
+                const f32x2 nal2 = pk(oka ? naa : 0.f, okb ? nab : 0.f);
+                const f32x2 one_m2 = add2(nal2, bc(1.f));
                 const f32x2 inv2 = pk(rcp_approx(lo_of(one_m2)), rcp_approx(hi_of(one_m2)));   // 1 - alpha >= 0.01
                 T2 = mul2(T2, inv2);
                 // the colour / depth blended BEHIND this Gaussian enters only through its dot product with dL/dpixel:
-                // S = <B, dp> obeys the same recurrence as B itself (S <- alpha <c, dp> + (1 - alpha) S)
+                // S = <B, dp> obeys the same recurrence as B itself (S <- S + alpha (<c, dp> - S))
                 const f32x2 cdp2 = fma2(bc(cd.w), dpd_2, fma2(bc(cd.z), dp2_2, fma2(bc(cd.y), dp1_2, mul2(bc(cd.x), dp0_2))));
-                f32x2 dL2 = mul2(fma2(S2, bc(-1.f), cdp2), T2);
-                dL2 = fma2(inv2, nTfbgd2, dL2);                   // - T_final / (1 - alpha) * <bg, dp>
-                S2 = fma2(al2, cdp2, mul2(one_m2, S2));
-                const f32x2 m2 = mul2(G2, dL2);
+                const f32x2 ne2 = fma2(cdp2, bc(-1.f), S2);       // S - <c, dp>
+                f32x2 ndL2 = mul2(ne2, T2);                       // -dL/dalpha, first term
+                ndL2 = fma2(inv2, Tfbgd2, ndL2);                  // + T_final / (1 - alpha) * <bg, dp>
+                S2 = fma2(nal2, ne2, S2);
+                const f32x2 m2 = mul2(G2, ndL2);                  // -m
                 const f32x2 mdx2 = mul2(m2, bc(dx)), mdy2 = mul2(m2, dy2);
-                float v[10];      // accumulator-row slots 0..6, 8..10 (ACC_STRIDE layout in common.cuh)
+                float v[10];      // NEGATED accumulator-row slots 0..6, 8..10 (ACC_STRIDE layout in common.cuh)
                 v[0] = hsum(mdx2); v[1] = hsum(mdy2);
                 v[2] = dx * v[0];                                 // both pixels share dx
                 v[3] = hsum(mul2(mdx2, dy2)); v[4] = hsum(mul2(mdy2, dy2));
                 v[5] = hsum(m2);
                 if (!MOMENTS_ONLY) {
-                    const f32x2 wgt2 = mul2(al2, T2);
+                    const f32x2 wgt2 = mul2(nal2, T2);            // -alpha T
                     v[6] = hsum(mul2(wgt2, dpd_2));
                     v[7] = hsum(mul2(wgt2, dp0_2)); v[8] = hsum(mul2(wgt2, dp1_2)); v[9] = hsum(mul2(wgt2, dp2_2));
                 } else {
@@ -285,16 +288,16 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
                         // a Gaussian's edge often reaches only one or two threads of the block: their partial sums go
                         // straight to the accumulator row (10 REDs) instead of through the 60-instruction reduction
                         if (valid) {
-                            atomicAdd(row + 0, v[0]); atomicAdd(row + 1, v[1]); atomicAdd(row + 2, v[2]); atomicAdd(row + 3, v[3]);
-                            atomicAdd(row + 4, v[4]); atomicAdd(row + 5, v[5]);
+                            atomicAdd(row + 0, -v[0]); atomicAdd(row + 1, -v[1]); atomicAdd(row + 2, -v[2]); atomicAdd(row + 3, -v[3]);
+                            atomicAdd(row + 4, -v[4]); atomicAdd(row + 5, -v[5]);
                             if (!MOMENTS_ONLY) {
-                                atomicAdd(row + 6, v[6]);
-                                atomicAdd(row + 8, v[7]); atomicAdd(row + 9, v[8]); atomicAdd(row + 10, v[9]);
+                                atomicAdd(row + 6, -v[6]);
+                                atomicAdd(row + 8, -v[7]); atomicAdd(row + 9, -v[8]); atomicAdd(row + 10, -v[9]);
                             }
                         }
                     } else {
                         const float sum = MOMENTS_ONLY ? transpose_reduce6(v, lane) : transpose_reduce10(v, lane);
-                        if (commits) atomicAdd(row + slot, sum);
+                        if (commits) atomicAdd(row + slot, -sum);
                     }
                 }
             }

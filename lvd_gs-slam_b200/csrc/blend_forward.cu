@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(BF_THREADS, LVDGS_BF_MINBLOCKS) blend_forward_
                 const float4 co = __ldg(conic_opacity + id);
                 s_rec[e].xy = make_float2(m.x, m.y);
                 s_rec[e].id = id;
-                s_rec[e].co = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, co.w);
+                s_rec[e].co = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, -co.w);   // base-2 conic, MINUS opacity
                 s_rec[e].cd = __ldg(rgbd + id);
                 const float rx = m.x - tx0, ry = m.y - ty0;
                 uint32_t xb = 0;
@@ -124,17 +124,19 @@ __global__ void __launch_bounds__(BF_THREADS, LVDGS_BF_MINBLOCKS) blend_forward_
                 const f32x2 dy2 = add2(bc(xy.y), npfy2);
                 const f32x2 p2 = fma2(mul2(bc(q.z), dy2), dy2, mul2(bc(dx), fma2(bc(q.y), dy2, bc(q.x * dx))));
                 const float p2a = lo_of(p2), p2b = hi_of(p2);
-                const float aa = fminf(0.99f, q.w * ex2_approx(p2a)), ab = fminf(0.99f, q.w * ex2_approx(p2b));
-                const bool oka = p2a <= 0.f && aa >= 1.f / 255.f, okb = p2b <= 0.f && ab >= 1.f / 255.f;
-                const f32x2 al2 = pk(aa, ab);
-                const f32x2 tT2 = mul2(T2, fma2(al2, bc(-1.f), bc(1.f)));
+                // q.w = -opacity: everything downstream wants -alpha (T - alpha T as ONE fma, weights that accumulate
+                // MINUS the colour), so no negation is ever issued
+                const float naa = fmaxf(-0.99f, q.w * ex2_approx(p2a)), nab = fmaxf(-0.99f, q.w * ex2_approx(p2b));
+                const bool oka = p2a <= 0.f && naa <= -1.f / 255.f, okb = p2b <= 0.f && nab <= -1.f / 255.f;
+                const f32x2 tT2 = fma2(pk(naa, nab), T2, T2);      // T (1 - alpha)
                 const float tTa = lo_of(tT2), tTb = hi_of(tT2);
                 const bool terma = oka && tTa < 0.0001f, termb = okb && tTb < 0.0001f;
                 const bool ca = oka && !terma, cb = okb && !termb;
-                const f32x2 w2 = mul2(al2, T2);
-                const f32x2 wgt2 = pk(ca ? lo_of(w2) : 0.f, cb ? hi_of(w2) : 0.f);
-                C0 = fma2(bc(cd.x), wgt2, C0); C1 = fma2(bc(cd.y), wgt2, C1); C2 = fma2(bc(cd.z), wgt2, C2); D = fma2(bc(cd.w), wgt2, D);
-                T2 = pk(ca ? tTa : lo_of(T2), cb ? tTb : hi_of(T2));
+                // one select per pixel (-alpha or 0); weight and T follow arithmetically (alpha = 0 leaves T untouched)
+                const f32x2 nae2 = pk(ca ? naa : 0.f, cb ? nab : 0.f);
+                const f32x2 nw2 = mul2(nae2, T2);
+                C0 = fma2(bc(cd.x), nw2, C0); C1 = fma2(bc(cd.y), nw2, C1); C2 = fma2(bc(cd.z), nw2, C2); D = fma2(bc(cd.w), nw2, D);
+                T2 = fma2(nae2, T2, T2);
                 const uint32_t idx = batch_first + (uint32_t)j + 1u;
                 last0 = ca ? idx : last0; last1 = cb ? idx : last1;
                 npfy2 = pk(terma ? -PIX_PARKED : lo_of(npfy2), termb ? -PIX_PARKED : hi_of(npfy2));
@@ -154,10 +156,10 @@ __global__ void __launch_bounds__(BF_THREADS, LVDGS_BF_MINBLOCKS) blend_forward_
         const float T = qi ? hi_of(T2) : lo_of(T2);
         final_T[pix] = T;
         n_contrib[pix] = qi ? last1 : last0;
-        out_color[pix] = (qi ? hi_of(C0) : lo_of(C0)) + T * bg0;
-        out_color[HW + pix] = (qi ? hi_of(C1) : lo_of(C1)) + T * bg1;
-        out_color[2 * HW + pix] = (qi ? hi_of(C2) : lo_of(C2)) + T * bg2;
-        out_depth[pix] = qi ? hi_of(D) : lo_of(D);
+        out_color[pix] = T * bg0 - (qi ? hi_of(C0) : lo_of(C0));      // the accumulators hold minus the sums
+        out_color[HW + pix] = T * bg1 - (qi ? hi_of(C1) : lo_of(C1));
+        out_color[2 * HW + pix] = T * bg2 - (qi ? hi_of(C2) : lo_of(C2));
+        out_depth[pix] = -(qi ? hi_of(D) : lo_of(D));
         out_opacity[pix] = 1.f - T;
     }
 }

@@ -245,8 +245,14 @@ int launch_compact_move(int64_t n, const uint8_t *keep, const void *ws, int n_ar
 
 int launch_gather_rows(int64_t n_idx, const int64_t *idx, int64_t n_src_rows, int n_arrays, const float *const *src,
                        float *const *dst, const int32_t *widths, cudaStream_t s);
+int launch_gaussian_activate(int64_t P, const float *raw_o, const float *raw_s, const float *raw_q, float *o, float *sc, float *q,
+                             cudaStream_t s);
+int launch_gaussian_activation_backward(int64_t P, const float *o, const float *sc, const float *q, const float *raw_q, float *g_o,
+                                        float *g_s, float *g_q, cudaStream_t s);
 int launch_pose_step(lvdgs_pose_state *state, const float *g_tau, const float *g_exposure, float lr_rot, float lr_trans,
                      float lr_exp, double beta1, double beta2, double eps, int step, float threshold, cudaStream_t s);
+
+int launch_fp32_peak(int blocks, int iters, int mode, float *out, double *fmas, cudaStream_t s);
 
 size_t dist2_workspace_bytes(int P);
 int launch_dist2(int P, const float *points, float *mean_dists, void *ws, size_t ws_bytes, cudaStream_t s);

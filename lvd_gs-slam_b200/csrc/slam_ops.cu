@@ -477,4 +477,61 @@ int launch_gather_rows(int64_t n_idx, const int64_t *idx, int64_t n_src_rows, in
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Row N1: GaussianModel's parametrisation on the device.  The reference optimises RAW parameters -- logit opacity,
+// log scale, un-normalised quaternion -- and hands the rasterizer their activations (get_opacity = sigmoid,
+// get_scaling = exp, get_rotation = normalize; SURVEY.md A.0, callers utils/slam_backend.py:98,184,277).
+// activate: raw -> rasterizer inputs, one thread per Gaussian.  activation_backward: gradients with respect to the
+// activated values (what lvdgs_rasterize_backward produces) -> gradients with respect to the raw parameters, in place:
+//   d/d raw_o = g o (1 - o),   d/d raw_s = g s,   d/d raw_q = (g - q^ <q^, g>) / |raw_q|.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gaussian_activate_kernel(int64_t P, const float *__restrict__ raw_o, const float *__restrict__ raw_s,
+                                                                const float4 *__restrict__ raw_q, float *__restrict__ o, float *__restrict__ sc,
+                                                                float4 *__restrict__ q) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    o[i] = 1.f / (1.f + expf(-raw_o[i]));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sc[3 * i + k] = expf(raw_s[3 * i + k]);
+    const float4 r = raw_q[i];
+    const float n = fmaxf(sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w), 1e-12f);     // torch.nn.functional.normalize eps
+    q[i] = make_float4(r.x / n, r.y / n, r.z / n, r.w / n);
+}
+
+__global__ void __launch_bounds__(256) gaussian_activation_backward_kernel(int64_t P, const float *__restrict__ o, const float *__restrict__ sc,
+                                                                           const float4 *__restrict__ q, const float4 *__restrict__ raw_q,
+                                                                           float *__restrict__ g_o, float *__restrict__ g_s, float4 *__restrict__ g_q) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    const float oi = o[i];
+    g_o[i] *= oi * (1.f - oi);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g_s[3 * i + k] *= sc[3 * i + k];
+    const float4 qi = q[i], r = raw_q[i], g = g_q[i];
+    const float inv = 1.f / fmaxf(sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w), 1e-12f);
+    const float d = qi.x * g.x + qi.y * g.y + qi.z * g.z + qi.w * g.w;
+    g_q[i] = make_float4((g.x - qi.x * d) * inv, (g.y - qi.y * d) * inv, (g.z - qi.z * d) * inv, (g.w - qi.w * d) * inv);
+}
+
+int launch_gaussian_activate(int64_t P, const float *raw_o, const float *raw_s, const float *raw_q, float *o, float *sc, float *q,
+                             cudaStream_t s) {
+    if (P <= 0) return 0;
+    LVDGS_PRE(s);
+    gaussian_activate_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(P, raw_o, raw_s, reinterpret_cast<const float4 *>(raw_q), o, sc,
+                                                                          reinterpret_cast<float4 *>(q));
+    LVDGS_LAUNCHED(s, "gaussian_activate");
+    return 0;
+}
+
+int launch_gaussian_activation_backward(int64_t P, const float *o, const float *sc, const float *q, const float *raw_q, float *g_o,
+                                        float *g_s, float *g_q, cudaStream_t s) {
+    if (P <= 0) return 0;
+    LVDGS_PRE(s);
+    gaussian_activation_backward_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(P, o, sc, reinterpret_cast<const float4 *>(q),
+                                                                                     reinterpret_cast<const float4 *>(raw_q), g_o, g_s,
+                                                                                     reinterpret_cast<float4 *>(g_q));
+    LVDGS_LAUNCHED(s, "gaussian_activation_backward");
+    return 0;
+}
+
 }  // namespace lvdgs

@@ -15,7 +15,7 @@ SRC_DIR = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 SO_PATH = os.path.join(PKG_DIR, "liblvdgs.so")
 SOURCES = ["api.cu", "preprocess.cu", "radix_sort.cu", "tile_sort.cu", "slam_ops.cu", "blend_forward.cu", "blend_backward.cu",
-           "preprocess_backward.cu", "knn.cu", "adam.cu", "cub_compare.cu"]
+           "preprocess_backward.cu", "knn.cu", "adam.cu", "cub_compare.cu", "peak.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("LVDGS_NVCC_DEFS", "").split()
 
@@ -117,7 +117,8 @@ EXPORTS = ["lvdgs_version", "lvdgs_last_error", "lvdgs_set_device", "lvdgs_launc
            "lvdgs_dist2_workspace_bytes", "lvdgs_dist2", "lvdgs_adam_step", "lvdgs_sort_workspace_bytes", "lvdgs_sort_pairs",
            "lvdgs_cub_sort_workspace_bytes", "lvdgs_cub_sort_pairs",
            "lvdgs_fused_loss_workspace_bytes", "lvdgs_fused_loss", "lvdgs_covis_counts", "lvdgs_n_obs",
-           "lvdgs_compact_workspace_bytes", "lvdgs_compact_count", "lvdgs_compact_move", "lvdgs_pose_step", "lvdgs_gather_rows"]
+           "lvdgs_compact_workspace_bytes", "lvdgs_compact_count", "lvdgs_compact_move", "lvdgs_pose_step", "lvdgs_gather_rows",
+           "lvdgs_fp32_peak", "lvdgs_gaussian_activate", "lvdgs_gaussian_activation_backward"]
 
 
 def lib():
@@ -166,6 +167,9 @@ def lib():
     L.lvdgs_compact_count.argtypes = [i64, vp, vp, sz, C.POINTER(vp), vp]
     L.lvdgs_compact_move.argtypes = [i64, vp, vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp]
     L.lvdgs_gather_rows.argtypes = [i64, vp, i64, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp]
+    L.lvdgs_gaussian_activate.argtypes = [i64] + [vp] * 7
+    L.lvdgs_gaussian_activation_backward.argtypes = [i64] + [vp] * 8
+    L.lvdgs_fp32_peak.argtypes = [i32, i32, i32, vp, C.POINTER(C.c_double), vp]
     L.lvdgs_pose_step.argtypes = [vp, vp, vp, f, f, f, C.c_double, C.c_double, C.c_double, i32, f, vp]
     _lib = L
     return L

@@ -26,6 +26,26 @@ from ._native import RasterParams, ptr
 
 FLAG_EXACT_PP, FLAG_OPACITY_GRAD, FLAG_ACCUMULATE, FLAG_POSE_ONLY = 1, 2, 4, 8
 
+# parameter groups of the contiguous parameter / gradient block, in block order
+GROUPS = ("means3D", "shs", "opacity", "scales", "rotations")
+
+
+def block_layout(P: int, sh_coeffs: int = 1, multiple: int = 4):
+    """Offsets (in floats) of the five per-Gaussian arrays inside ONE contiguous float32 block -- the layout shared by
+    RasterEngine.grad_flat and lvdgs.mapping.ShardedMapper.param_flat: [means3D 3 | shs 3M | opacity 1 | scales 3 |
+    rotations 4] per Gaussian, array after array, every array starting on a 16-byte boundary (float4 accesses in the
+    kernels) and the total rounded up to `multiple` floats (a multiple of 4 x world makes the block reduce-scatterable).
+    Returns ({name: (offset, length)}, total)."""
+    widths = {"means3D": 3, "shs": 3 * sh_coeffs, "opacity": 1, "scales": 3, "rotations": 4}
+    out, off = {}, 0
+    for name in GROUPS:
+        n = widths[name] * P
+        out[name] = (off, n)
+        off += (n + 3) & ~3
+    multiple = max(4, int(multiple))
+    total = (off + multiple - 1) // multiple * multiple
+    return out, total
+
 
 class ViewCamera:
     """Device-resident camera block: the five small tensors GaussianRasterizationSettings carries."""
@@ -62,6 +82,7 @@ class _Slot:
         self.n_touched = torch.empty(P, dtype=torch.int32, device=dev)
         self.g_means2D = torch.empty(P, 3, **f32)
         self.g_tau = torch.empty(6, **f32)
+        self.streams = ()            # side streams that use this slot's tensors (set by the engine)
         self.R = 0
         self.capacity = 0            # instances the binning arena was last laid out for
         self.hint = 0                # speculative-launch capacity hint for the next forward
@@ -69,32 +90,43 @@ class _Slot:
     def _resize(self, _user, which, nbytes):
         buf = self.arena[int(which)]
         if buf.numel() < nbytes:                       # geometric growth; steady state never allocates
+            # the replaced arena may still be read by this slot's previous backward on the backward stream (the host
+            # never blocks on it): tell the caching allocator, so the block is not handed out again before those kernels
+            # have finished
+            for st in self.streams:
+                buf.record_stream(st)
             buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.dev)
+            for st in self.streams:
+                buf.record_stream(st)
             self.arena[int(which)] = buf
         return buf.data_ptr()
 
 
 class RasterEngine:
     def __init__(self, P: int, W: int, H: int, sh_coeffs: int = 1, sh_degree: int = 0, device="cuda", flags: int = 0,
-                 slots: int = 2):
+                 slots: int = 2, grad_flat=None):
         self.L = _native.lib()
         self.dev = torch.device(device)
         self.P, self.W, self.H, self.M, self.D = P, W, H, sh_coeffs, sh_degree
         self.flags = flags
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.slots = [_Slot(self) for _ in range(max(1, slots))]
-        # gradient block (contiguous; one NCCL message)
-        sizes = [("means3D", 3), ("shs", 3 * sh_coeffs), ("opacity", 1), ("scales", 3), ("rotations", 4)]
-        total = sum(k for _, k in sizes) * P
-        self.grad_flat = torch.zeros(total, **f32)
-        self.grads = {}
-        off = 0
-        for name, k in sizes:
-            self.grads[name] = self.grad_flat[off:off + k * P]
-            off += k * P
+        # gradient block (contiguous; one NCCL message).  A caller that shards the optimiser (lvdgs.mapping) passes its own,
+        # suitably padded, buffer.
+        layout, total = block_layout(P, sh_coeffs)
+        if grad_flat is not None:
+            assert grad_flat.numel() >= total and grad_flat.dtype == torch.float32 and grad_flat.is_contiguous()
+        self.grad_flat = grad_flat if grad_flat is not None else torch.zeros(total, **f32)
+        self.grads = {name: self.grad_flat[off:off + n] for name, (off, n) in layout.items()}
         import os
         self.s_fwd = torch.cuda.Stream(self.dev, priority=int(os.environ.get("LVDGS_FWD_PRIORITY", "-1")))   # short latency-bound kernels get SM slots first
         self.s_bwd = torch.cuda.Stream(self.dev)
+        # every slot tensor is allocated on the construction stream but used on the two side streams
+        for sl in self.slots:
+            sl.streams = (self.s_fwd, self.s_bwd)
+            for t in (*sl.arena.values(), sl.scratch, sl.color, sl.depth, sl.opacity, sl.radii, sl.n_touched, sl.g_means2D, sl.g_tau):
+                for st in sl.streams:
+                    t.record_stream(st)
         if self.dev.index is not None:
             self.L.lvdgs_set_device(self.dev.index)
 

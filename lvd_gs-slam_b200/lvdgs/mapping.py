@@ -6,11 +6,24 @@ One mapping iteration of the reference (utils/slam_backend.py:153-389) renders e
 (`loss_mapping +=`, :266/:300), back-propagates once and takes one Adam step.  The views are independent given the
 map, so here: one process per GPU, the map replicated, keyframe k owned by rank k mod world; every rank accumulates
 the parameter gradients of its views into one contiguous float32 block (lvdgs.engine.RasterEngine.grad_flat: the
-backward kernel adds into it, there is no pack kernel) and the only data-path collective is ONE SUM all-reduce of
-that block per iteration (56 B per Gaussian at SH degree 0), followed by the identical Adam update on every rank --
-replicas stay bit-identical without a broadcast.  Densification statistics ride along: the accumulated 2-D
-gradient norms and their denominators are SUM-reduced, `max_radii2D` is MAX-reduced (utils/slam_backend.py:350-357).
-Per-keyframe visibility masks (`n_touched > 0`, :311-315) stay on the owning rank.
+backward kernel adds into it, there is no pack kernel).  The exchange step per iteration (NCCL):
+
+    reduce-scatter (SUM) of the gradient block  ->  fused Adam on this rank's 1/world slice  ->  all-gather of the
+    updated parameters,
+
+i.e. the optimiser state is sharded (ZeRO-1): the same bytes cross NVLink as in an all-reduce, but the Adam kernel
+touches 1/world of the block on every rank and the gradient block is re-zeroed off the critical path.  With a backend
+that has no reduce-scatter (gloo, the CPU tests) the block is all-reduced and every rank runs the identical full update.
+Either way the replicas stay bit-identical without a broadcast.
+
+Parametrisation: like the reference's GaussianModel the block holds RAW parameters -- logit opacity, log
+scale, un-normalised quaternion -- and the rasterizer is fed their activations (lvdgs_gaussian_activate); the gradients
+it returns are taken back through the activations (lvdgs_gaussian_activation_backward) before the exchange, so Adam
+works on the same variables as `GaussianModel.optimizer` (opacity can never leave (0, 1), rotations stay unit).
+
+Densification statistics ride along: the accumulated 2-D gradient norms and their denominators are SUM-reduced,
+`max_radii2D` is MAX-reduced (utils/slam_backend.py:350-357).  Per-keyframe visibility masks (`n_touched > 0`, :311-315)
+stay on the owning rank.
 
 The collective / sharding logic is device-agnostic on purpose: the GPU path hands it RasterEngine's gradient block
 over NCCL, the CPU tests (gloo, world_size 2) hand it a stand-in gradient function and a stand-in optimiser.
@@ -22,8 +35,9 @@ from typing import Callable, Dict, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-# parameter groups in block order, with their widths per Gaussian (M = SH coefficients per Gaussian)
-GROUPS = ("means3D", "shs", "opacity", "scales", "rotations")
+from .engine import GROUPS, block_layout
+
+ACTIVATED = ("opacity", "scales", "rotations")     # groups whose raw value differs from what the rasterizer consumes
 
 
 def group_widths(sh_coeffs: int = 1) -> Dict[str, int]:
@@ -39,50 +53,116 @@ class ShardedMapper:
     """Replicated flat parameter block + Adam state; gradient exchange over torch.distributed."""
 
     def __init__(self, P: int, sh_coeffs: int = 1, device="cpu", lrs: Optional[Dict[str, float]] = None,
-                 betas=(0.9, 0.999), eps: float = 1e-15, group=None, optimizer_fn=None):
-        """optimizer_fn(mapper, grad_flat): stand-in optimiser for host-logic tests on CPU tensors.  The product path
+                 betas=(0.9, 0.999), eps: float = 1e-15, group=None, optimizer_fn=None, raw: bool = True):
+        """raw: the block holds GaussianModel's raw parameters and `view()` returns their activations (the default).
+        raw=False keeps the round-1 behaviour (the block holds what the rasterizer consumes) for host-logic tests.
+        optimizer_fn(mapper, grad_flat): stand-in optimiser for host-logic tests on CPU tensors.  The product path
         (CUDA tensors) always runs the fused lvdgs_adam_step kernel; there is no CPU implementation in this package."""
-        self.P, self.M = P, sh_coeffs
+        self.M = sh_coeffs
         self.optimizer_fn = optimizer_fn
         self.device = torch.device(device)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        widths = group_widths(sh_coeffs)
-        total = sum(widths.values()) * P
-        self.param_flat = torch.zeros(total, dtype=torch.float32, device=self.device)
-        self.exp_avg = torch.zeros_like(self.param_flat)
-        self.exp_avg_sq = torch.zeros_like(self.param_flat)
-        self.lr_flat = torch.empty_like(self.param_flat)
+        self.raw = bool(raw) and self.device.type == "cuda"
         # 3DGS / MonoGS default learning rates (the reference reads them from configs/mono/*/base_config.yaml opt_params)
-        lrs = lrs or {"means3D": 1.6e-4, "shs": 2.5e-3, "opacity": 5e-2, "scales": 1e-3, "rotations": 1e-3}
-        self.params: Dict[str, torch.Tensor] = {}
-        self.slices: Dict[str, slice] = {}
-        off = 0
-        for name in GROUPS:
-            n = widths[name] * P
-            self.slices[name] = slice(off, off + n)
-            self.params[name] = self.param_flat[off:off + n]
-            self.lr_flat[off:off + n] = lrs[name]
-            off += n
+        self.lrs = dict(lrs or {"means3D": 1.6e-4, "shs": 2.5e-3, "opacity": 5e-2, "scales": 1e-3, "rotations": 1e-3})
         self.betas, self.eps, self.t = betas, eps, 0
+        self._alloc(P)
         self.grad_norm_accum = torch.zeros(P, dtype=torch.float32, device=self.device)
         self.denom = torch.zeros(P, dtype=torch.float32, device=self.device)
         self.max_radii2D = torch.zeros(P, dtype=torch.float32, device=self.device)
+        self._zero_stream = None
+        self._zero_done = None
+
+    # ---- storage ----
+    def _alloc(self, P: int):
+        self.P = P
+        self.layout, self.total = block_layout(P, self.M, multiple=4 * self.world)
+        z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.param_flat, self.exp_avg, self.exp_avg_sq = z(self.total), z(self.total), z(self.total)
+        self._bind()
+        self.moments_sharded = False
+
+    def _bind(self):
+        self.slices = {n: slice(off, off + ln) for n, (off, ln) in self.layout.items()}
+        self.params = {n: self.param_flat[sl] for n, sl in self.slices.items()}
+        if self.raw:      # activated copies of the three groups the rasterizer does not take raw
+            self.act_layout, act_total, off = {}, 0, 0
+            for n in ACTIVATED:
+                ln = self.layout[n][1]
+                self.act_layout[n] = (off, ln)
+                off += (ln + 3) & ~3
+            self.act_flat = torch.zeros(max(off, 4), dtype=torch.float32, device=self.device)
+            self.act = {n: self.act_flat[o:o + ln] for n, (o, ln) in self.act_layout.items()}
+        self.lr_flat = torch.zeros_like(self.param_flat)      # per-element learning rate (stand-in optimisers of the CPU tests)
+        for n, sl in self.slices.items():
+            self.lr_flat[sl] = float(self.lrs[n])
+        # reduce-scatter slice of this rank
+        self.shard_len = self.total // self.world
+        self.shard = slice(self.rank * self.shard_len, (self.rank + 1) * self.shard_len)
+
+    def new_grad_block(self) -> torch.Tensor:
+        """A zeroed gradient block with this mapper's layout and padding (hand it to RasterEngine(grad_flat=...))."""
+        return torch.zeros(self.total, dtype=torch.float32, device=self.device)
 
     # ---- views of the parameter block in the rasterizer's input layout ----
     def view(self, name: str) -> torch.Tensor:
         w = group_widths(self.M)[name]
-        t = self.params[name]
+        t = self.act[name] if (self.raw and name in ACTIVATED) else self.params[name]
         if name == "shs":
             return t.view(self.P, self.M, 3)
         return t.view(self.P, w)
 
+    def raw_view(self, name: str) -> torch.Tensor:
+        return self.params[name].view(self.P, -1)
+
     def load(self, **arrays):
+        """Loads ACTIVATED values (opacity in (0,1), positive scales, rotations as given), as a scene provides them; with
+        raw storage they are converted once: logit, log, identity (GaussianModel.create_pcd does the same)."""
         for name, a in arrays.items():
-            self.params[name].copy_(torch.as_tensor(a, dtype=torch.float32).reshape(-1))
+            v = torch.as_tensor(a, dtype=torch.float32).reshape(-1).to(self.device)
+            if self.raw and name == "opacity":
+                v = torch.log(v / (1.0 - v))
+            elif self.raw and name == "scales":
+                v = torch.log(v)
+            self.params[name].copy_(v)
+        self.activate()
+
+    def _lib(self):
+        import ctypes as C
+        from . import _native
+        return C, _native, _native.lib()
+
+    def _stream(self):
+        import ctypes as C
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def activate(self):
+        """raw -> what the rasterizer consumes (sigmoid / exp / normalize), one fused kernel."""
+        if not self.raw or self.P == 0:
+            return
+        C, _native, L = self._lib()
+        rc = L.lvdgs_gaussian_activate(self.P, _native.ptr(self.params["opacity"]), _native.ptr(self.params["scales"]),
+                                       _native.ptr(self.params["rotations"]), _native.ptr(self.act["opacity"]),
+                                       _native.ptr(self.act["scales"]), _native.ptr(self.act["rotations"]), self._stream())
+        _native.check(rc, "lvdgs_gaussian_activate")
+
+    def activation_backward(self, grad_flat: torch.Tensor):
+        """gradients w.r.t. the activated values (what the backward kernel accumulated) -> w.r.t. the raw parameters."""
+        if not self.raw or self.P == 0:
+            return
+        C, _native, L = self._lib()
+        g = lambda n: _native.ptr(grad_flat[self.slices[n]])
+        rc = L.lvdgs_gaussian_activation_backward(self.P, _native.ptr(self.act["opacity"]), _native.ptr(self.act["scales"]),
+                                                  _native.ptr(self.act["rotations"]), _native.ptr(self.params["rotations"]),
+                                                  g("opacity"), g("scales"), g("rotations"), self._stream())
+        _native.check(rc, "lvdgs_gaussian_activation_backward")
 
     # ---- collectives ----
+    def _can_scatter(self) -> bool:
+        return self.world > 1 and self.param_flat.is_cuda and dist.get_backend(self.group) == "nccl"
+
     def reduce_gradients(self, grad_flat: torch.Tensor) -> torch.Tensor:
         """SUM over ranks of the contiguous gradient block (the mapping loss is a sum over views)."""
         if self.world > 1:
@@ -104,27 +184,84 @@ class ShardedMapper:
         self.max_radii2D = torch.where(visible, torch.maximum(self.max_radii2D, radii.to(torch.float32)), self.max_radii2D)
 
     # ---- optimiser ----
+    def _adam_range(self, grads: torch.Tensor, lo: int, hi: int):
+        """Fused Adam (lvdgs_adam_step) on block elements [lo, hi) with per-group learning rates; `grads` holds the
+        gradients of exactly that range."""
+        C, _native, L = self._lib()
+        ends, lr = [], []
+        for n in GROUPS:      # group ends clipped to the range, relative to its start (padding inherits the group before it)
+            off, ln = self.layout[n]
+            nxt = min((o for o, _ in self.layout.values() if o > off), default=self.total)
+            ends.append(min(max(nxt, lo), hi) - lo)
+            lr.append(float(self.lrs[n]))
+        ends[-1] = hi - lo
+        rc = L.lvdgs_adam_step(hi - lo, _native.ptr(self.param_flat[lo:hi]), _native.ptr(grads), _native.ptr(self.exp_avg[lo:hi]),
+                               _native.ptr(self.exp_avg_sq[lo:hi]), len(GROUPS), (C.c_int64 * len(GROUPS))(*ends),
+                               (C.c_float * len(GROUPS))(*lr), self.betas[0], self.betas[1], self.eps, self.t, self._stream())
+        _native.check(rc, "lvdgs_adam_step")
+
     def adam_step(self, grad_flat: torch.Tensor):
-        """Adam on the whole block with per-group learning rates: one fused kernel of the C ABI (lvdgs_adam_step).
+        """Adam on the whole block with an already reduced gradient: one fused kernel of the C ABI (lvdgs_adam_step).
         Identical inputs on every rank -> identical result, so the replicas never need a broadcast."""
         self.t += 1
         if self.optimizer_fn is not None:
             return self.optimizer_fn(self, grad_flat)
         if not self.param_flat.is_cuda:
             raise RuntimeError("ShardedMapper.adam_step: parameters must live on a CUDA device (no CPU path)")
-        import ctypes as C
-        from . import _native
-        L = _native.lib()
-        ends = (C.c_int64 * len(GROUPS))(*[self.slices[n].stop for n in GROUPS])
-        if not hasattr(self, "_lrs_c"):
-            self._lrs_c = (C.c_float * len(GROUPS))(*[float(self.lr_flat[self.slices[n].start]) for n in GROUPS])
-        rc = L.lvdgs_adam_step(self.param_flat.numel(), _native.ptr(self.param_flat), _native.ptr(grad_flat),
-                               _native.ptr(self.exp_avg), _native.ptr(self.exp_avg_sq), len(GROUPS), ends, self._lrs_c,
-                               self.betas[0], self.betas[1], self.eps, self.t,
-                               C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
-        _native.check(rc, "lvdgs_adam_step")
+        self._adam_range(grad_flat, 0, self.total)
+        self.activate()
+
+    def exchange_and_update(self, grad_flat: torch.Tensor):
+        """The exchange step of one iteration: raw-parameter chain rule, gradient SUM over the ranks, Adam, activations.
+        NCCL: reduce-scatter -> Adam on this rank's slice -> all-gather of the parameters; the gradient block is zeroed
+        for the next iteration on a side stream while the all-gather runs."""
+        self.activation_backward(grad_flat)
+        if not self._can_scatter():
+            self.reduce_gradients(grad_flat)
+            self.adam_step(grad_flat)
+            grad_flat.zero_()
+            return
+        self.t += 1
+        if not hasattr(self, "_g_shard") or self._g_shard.numel() != self.shard_len:
+            self._g_shard = torch.empty(self.shard_len, dtype=torch.float32, device=self.device)
+        dist.reduce_scatter_tensor(self._g_shard, grad_flat, op=dist.ReduceOp.SUM, group=self.group)
+        cur = torch.cuda.current_stream(self.device)
+        if self._zero_stream is None:
+            self._zero_stream = torch.cuda.Stream(self.device)
+            self._zero_done = torch.cuda.Event()
+        self._zero_stream.wait_stream(cur)                       # the reduce-scatter has consumed the block
+        with torch.cuda.stream(self._zero_stream):
+            grad_flat.zero_()
+            self._zero_done.record(self._zero_stream)
+        self._adam_range(self._g_shard, self.shard.start, self.shard.stop)
+        self.moments_sharded = True                              # only this rank's slice of exp_avg / exp_avg_sq is current
+        dist.all_gather_into_tensor(self.param_flat, self.param_flat[self.shard], group=self.group)   # in place
+        self.activate()
+        cur.wait_event(self._zero_done)
+
+    def gather_moments(self):
+        """Makes exp_avg / exp_avg_sq complete on every rank again (before prune / densify move rows around)."""
+        if self.moments_sharded and self.world > 1:
+            for m in (self.exp_avg, self.exp_avg_sq):
+                dist.all_gather_into_tensor(m, m[self.shard].clone(), group=self.group)
+        self.moments_sharded = False
 
     # ---- map maintenance ----
+    def _rows(self, flat):
+        w = group_widths(self.M)
+        return [flat[self.slices[n]].view(self.P, w[n]) for n in GROUPS]
+
+    def _rebuild(self, P2: int, new_rows, stats):
+        """Installs new per-group row tensors (params, exp_avg, exp_avg_sq: 3 x 5 tensors of P2 rows) as the block."""
+        ng = len(GROUPS)
+        self._alloc(P2)
+        for i, flat in enumerate((self.param_flat, self.exp_avg, self.exp_avg_sq)):
+            for j, n in enumerate(GROUPS):
+                if P2:
+                    flat[self.slices[n]].copy_(new_rows[i * ng + j].reshape(-1))
+        self.grad_norm_accum, self.denom, self.max_radii2D = stats
+        self.activate()
+
     def prune(self, keep: torch.Tensor) -> int:
         """GaussianModel.prune_points on the replicated block (callers utils/slam_backend.py:128-145,322-339): drops the
         rows where `keep` is zero from every parameter group, both Adam moments and the densification statistics -- one
@@ -134,84 +271,55 @@ class ShardedMapper:
         if not self.param_flat.is_cuda:
             raise RuntimeError("ShardedMapper.prune: parameters must live on a CUDA device (no CPU path)")
         from .slam_ops import compact_rows
-        widths = group_widths(self.M)
-        srcs = []
-        for flat in (self.param_flat, self.exp_avg, self.exp_avg_sq):
-            srcs += [flat[self.slices[n]].view(self.P, widths[n]) for n in GROUPS]
+        self.gather_moments()
+        srcs = self._rows(self.param_flat) + self._rows(self.exp_avg) + self._rows(self.exp_avg_sq)
         srcs += [self.grad_norm_accum.view(self.P, 1), self.denom.view(self.P, 1), self.max_radii2D.view(self.P, 1)]
         new = compact_rows(keep, srcs)
         P2 = new[0].shape[0]
         ng = len(GROUPS)
-        lr_of = {n: float(self.lr_flat[self.slices[n].start]) if self.P else 0.0 for n in GROUPS}
-        flats = [torch.cat([t.reshape(-1) for t in new[i * ng:(i + 1) * ng]]) if P2 else
-                 torch.zeros(0, dtype=torch.float32, device=self.device) for i in range(3)]
-        self.param_flat, self.exp_avg, self.exp_avg_sq = flats
-        self.grad_norm_accum, self.denom, self.max_radii2D = (t.reshape(-1) for t in new[3 * ng:])
-        self.lr_flat = torch.empty_like(self.param_flat)
-        self.P, off = P2, 0
-        for name in GROUPS:
-            n = widths[name] * P2
-            self.slices[name] = slice(off, off + n)
-            self.params[name] = self.param_flat[off:off + n]
-            self.lr_flat[off:off + n] = lr_of[name]
-            off += n
+        self._rebuild(P2, new[:3 * ng], tuple(t.reshape(-1) for t in new[3 * ng:]))
         return P2
 
     def densify_clone(self, index: torch.Tensor, overrides: Optional[Dict[str, torch.Tensor]] = None) -> int:
         """Appends copies of the Gaussians `index` (int64) to the replicated block -- GaussianModel.densify_and_clone, and
         with `overrides` = {"means3D": new positions, "scales": new scales} the append half of densify_and_split (callers
-        utils/slam_backend.py:359-376).  New rows get zero Adam moments and zero densification statistics, like
-        densification_postfix.  The rows of all groups are gathered in one launch (lvdgs_gather_rows) straight into the new
-        block.  Every rank must call it with identical arguments.  Returns the new number of Gaussians."""
+        utils/slam_backend.py:359-376).  Overrides are in the block's own parametrisation (raw log-scales with raw=True).
+        New rows get zero Adam moments and zero densification statistics, like densification_postfix.  The rows of all
+        groups are gathered in one launch (lvdgs_gather_rows).  Every rank must call it with identical arguments.
+        Returns the new number of Gaussians."""
         if not self.param_flat.is_cuda:
             raise RuntimeError("ShardedMapper.densify_clone: parameters must live on a CUDA device (no CPU path)")
         from .slam_ops import gather_rows
+        self.gather_moments()
         widths = group_widths(self.M)
         k = int(index.numel())
-        P2 = self.P + k
-        lr_of = {n: float(self.lr_flat[self.slices[n].start]) if self.P else 0.0 for n in GROUPS}
-        new_flat = torch.empty(sum(widths.values()) * P2, dtype=torch.float32, device=self.device)
-        new_m, new_v = torch.zeros_like(new_flat), torch.zeros_like(new_flat)
-        new_slices, off, tails, srcs = {}, 0, [], []
-        for name in GROUPS:
-            w = widths[name]
-            new_slices[name] = slice(off, off + w * P2)
-            old = slice(self.slices[name].start, self.slices[name].stop)
-            new_flat[off:off + w * self.P] = self.param_flat[old]
-            new_m[off:off + w * self.P] = self.exp_avg[old]
-            new_v[off:off + w * self.P] = self.exp_avg_sq[old]
-            tails.append(new_flat[off + w * self.P:off + w * P2].view(k, w))
-            srcs.append(self.param_flat[old].view(self.P, w))
-            off += w * P2
-        gather_rows(index, srcs, out=tails)
+        old_P = self.P
+        old = (self._rows(self.param_flat), self._rows(self.exp_avg), self._rows(self.exp_avg_sq))
+        tails = [torch.empty(k, widths[n], dtype=torch.float32, device=self.device) for n in GROUPS]
+        gather_rows(index, old[0], out=tails)
         for name, t in (overrides or {}).items():
             tails[GROUPS.index(name)].copy_(t.reshape(k, widths[name]))
+        zero = lambda n: torch.zeros(k, widths[n], dtype=torch.float32, device=self.device)
+        rows = [torch.cat([o, t]) for o, t in zip(old[0], tails)]
+        rows += [torch.cat([o, zero(n)]) for o, n in zip(old[1], GROUPS)]
+        rows += [torch.cat([o, zero(n)]) for o, n in zip(old[2], GROUPS)]
         pad = torch.zeros(k, dtype=torch.float32, device=self.device)
-        self.grad_norm_accum = torch.cat([self.grad_norm_accum, pad])
-        self.denom = torch.cat([self.denom, pad])
-        self.max_radii2D = torch.cat([self.max_radii2D, pad])
-        self.param_flat, self.exp_avg, self.exp_avg_sq = new_flat, new_m, new_v
-        self.lr_flat = torch.empty_like(new_flat)
-        self.P, self.slices = P2, new_slices
-        for name in GROUPS:
-            self.params[name] = self.param_flat[self.slices[name]]
-            self.lr_flat[self.slices[name]] = lr_of[name]
-        return P2
+        stats = (torch.cat([self.grad_norm_accum, pad]), torch.cat([self.denom, pad]), torch.cat([self.max_radii2D, pad]))
+        self._rebuild(old_P + k, rows, stats)
+        return self.P
 
     # ---- one mapping iteration ----
     def step(self, n_views: int, render_and_grad: Callable[[int], None], grad_flat: torch.Tensor,
              zero: Optional[Callable[[], None]] = None, extra_views: Sequence[int] = ()):
-        """render_and_grad(k) must ADD view k's parameter gradients into `grad_flat`.
+        """render_and_grad(k) must ADD view k's parameter gradients (with respect to the values `view()` returns) into
+        `grad_flat`, which must be zero on entry the first time; the exchange step leaves it zeroed for the next call.
         `extra_views`: the reference's 2 random older keyframes (utils/slam_backend.py:275); the caller draws them
         with a generator seeded identically on every rank, they are sharded like the window."""
         if zero is not None:
             zero()
-        else:
-            grad_flat.zero_()
         views = list(range(n_views)) + list(extra_views)
         mine = [views[i] for i in shard_keyframes(len(views), self.world, self.rank)]
         for k in mine:
             render_and_grad(k)
-        self.reduce_gradients(grad_flat)
-        self.adam_step(grad_flat)
+        self.exchange_and_update(grad_flat)
         return mine

@@ -50,6 +50,12 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads the oracle uses from now on (torchrun sets OMP_NUM_THREADS=1 in every rank's environment)."""
+    lib().oracle_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 def _f(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
 

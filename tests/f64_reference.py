@@ -55,8 +55,10 @@ def eval_sh(deg, sh, dirs):
 
 
 def forward(means3D, scales, rotations, opacities, shs, tau, *, W2C, Pr, campos, bg, W, H, tanfovx, tanfovy,
-            sh_degree, fwd, colors_precomp=None):
-    """W2C, Pr: math-convention 4x4 float64 (NOT transposed). fwd: oracle forward dict (constants)."""
+            sh_degree, fwd, colors_precomp=None, valid_cache=None):
+    """W2C, Pr: math-convention 4x4 float64 (NOT transposed). fwd: oracle forward dict (constants).
+    valid_cache: optional dict; the per-tile blend decisions (power <= 0, alpha >= 1/255) are stored in it on the first
+    call and reused afterwards, so that finite differences do not step across those discontinuities."""
     dt = torch.float64
     V = SE3_exp(tau) @ W2C
     Pj = Pr @ V
@@ -119,6 +121,8 @@ def forward(means3D, scales, rotations, opacities, shs, tau, *, W2C, Pr, campos,
                 alpha = torch.clamp_max(opacities[ids].reshape(1, -1) * torch.exp(power), 0.99)
                 k = torch.arange(r1 - r0)[None, :]
                 valid = (power <= 0) & (alpha >= 1.0 / 255.0) & (k < ncontrib[y0:y1, x0:x1].reshape(-1, 1))
+                if valid_cache is not None:
+                    valid = valid_cache.setdefault((ty, tx), valid.detach())
                 aeff = torch.where(valid, alpha, torch.zeros_like(alpha))
                 Tincl = torch.cumprod(1 - aeff, 1)
                 Texcl = torch.cat([torch.ones(npx, 1, dtype=dt), Tincl[:, :-1]], 1)

@@ -87,3 +87,33 @@ def run_oracle(sc, cam, bg, grads=None, flags=0, use_precomp_color=False, use_pr
 def rel_err(a, b):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+def tainted_gaussians(fwd, thr=1e-5):
+    """Gaussians that can reach a knife-edge pixel (oracle margin <= thr): in that pixel's tile list and with the pixel
+    inside their 3-sigma square.  Their blend decisions there legitimately depend on the last ulp of exp(), so gradient
+    comparisons set them aside (as the forward comparison sets the pixels aside)."""
+    W, H = fwd["W"], fwd["H"]
+    gx = (W + 15) // 16
+    tainted = np.zeros(fwd["P"], bool)
+    ys, xs = np.nonzero(~(fwd["margin"] > thr))
+    for y, x in zip(ys, xs):
+        r0, r1 = fwd["ranges"][(y // 16) * gx + x // 16]
+        ids = fwd["point_list"][r0:r1]
+        m, r = fwd["means2D"][ids], fwd["radii"][ids].astype(np.float32) + 1.0
+        tainted[ids[(np.abs(m[:, 0] - x) <= r) & (np.abs(m[:, 1] - y) <= r)]] = True
+    return tainted
+
+
+def grad_mismatch(a, b, rows=None, rtol=1e-3):
+    """Fraction of elements violating north_star's gradient bar PER ELEMENT: |a - b| <= rtol |b| + rtol * median|b|
+    (median over the non-zero reference elements: the absolute floor for elements that are themselves rounding noise).
+    rows: optional boolean mask of the rows (Gaussians) to compare."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    a = a.reshape(b.shape)
+    if rows is not None:
+        a, b = a[rows], b[rows]
+    nz = np.abs(b[b != 0])
+    atol = rtol * (np.median(nz) if nz.size else 0.0)
+    bad = np.abs(a - b) > rtol * np.abs(b) + atol
+    return float(bad.mean()) if bad.size else 0.0

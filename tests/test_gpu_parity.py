@@ -10,9 +10,13 @@ import torch
 
 import oracle
 from lvdgs import synth
-from gpu_harness import run_cuda, run_oracle, rel_err
+from gpu_harness import run_cuda, run_oracle, rel_err, tainted_gaussians, grad_mismatch
 
 pytestmark = pytest.mark.gpu
+
+# float32 sums of +- terms far larger than their result (|result| << sum |terms|) carry rounding noise above any
+# relative bar on the result: at most this fraction of the elements of a gradient tensor may miss the per-element bar
+GRAD_OUTLIER_FRAC = 1e-4
 
 CASES = {
     "vga50k": dict(cam="vga", N=50_000, sh=0, bg=(0.0, 0.0, 0.0)),          # BASELINE configs[0]
@@ -102,16 +106,21 @@ def test_blend_forward(case):
 
 
 def test_backward(case):
+    """north_star: gradients within 1e-3 relative -- checked PER ELEMENT (|a - b| <= 1e-3 |b| + 1e-3 median|b|) on every
+    Gaussian that cannot reach a knife-edge pixel; the pose gradient (a sum over all Gaussians) per component."""
     g, go, f = case["g"], case["go"], case["fwd"]
-    frac_bad = 1.0 - (f["margin"] > 1e-5).mean()
-    tol = 1e-3 + 20 * frac_bad      # knife-edge pixels perturb the sums slightly; still ~1e-3
-    assert rel_err(g["means2D"][:, :2], go["dL_dmean2D"]) < tol
+    clean = ~tainted_gaussians(f)
+    assert clean.mean() > 0.5, clean.mean()          # ~99 % on the small cases, ~83 % at 1-2 M Gaussians
+    pairs = [("means2D", g["means2D"][:, :2], go["dL_dmean2D"]), ("means3D", g["means3D"], go["dL_dmeans3D"]),
+             ("opacity", g["opacities"].reshape(-1), go["dL_dopacity"]), ("scales", g["scales"], go["dL_dscales"]),
+             ("rotations", g["rotations"], go["dL_drots"]), ("shs", g["shs"], go["dL_dsh"])]
+    for name, a, b in pairs:
+        frac = grad_mismatch(a, b, rows=clean)
+        assert frac <= GRAD_OUTLIER_FRAC, f"{name}: {frac:.2e} of the elements outside 1e-3 relative"
     assert np.all(g["means2D"][:, 2] == 0)
-    assert rel_err(g["means3D"], go["dL_dmeans3D"]) < tol
-    assert rel_err(g["opacities"].reshape(-1), go["dL_dopacity"]) < tol
-    assert rel_err(g["scales"], go["dL_dscales"]) < tol
-    assert rel_err(g["rotations"], go["dL_drots"]) < tol
-    assert rel_err(g["shs"], go["dL_dsh"]) < tol
+    # the pose gradient sums every Gaussian, tainted ones included: the knife-edge pairs enter with their full weight
+    frac_bad = 1.0 - (f["margin"] > 1e-5).mean()
+    tol = 1e-3 + 20 * frac_bad
     assert rel_err(g["rho"], go["grad_rho"]) < tol
     assert rel_err(g["theta"], go["grad_theta"]) < tol
 

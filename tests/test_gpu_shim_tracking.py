@@ -13,75 +13,17 @@ from gaussian_splatting.gaussian_renderer import render, render_with_custom_reso
 pytestmark = pytest.mark.gpu
 
 
-# ---- restated from /root/reference/utils/pose_utils.py:11-87 (the consumer of the pose gradients) ----
-def skew(x):
-    s = torch.zeros(3, 3, device=x.device, dtype=x.dtype)
-    s[0, 1], s[0, 2], s[1, 0], s[1, 2], s[2, 0], s[2, 1] = -x[2], x[1], x[2], -x[0], -x[1], x[0]
-    return s
+# The reference's own Camera / SE3_exp / update_pose (utils/camera_utils.py:8-166, utils/pose_utils.py:56-87) when
+# /root/reference is mounted, else the restatements that tests/test_reference_pin.py pins against them.
+import ref_conventions as rc
+
+_PU, _SU, _CU, REF_SOURCE = rc.load()
+SE3_exp, update_pose = _PU.SE3_exp, _PU.update_pose
+Gaussians, Pipe = rc.Gaussians, rc.Pipe
 
 
-def SE3_exp(tau):
-    rho, theta = tau[:3], tau[3:]
-    W = skew(theta); W2 = W @ W
-    ang = torch.norm(theta)
-    I = torch.eye(3, device=tau.device, dtype=tau.dtype)
-    if ang < 1e-5:
-        R = I + W + 0.5 * W2; V = I + 0.5 * W + W2 / 6.0
-    else:
-        R = I + (torch.sin(ang) / ang) * W + ((1 - torch.cos(ang)) / ang ** 2) * W2
-        V = I + W * ((1 - torch.cos(ang)) / ang ** 2) + W2 * ((ang - torch.sin(ang)) / ang ** 3)
-    T = torch.eye(4, device=tau.device, dtype=tau.dtype)
-    T[:3, :3] = R; T[:3, 3] = V @ rho
-    return T
-
-
-class Cam(torch.nn.Module):
-    """Fields of utils/camera_utils.py:Camera that render() reads (:42-56,106-120)."""
-
-    def __init__(self, c: synth.Cam, dev):
-        super().__init__()
-        self.R = torch.tensor(c.R, dtype=torch.float32, device=dev)
-        self.T = torch.tensor(c.T, dtype=torch.float32, device=dev)
-        self.FoVx, self.FoVy = c.FoVx, c.FoVy
-        self.image_height, self.image_width = c.image_height, c.image_width
-        self.projection_matrix = torch.tensor(c.projection_matrix, device=dev)
-        self.cam_rot_delta = torch.nn.Parameter(torch.zeros(3, device=dev))
-        self.cam_trans_delta = torch.nn.Parameter(torch.zeros(3, device=dev))
-
-    @property
-    def world_view_transform(self):
-        Rt = torch.eye(4, device=self.R.device)
-        Rt[:3, :3] = self.R; Rt[:3, 3] = self.T
-        return Rt.transpose(0, 1)
-
-    @property
-    def full_proj_transform(self):
-        return self.world_view_transform.unsqueeze(0).bmm(self.projection_matrix.unsqueeze(0)).squeeze(0)
-
-    @property
-    def camera_center(self):
-        return self.world_view_transform.inverse()[3, :3]
-
-
-def update_pose(cam):
-    tau = torch.cat([cam.cam_trans_delta, cam.cam_rot_delta]).detach()
-    T = torch.eye(4, device=tau.device); T[:3, :3] = cam.R; T[:3, 3] = cam.T
-    new = SE3_exp(tau) @ T
-    cam.R, cam.T = new[:3, :3], new[:3, 3]
-    cam.cam_rot_delta.data.fill_(0); cam.cam_trans_delta.data.fill_(0)
-
-
-class Gaussians:
-    def __init__(self, sc, dev):
-        t = lambda a: torch.tensor(a, device=dev)
-        self.get_xyz, self.get_opacity, self.get_scaling = t(sc["means3D"]), t(sc["opacities"]), t(sc["scales"])
-        self.get_rotation, self.get_features = t(sc["rotations"]), t(sc["shs"])
-        self.active_sh_degree = 0
-
-
-class Pipe:
-    convert_SHs_python = False
-    compute_cov3D_python = False
+def Cam(c: synth.Cam, dev):
+    return rc.make_camera(_CU, c, dev)
 
 
 def test_render_dict_and_custom_resolution():
@@ -126,7 +68,7 @@ def test_tracking_loop_recovers_a_perturbed_pose():
     cam = Cam(c, dev)
     tau0 = torch.tensor([0.03, -0.02, 0.04, math.radians(0.4), math.radians(-0.3), math.radians(0.2)], device=dev)
     T0 = SE3_exp(tau0) @ torch.eye(4, device=dev)
-    cam.R, cam.T = T0[:3, :3].contiguous(), T0[:3, 3].contiguous()
+    cam.update_RT(T0[:3, :3].contiguous(), T0[:3, 3].contiguous())
 
     def pose_err():
         return float(torch.norm(cam.T - true_cam.T)), float(torch.norm(cam.R - true_cam.R))
@@ -139,8 +81,9 @@ def test_tracking_loop_recovers_a_perturbed_pose():
         loss = (pkg["opacity"] * (pkg["render"] - target).abs()).mean()      # get_loss_tracking_rgb, utils/slam_utils.py:53-62
         opt.zero_grad()
         loss.backward()
-        opt.step()
-        update_pose(cam)
+        with torch.no_grad():
+            opt.step()
+            update_pose(cam)
         losses.append(float(loss))
     e1 = pose_err()
     assert losses[-1] < 0.35 * losses[0], (losses[0], losses[-1])

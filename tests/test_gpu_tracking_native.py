@@ -1,7 +1,8 @@
 """The device-resident tracking loop (lvdgs.tracking.PoseTracker: rasterizer + fused loss + lvdgs_pose_step) against the
 reference's formulation of the same loop -- torch.optim.Adam on (cam_rot_delta, cam_trans_delta, exposure_a,
-exposure_b) + update_pose (utils/slam_frontend.py:1466-1521, utils/pose_utils.py:56-87), restated in
-tests/test_gpu_shim_tracking.py."""
+exposure_b) + update_pose (utils/slam_frontend.py:1466-1521, utils/pose_utils.py:56-87): the reference's own Camera /
+SE3_exp / update_pose when /root/reference is mounted, else the restatements pinned against them
+(tests/ref_conventions.py, tests/test_reference_pin.py)."""
 import ctypes as C
 import math
 
@@ -70,13 +71,15 @@ def test_native_tracking_loop_follows_the_reference_loop():
     iters = 40
     # reference formulation
     cam = Cam(c, dev)
-    cam.R, cam.T = T0[:3, :3].contiguous(), T0[:3, 3].contiguous()
+    cam.update_RT(T0[:3, :3].contiguous(), T0[:3, 3].contiguous())
     opt = torch.optim.Adam([{"params": [cam.cam_rot_delta], "lr": 0.003}, {"params": [cam.cam_trans_delta], "lr": 0.001}])
     ref_losses = []
     for it in range(iters):
         pkg = render(cam, pc, Pipe(), bg)
         loss = (pkg["opacity"] * (pkg["render"] - target).abs()).mean()
-        opt.zero_grad(); loss.backward(); opt.step(); update_pose(cam)
+        opt.zero_grad(); loss.backward()
+        with torch.no_grad():
+            opt.step(); update_pose(cam)
         ref_losses.append(float(loss))
     # device-resident loop
     tr = trk.PoseTracker(40_000, c.image_width, c.image_height, c.tanfovx, c.tanfovy, device=dev, lr_rot=0.003, lr_trans=0.001,
@@ -84,7 +87,7 @@ def test_native_tracking_loop_follows_the_reference_loop():
     args = (pc.get_xyz, pc.get_opacity, pc.get_scaling, pc.get_rotation, pc.get_features, target)
     # (a) one iteration from the start pose: same loss, same pose gradient as the plugin + autograd path
     cam1 = Cam(c, dev)
-    cam1.R, cam1.T = T0[:3, :3].contiguous(), T0[:3, 3].contiguous()
+    cam1.update_RT(T0[:3, :3].contiguous(), T0[:3, 3].contiguous())
     pkg = render(cam1, pc, Pipe(), bg)
     loss1 = (pkg["opacity"] * (pkg["render"] - target).abs()).mean()
     loss1.backward()

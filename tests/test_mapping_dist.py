@@ -35,13 +35,13 @@ def torch_adam(m, grad):
 def _fake_view_grad(mapper, k, P):
     """Deterministic stand-in for 'render view k and back-propagate': depends on the view and on the parameters."""
     g = torch.Generator().manual_seed(100 + k)
-    base = torch.randn(mapper.param_flat.numel(), generator=g)
+    base = torch.randn(14 * P + 64, generator=g)[:mapper.param_flat.numel()]      # independent of the tail padding
     return base * 1e-2 + 0.1 * torch.sin(mapper.param_flat * (k + 1))
 
 
 def _init_params(mapper, P):
     g = torch.Generator().manual_seed(7)
-    mapper.param_flat.copy_(torch.randn(mapper.param_flat.numel(), generator=g))
+    mapper.param_flat.copy_(torch.randn(14 * P + 64, generator=g)[:mapper.param_flat.numel()])
 
 
 def _run_rank(rank, world, port, P, n_views, iters, out_dir):
@@ -91,7 +91,8 @@ def test_two_ranks_match_single_process(tmp_path):
         extra = [n_views + int(x) for x in torch.randperm(4, generator=torch.Generator().manual_seed(it))[:2]]
         ref.step(n_views, lambda k: grad.add_(_fake_view_grad(ref, k, P)), grad, extra_views=extra)
     # float32 sums in a different association (per-rank partial sums, then all-reduce): equal to rounding
-    assert torch.allclose(r0["params"], ref.param_flat, rtol=1e-5, atol=1e-6)
+    n = ref.param_flat.numel()                  # the 2-rank block carries up to 4 more floats of tail padding (reduce-scatterable)
+    assert torch.allclose(r0["params"][:n], ref.param_flat, rtol=1e-5, atol=1e-6)
     # densification side-band: SUM of norms / counts, MAX of radii
     assert torch.equal(r0["accum"], r1["accum"]) and torch.equal(r0["radii"], r1["radii"])
     expect_denom = torch.full((P,), float(iters))
@@ -100,17 +101,23 @@ def test_two_ranks_match_single_process(tmp_path):
 
 
 def test_block_layout_matches_engine_gradient_block():
-    """The mapper's parameter block and RasterEngine.grad_flat use the same group order and widths, so the
-    all-reduced gradient block can be consumed by adam_step without any repacking."""
+    """The mapper's parameter block and RasterEngine.grad_flat use the same layout (lvdgs.engine.block_layout: group order,
+    widths, 16-byte aligned group starts), so the reduced gradient block is consumed by adam_step without repacking."""
+    from lvdgs.engine import block_layout
     P, M = 10, 4
     m = ShardedMapper(P, sh_coeffs=M, device="cpu")
+    layout, total = block_layout(P, M)
     w = group_widths(M)
     off = 0
     for name in ("means3D", "shs", "opacity", "scales", "rotations"):
-        assert m.slices[name] == slice(off, off + w[name] * P)
-        off += w[name] * P
+        assert m.slices[name] == slice(off, off + w[name] * P) == slice(layout[name][0], layout[name][0] + layout[name][1])
+        off += (w[name] * P + 3) // 4 * 4
+    assert m.param_flat.numel() == total == off
     assert m.view("shs").shape == (P, M, 3) and m.view("rotations").shape == (P, 4)
     assert m.view("means3D").data_ptr() == m.param_flat.data_ptr()
+    # a reduce-scatterable block: the padded total is a multiple of 4 x world
+    for world in (2, 3, 8):
+        assert block_layout(257, 1, multiple=4 * world)[1] % (4 * world) == 0
 
 
 def test_cpu_parameters_without_stand_in_optimizer_raise():
