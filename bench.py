@@ -34,6 +34,7 @@ import numpy as np
 # keep stdout to the single JSON line the driver parses: NCCL prints its version banner there at VERSION level
 if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # whatever NCCL logs (its banner included) goes to stderr
 
 METRIC = "fwd+bwd render Mpix/s at 1241x376, 500k Gaussians"
 CPU_BASELINE_DETAIL = ("C/OpenMP restatement of the reference's algorithm (oracle/raster_oracle.c), not the pure-torch "
@@ -401,6 +402,78 @@ def main():
     e2e_val = wl["views"] * H * W / (e2e_ms * 1e-3) / 1e6
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---------------- e2e over the C ABI engine: same host buffers, same copies, views pipelined ----------------
+    # The plugin surface above has to follow the reference's single-stream program order (all renders, one backward).  A
+    # caller written against the C ABI (lvdgs.engine.RasterEngine) can overlap the views; this is that path with the SAME
+    # per-step host traffic: H2D of every view's target image / depth / camera from pinned memory, the fused mapping loss
+    # (lvdgs_fused_loss) between forward and backward, D2H of every view's loss and pose gradient.
+    from lvdgs import slam_ops as _so
+    # one staging slot per view of the rank (7.5 MB each): every upload of a step is queued on the copy stream up front and
+    # only waits for the previous step's use of its own slot
+    NS = len(my_views)
+    st_c = [dict(img=torch.empty(3, H, W, device=dev), dep=torch.empty(1, H, W, device=dev), cam=torch.empty(52, device=dev),
+                 ready=torch.cuda.Event(), free=torch.cuda.Event(), g_img=torch.empty(3, H, W, device=dev),
+                 g_dep=torch.empty(1, H, W, device=dev), out=torch.empty(4, device=dev)) for _ in range(NS)]
+    res_c = torch.zeros(len(my_views), 8).pin_memory()
+
+    class _StagedCamera:
+        """ViewCamera over a staging slot: the five device arrays are views into the 52 floats copied from the host."""
+        def __init__(self, cam, st):
+            self.W, self.H, self.tanfovx, self.tanfovy = cam.image_width, cam.image_height, cam.tanfovx, cam.tanfovy
+            c_ = st["cam"]
+            self.view, self.proj, self.proj_raw, self.campos, self.bg = c_[0:16], c_[16:32], c_[32:48], c_[48:51], bgt
+
+    staged = [[_StagedCamera(cams[k], st_c[j]) for j, k in enumerate(my_views)]]
+
+    def prefetch_c(j):
+        st, hb = st_c[j], host[my_views[j]]
+        copy_stream.wait_event(st["free"])
+        with torch.cuda.stream(copy_stream):
+            st["img"].copy_(hb["img"], non_blocking=True); st["dep"].copy_(hb["dep"], non_blocking=True)
+            st["cam"].copy_(hb["cam"], non_blocking=True)
+            st["ready"].record(copy_stream)
+
+    def upstream_c(j, slot):
+        """Runs on the backward stream after view j's forward: loss + upstream gradients from the staged targets."""
+        st = st_c[j]
+        _so.fused_loss_into(slot.color, slot.depth, st["img"], st["dep"], st["g_img"], st["g_dep"], st["out"],
+                            rgb_boundary_threshold=-1.0, w_rgb=0.9, w_depth=0.1)
+        res_c[j, 0:1].copy_(st["out"][0:1], non_blocking=True)
+        return st["g_img"], st["g_dep"], None
+
+    def after_view_c(j, slot):
+        res_c[j, 1:7].copy_(slot.g_tau, non_blocking=True)
+        st_c[j]["free"].record(torch.cuda.current_stream())           # targets + camera of this slot consumed (fwd and bwd)
+
+    def step_c_abi():
+        args_ = [mapper.view(k) for k in ("means3D", "opacity", "scales", "rotations", "shs")]
+        for j in range(NS):
+            prefetch_c(j)
+        # the forward stream waits for view j's camera right before the view is launched; the backward stream (loss) follows it
+        eng.run_views(staged[0], *args_, upstream_c, on_view=after_view_c,
+                      before_view=lambda j: eng.s_fwd.wait_event(st_c[j]["ready"]))
+        mapper.exchange_and_update(eng.grad_flat)
+        torch.cuda.current_stream().synchronize()                      # the step's results are on the host
+
+    for _ in range(max(3, args.warmup)):
+        step_c_abi()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_c_abi()
+    e1.record()
+    barrier()
+    c_ms = e0.elapsed_time(e1) / args.steps
+    tms = torch.tensor([c_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    c_ms = float(tms.item())
+    e2e_c_abi = {"value": wl["views"] * H * W / (c_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": c_ms,
+                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": res_c.numel() * 4,
+                 "path": "lvdgs.engine.RasterEngine.run_views over the C ABI (forward of view k+1 overlaps backward of view k) + "
+                         "lvdgs_fused_loss between them + ShardedMapper.exchange_and_update; per view H2D of target image / depth / "
+                         "camera from pinned memory on a copy stream, D2H of loss and pose gradient"}
+
     # ---------------- per-kernel device times + roofline (rank 0, outside the timed regions) ----------------
     roof, kernels = None, []
     if rank == 0:
@@ -529,6 +602,7 @@ def main():
                         "d2h_bytes_per_step": d2h, "path": "diff_gaussian_rasterization.GaussianRasterizer (autograd) + "
                                 + ("torch L1 loss" if torch_loss else "lvdgs.slam_ops.fused_loss (mapping rgbd loss)") + ", losses summed over the window and one backward (as utils/slam_backend.py:167-306) + torch Adam; "
                                 "H2D of the next view prefetched on a copy stream"},
+                "e2e_c_abi": e2e_c_abi,
                 "gpu_launches": launches, "mapping_iters_per_s": 1e3 / ms, "ms_per_step_by_rank": ms_per_rank,
                 "per_view_unpipelined": per_view, "mapping_1m": mapping_1m, "clocks": clocks, "roofline": roof,
                 "kernels": kernels, "cpu_baseline": cpu, "tracking": tracking}

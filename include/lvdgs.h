@@ -108,6 +108,10 @@ int lvdgs_set_device(int device);
 /* kernels launched by this library since the last reset (bench.py's gpu_launches) */
 int64_t lvdgs_launch_count(void);
 void lvdgs_reset_launch_count(void);
+/* forwards of the calling thread whose speculatively launched tail had to be repeated (capacity hint too small, or a tile
+ * list longer than the recent frames of the same device and image size suggested) -- a cost counter, never a correctness
+ * matter */
+int64_t lvdgs_tail_rerun_count(void);
 
 /*
  * Per-launch device timing for bench.py's roofline: between begin and end every kernel launch of this library is
@@ -241,6 +245,22 @@ int lvdgs_fused_loss(int32_t width, int32_t height, const float *color, const fl
                      const float *gt_color, const float *gt_depth, const float *grad_mask, const float *exposure,
                      float rgb_boundary_threshold, float w_rgb, float w_depth, int32_t flags, float *g_color,
                      float *g_depth, float *g_opacity, float *out, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Row N3, the masked mapping loss LVD-GS runs when a keyframe carries a static mask (utils/slam_backend.py:199-261):
+ * dynamic pixels (static_mask == 0) are painted with `background` in both the render and the ground truth, then
+ *   loss = (1 - lambda_dssim) * l1_loss(mi, mg) + lambda_dssim * (1 - ssim(mi, mg))
+ *        + depth_lambda * mean_{static & mono > 0 & D > 0} |D - mono|              (dropped when that set is empty)
+ * with gaussian_splatting.utils.loss_utils' l1_loss / ssim (11x11 Gaussian window, sigma 1.5, zero padding).
+ * image / gt_image [3,H,W]; static_mask uint8 [H,W] or NULL (all static); background [3]; depth / mono_depth [H,W] or NULL.
+ * Outputs: g_image [3,H,W] = dL/dimage, g_depth [H,W] (NULL ok), out[8] (device) = {loss, mean SSIM, mean |mi - mg|,
+ * depth mean, depth pixel count, ...}.  Deterministic.  workspace: zero-filled before its first use.
+ */
+size_t lvdgs_masked_ssim_loss_workspace_bytes(int32_t width, int32_t height);
+int lvdgs_masked_ssim_loss(int32_t width, int32_t height, const float *image, const float *gt_image, const uint8_t *static_mask,
+                           const float *background, const float *depth, const float *mono_depth, float lambda_dssim,
+                           float depth_lambda, float *g_image, float *g_depth, float *out, void *workspace, size_t workspace_bytes,
+                           void *stream);
 
 /*
  * Row N4.  Keyframe covisibility from per-Gaussian visibility (n_touched > 0), replacing the logical_and / logical_or

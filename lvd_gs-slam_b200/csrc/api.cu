@@ -13,6 +13,7 @@ namespace lvdgs {
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
 thread_local int g_debug_sync = 0;
+static thread_local int64_t t_tail_reruns = 0;     // forwards of this thread whose speculative tail had to be repeated
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -23,11 +24,11 @@ void set_error(const char *fmt, ...) {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- optional per-launch profiler: one CUDA event after every launch, on the launching stream ----
+// The profiler belongs to the thread that switched it on: other threads (another engine, another device) launch unprofiled.
 struct ProfEntry { const char *name; cudaEvent_t ev; cudaEvent_t pre; };
-static std::vector<ProfEntry> g_prof;
-static bool g_prof_on = false;
-
-static cudaEvent_t g_prof_pending_pre = nullptr;
+static thread_local std::vector<ProfEntry> g_prof;
+static thread_local bool g_prof_on = false;
+static thread_local cudaEvent_t g_prof_pending_pre = nullptr;
 
 int profile_pre(cudaStream_t s) {
     if (!g_prof_on) return 0;
@@ -138,6 +139,7 @@ int lvdgs_version(void) { return 100; }
 const char *lvdgs_last_error(void) { return g_err; }
 int lvdgs_set_device(int device) { LVDGS_CHECK(cudaSetDevice(device)); return 0; }
 int64_t lvdgs_launch_count(void) { return g_launches.load(); }
+int64_t lvdgs_tail_rerun_count(void) { return t_tail_reruns; }
 void lvdgs_reset_launch_count(void) { g_launches.store(0); }
 
 int lvdgs_profile_begin(void *stream) {
@@ -174,17 +176,32 @@ int lvdgs_get_geom_layout(int32_t P, lvdgs_geom_layout *out) { if (!out) return 
 int lvdgs_get_binning_layout(int64_t R, lvdgs_binning_layout *out) { if (!out) return 1; binning_layout(R, *out); return 0; }
 int lvdgs_get_img_layout(int32_t W, int32_t H, lvdgs_img_layout *out) { if (!out) return 1; img_layout(W, H, *out); return 0; }
 
-// pinned slot + event for the asynchronous read-back of the instance count (one per host thread, created once)
-static thread_local uint32_t *t_pinned_R = nullptr;
-static thread_local cudaEvent_t t_R_event = nullptr;
-// longest tile lists of this thread's last forwards (read back with R): decide whether the next forward launches
-// tile_sort's long-list classes speculatively (a wrong guess costs time, never correctness).  The maximum over the last
-// eight forwards is used, so cameras with and without long lists rendered in turn (a mapping window) never re-run.
-static thread_local uint32_t t_longest_hist[8] = {0xffffffffu, 0, 0, 0, 0, 0, 0, 0};
-static thread_local int t_longest_pos = 0;
-static uint32_t longest_recent() {
+// pinned slot + event for the asynchronous read-back of the instance count: one per host thread AND device (an event
+// belongs to the device it was created on)
+struct ReadBack { uint32_t *pinned = nullptr; cudaEvent_t event = nullptr; };
+static thread_local ReadBack t_readback[MAX_DEVICES];
+// longest tile lists of this thread's last forwards (read back with R), per (device, image size): decide whether the next
+// forward launches tile_sort's long-list classes speculatively (a wrong guess costs time, never correctness).  The
+// maximum over the last eight forwards OF THE SAME SHAPE is used, so cameras with and without long lists rendered in turn
+// (a mapping window), or a full-resolution tracking render alternating with the 512x144 depth render of
+// utils/init_pose.py:145, never re-run each other's tails.
+struct LongestHist { uint64_t key = ~0ull; uint32_t v[8] = {0xffffffffu, 0, 0, 0, 0, 0, 0, 0}; int pos = 0; };
+static thread_local LongestHist t_longest[8];      // a handful of (device, W, H) combinations per thread, LRU by slot 0
+static LongestHist &longest_for(int dev, int W, int H) {
+    const uint64_t key = ((uint64_t)dev << 48) | ((uint64_t)(uint32_t)W << 24) | (uint64_t)(uint32_t)H;
+    for (int i = 0; i < 8; ++i)
+        if (t_longest[i].key == key) {
+            if (i) { LongestHist h = t_longest[i]; for (int j = i; j > 0; --j) t_longest[j] = t_longest[j - 1]; t_longest[0] = h; }
+            return t_longest[0];
+        }
+    for (int j = 7; j > 0; --j) t_longest[j] = t_longest[j - 1];
+    t_longest[0] = LongestHist();
+    t_longest[0].key = key;
+    return t_longest[0];
+}
+static uint32_t longest_recent(const LongestHist &h) {
     uint32_t m = 0;
-    for (uint32_t v : t_longest_hist) m = v > m ? v : m;
+    for (uint32_t v : h.v) m = v > m ? v : m;
     return m;
 }
 
@@ -259,10 +276,15 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
         return launch_blend_forward(W, H, 0, nullptr, im.ranges, nullptr, g, nullptr, background, out_color, out_depth, out_opacity, im.final_T,
                                     im.n_contrib, n_touched, s);
     }
-    if (!t_pinned_R) {
-        LVDGS_CHECK(cudaHostAlloc((void **)&t_pinned_R, 64, cudaHostAllocDefault));
-        LVDGS_CHECK(cudaEventCreateWithFlags(&t_R_event, cudaEventDisableTiming));
+    const int dev_id = current_device();
+    ReadBack &rb = t_readback[dev_id];
+    if (!rb.pinned) {
+        LVDGS_CHECK(cudaHostAlloc((void **)&rb.pinned, 64, cudaHostAllocDefault));
+        LVDGS_CHECK(cudaEventCreateWithFlags(&rb.event, cudaEventDisableTiming));
     }
+    uint32_t *const t_pinned_R = rb.pinned;
+    const cudaEvent_t t_R_event = rb.event;
+    LongestHist &lh = longest_for(dev_id, W, H);
     lvdgs_geom_layout gl; geom_layout(p.P, gl);
     void *geom_base = resize(resize_user, LVDGS_BUF_GEOM, gl.total);
     if (!geom_base) { set_error("resize callback returned NULL (geom)"); return 1; }
@@ -286,7 +308,7 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
         void *bin_base = resize(resize_user, LVDGS_BUF_BINNING, bl.total);
         if (!bin_base) { set_error("resize callback returned NULL (binning)"); return 1; }
         // guess from the previous forward, with hysteresis
-        launched_long = (p.flags & LVDGS_FLAG_GLOBAL_SORT) || longest_recent() >= (uint32_t)(tile_sort_long_threshold() * 3 / 4);
+        launched_long = (p.flags & LVDGS_FLAG_GLOBAL_SORT) || longest_recent(lh) >= (uint32_t)(tile_sort_long_threshold() * 3 / 4);
         if (launch_bin_and_blend(p, g, bin_ptrs(bin_base, capacity), im, capacity, false, launched_long, background, out_color, out_depth,
                                  out_opacity, n_touched, s)) return 1;
         launched = true;
@@ -295,11 +317,12 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     if (profile_mark("(host: R read-back)", s)) return 1;
     const int64_t R = t_pinned_R[0];
     const uint32_t longest = t_pinned_R[1];
-    t_longest_pos = (t_longest_pos + 1) & 7;
-    t_longest_hist[t_longest_pos] = longest;
+    lh.pos = (lh.pos + 1) & 7;
+    lh.v[lh.pos] = longest;
     *num_rendered = R;
     const bool need_long = longest >= (uint32_t)tile_sort_long_threshold();      // exact: just read back
     if (!launched || R > capacity || (need_long && !launched_long)) {
+        if (launched) ++t_tail_reruns;
         if (!launched || R > capacity) capacity = R > 0 ? R : 1;
         lvdgs_binning_layout bl; binning_layout(capacity, bl);
         void *bin_base = resize(resize_user, LVDGS_BUF_BINNING, bl.total);
@@ -404,6 +427,17 @@ int lvdgs_fused_loss(int32_t width, int32_t height, const float *color, const fl
     return launch_fused_loss(width, height, color, depth, opacity, gt_color, gt_depth, grad_mask, exposure,
                              rgb_boundary_threshold, w_rgb, w_depth, flags, g_color, g_depth, g_opacity, out, workspace,
                              workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t lvdgs_masked_ssim_loss_workspace_bytes(int32_t width, int32_t height) { return masked_ssim_workspace_bytes(width, height); }
+int lvdgs_masked_ssim_loss(int32_t width, int32_t height, const float *image, const float *gt_image, const uint8_t *static_mask,
+                           const float *background, const float *depth, const float *mono_depth, float lambda_dssim,
+                           float depth_lambda, float *g_image, float *g_depth, float *out, void *workspace, size_t workspace_bytes,
+                           void *stream) {
+    if (width <= 0 || height <= 0 || !image || !gt_image || !background || !g_image || !out || !workspace) { set_error("masked_ssim_loss: bad arguments"); return 1; }
+    g_debug_sync = 0;
+    return launch_masked_ssim_loss(width, height, image, gt_image, static_mask, background, depth, mono_depth, lambda_dssim,
+                                   depth_lambda, g_image, g_depth, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int lvdgs_covis_counts(int64_t n, const void *a, const void *b, int32_t elem_bytes, uint64_t *out, void *stream) {

@@ -41,6 +41,12 @@ extern thread_local int g_debug_sync;
         if (lvdgs::g_debug_sync) LVDGS_CHECK(cudaStreamSynchronize(stream));                     \
     } while (0)
 
+// Per-device state: function attributes (opt-in shared memory sizes) and device properties belong to ONE device; a process
+// that drives several GPUs (one engine per device, or the tests' two-GPU runs) needs them once per device, not once per
+// process.  current_device() is the device the calling thread has selected (lvdgs_set_device / cudaSetDevice).
+constexpr int MAX_DEVICES = 64;
+static inline int current_device() { int d = 0; cudaGetDevice(&d); return d < 0 || d >= MAX_DEVICES ? 0 : d; }
+
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
@@ -236,6 +242,10 @@ int launch_fused_loss(int W, int H, const float *color, const float *depth, cons
                       const float *gt_depth, const float *grad_mask, const float *exposure, float thr, float w_rgb,
                       float w_depth, int flags, float *g_color, float *g_depth, float *g_opacity, float *out, void *ws,
                       size_t ws_bytes, cudaStream_t s);
+size_t masked_ssim_workspace_bytes(int W, int H);
+int launch_masked_ssim_loss(int W, int H, const float *image, const float *gt, const uint8_t *mask, const float *bg,
+                            const float *depth, const float *mono, float lambda_dssim, float depth_lambda, float *g_image,
+                            float *g_depth, float *out, void *ws, size_t ws_bytes, cudaStream_t s);
 int launch_covis(int64_t n, const void *a, const void *b, int elem, unsigned long long *out, cudaStream_t s);
 int launch_n_obs(int64_t n, int K, const void *const *masks_dev, int elem, int32_t *n_obs, cudaStream_t s);
 size_t compact_workspace_bytes(int64_t n);

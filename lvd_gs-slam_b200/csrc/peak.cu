@@ -9,9 +9,9 @@
 
 namespace lvdgs {
 
-__device__ __forceinline__ float fsel_asm(float a, float b, float c) {      // ALU pipe: c > 0 ? a : b
+__device__ __forceinline__ float fsel_asm(float a, float b, float c) {      // ALU pipe, two instructions: a > c ? a : b
     float d;
-    asm volatile("{ .reg .pred p; setp.gt.f32 p, %3, 0f00000000; selp.f32 %0, %1, %2, p; }" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    asm volatile("{ .reg .pred p; setp.gt.f32 p, %1, %3; selp.f32 %0, %1, %2, p; }" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
 

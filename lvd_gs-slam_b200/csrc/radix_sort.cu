@@ -11,6 +11,7 @@
 // consecutive addresses per digit.  HBM traffic per pass: 12 B read + 12 B written per pair; one
 // up-front histogram kernel reads the keys once for all passes.
 #include "common.cuh"
+#include <atomic>
 
 namespace lvdgs {
 
@@ -266,10 +267,11 @@ int launch_sort_pairs(int64_t n, const uint32_t *n_dev, uint64_t *keys0, uint64_
     unsigned char *lb_base = reinterpret_cast<unsigned char *>(ws_raw) + align_up(sizeof(SortWs));
     const size_t lb_stride = align_up((size_t)ntiles * RS_BINS * sizeof(uint32_t));
     LVDGS_CHECK(cudaMemsetAsync(ws_raw, 0, align_up(sizeof(SortWs)) + lb_stride * passes, s));
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<bool> attr_set[MAX_DEVICES];          // per device (see common.cuh)
+    const int dev = current_device();
+    if (!attr_set[dev].load(std::memory_order_acquire)) {
         LVDGS_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        attr_set = true;
+        attr_set[dev].store(true, std::memory_order_release);
     }
     const uint32_t *hist_scanned = pre_hist;
     if (!pre_hist) {

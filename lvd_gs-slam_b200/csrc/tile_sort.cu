@@ -23,6 +23,7 @@
 //                   stages in place in global memory (L2) and the narrow ones chunk by chunk in shared memory.
 // The two upper classes are launched only when the previous frame's longest list calls for them (api.cu).
 #include "common.cuh"
+#include <atomic>
 
 #ifndef LVDGS_TS_Q32
 #define LVDGS_TS_Q32 1        // short lists: 32-bit stand-ins + fix-up (0: the 64-bit network directly)
@@ -529,16 +530,17 @@ int launch_tile_sort(int tiles, int64_t capacity, const uint32_t *n_dev, const u
                      uint64_t *seg, uint64_t *keys_out, uint32_t *vals_out, bool long_lists, cudaStream_t s) {
     if (tiles <= 0) return 0;
     const uint32_t cap = (uint32_t)min(capacity, (int64_t)0xffffffffll);
-    static int sm_count = 0;
+    static std::atomic<int> sm_counts[MAX_DEVICES];          // per device (see common.cuh): attributes set + SM count
+    const int dev_id = current_device();
+    int sm_count = sm_counts[dev_id].load(std::memory_order_acquire);
     auto long_k = tile_sort_long_kernel<TS_LONG_THREADS, TS_LONG_CAP>;
     auto mid_k = tile_sort_mid_kernel<TS_MID_THREADS, TS_MID_CAP>;
     constexpr size_t mid_smem = ts_mid_smem_bytes(TS_MID_THREADS, TS_MID_CAP);
     if (!sm_count) {
-        int dev = 0;
-        LVDGS_CHECK(cudaGetDevice(&dev));
         LVDGS_CHECK(cudaFuncSetAttribute(long_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts_smem_bytes(TS_LONG_CAP)));
         LVDGS_CHECK(cudaFuncSetAttribute(mid_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem));
-        LVDGS_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        LVDGS_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev_id));
+        sm_counts[dev_id].store(sm_count, std::memory_order_release);
     }
     if (long_lists) {
         LVDGS_PRE(s);

@@ -87,9 +87,10 @@ _RESIZE_CB = _native.RESIZE_FN(_resize)
 
 
 def _select_device(L, dev):
-    if getattr(_tls, "device_index", None) != dev.index and dev.index is not None:
+    # unconditionally: torch.cuda.set_device / another engine may have changed the thread's device since the last call,
+    # and cudaSetDevice on the current device is free
+    if dev.index is not None:
         L.lvdgs_set_device(dev.index)
-        _tls.device_index = dev.index
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta,

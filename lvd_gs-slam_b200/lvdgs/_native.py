@@ -15,7 +15,7 @@ SRC_DIR = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 SO_PATH = os.path.join(PKG_DIR, "liblvdgs.so")
 SOURCES = ["api.cu", "preprocess.cu", "radix_sort.cu", "tile_sort.cu", "slam_ops.cu", "blend_forward.cu", "blend_backward.cu",
-           "preprocess_backward.cu", "knn.cu", "adam.cu", "cub_compare.cu", "peak.cu"]
+           "preprocess_backward.cu", "knn.cu", "adam.cu", "cub_compare.cu", "peak.cu", "ssim_loss.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("LVDGS_NVCC_DEFS", "").split()
 
@@ -110,7 +110,7 @@ class ImgLayout(C.Structure):
 
 RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int32, C.c_size_t)
 
-EXPORTS = ["lvdgs_version", "lvdgs_last_error", "lvdgs_set_device", "lvdgs_launch_count", "lvdgs_reset_launch_count",
+EXPORTS = ["lvdgs_version", "lvdgs_last_error", "lvdgs_set_device", "lvdgs_launch_count", "lvdgs_reset_launch_count", "lvdgs_tail_rerun_count",
            "lvdgs_profile_begin", "lvdgs_profile_end",
            "lvdgs_get_geom_layout", "lvdgs_get_binning_layout", "lvdgs_get_img_layout", "lvdgs_rasterize_forward",
            "lvdgs_backward_scratch_bytes", "lvdgs_rasterize_backward", "lvdgs_mark_visible",
@@ -118,7 +118,8 @@ EXPORTS = ["lvdgs_version", "lvdgs_last_error", "lvdgs_set_device", "lvdgs_launc
            "lvdgs_cub_sort_workspace_bytes", "lvdgs_cub_sort_pairs",
            "lvdgs_fused_loss_workspace_bytes", "lvdgs_fused_loss", "lvdgs_covis_counts", "lvdgs_n_obs",
            "lvdgs_compact_workspace_bytes", "lvdgs_compact_count", "lvdgs_compact_move", "lvdgs_pose_step", "lvdgs_gather_rows",
-           "lvdgs_fp32_peak", "lvdgs_gaussian_activate", "lvdgs_gaussian_activation_backward"]
+           "lvdgs_fp32_peak", "lvdgs_gaussian_activate", "lvdgs_gaussian_activation_backward",
+           "lvdgs_masked_ssim_loss_workspace_bytes", "lvdgs_masked_ssim_loss"]
 
 
 def lib():
@@ -137,6 +138,7 @@ def lib():
     L.lvdgs_set_device.argtypes = [C.c_int]
     L.lvdgs_launch_count.restype = i64
     L.lvdgs_reset_launch_count.restype = None
+    L.lvdgs_tail_rerun_count.restype = i64
     L.lvdgs_profile_begin.argtypes = [vp]
     L.lvdgs_profile_end.argtypes = [vp, C.c_char_p, sz, C.POINTER(f), i32]
     L.lvdgs_get_geom_layout.argtypes = [i32, C.POINTER(GeomLayout)]
@@ -169,6 +171,9 @@ def lib():
     L.lvdgs_gather_rows.argtypes = [i64, vp, i64, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp]
     L.lvdgs_gaussian_activate.argtypes = [i64] + [vp] * 7
     L.lvdgs_gaussian_activation_backward.argtypes = [i64] + [vp] * 8
+    L.lvdgs_masked_ssim_loss_workspace_bytes.argtypes = [i32, i32]
+    L.lvdgs_masked_ssim_loss_workspace_bytes.restype = sz
+    L.lvdgs_masked_ssim_loss.argtypes = [i32, i32] + [vp] * 6 + [f, f] + [vp] * 4 + [sz, vp]
     L.lvdgs_fp32_peak.argtypes = [i32, i32, i32, vp, C.POINTER(C.c_double), vp]
     L.lvdgs_pose_step.argtypes = [vp, vp, vp, f, f, f, C.c_double, C.c_double, C.c_double, i32, f, vp]
     _lib = L

@@ -78,14 +78,34 @@ class _Slot:
         self.color = torch.empty(3, H, W, **f32)
         self.depth = torch.empty(1, H, W, **f32)
         self.opacity = torch.empty(1, H, W, **f32)
-        self.radii = torch.empty(P, dtype=torch.int32, device=dev)
-        self.n_touched = torch.empty(P, dtype=torch.int32, device=dev)
-        self.g_means2D = torch.empty(P, 3, **f32)
+        self._cap_P = P
+        self._radii = torch.empty(P, dtype=torch.int32, device=dev)
+        self._n_touched = torch.empty(P, dtype=torch.int32, device=dev)
+        self._g_means2D = torch.empty(P, 3, **f32)
+        self.radii, self.n_touched, self.g_means2D = self._radii, self._n_touched, self._g_means2D
         self.g_tau = torch.empty(6, **f32)
         self.streams = ()            # side streams that use this slot's tensors (set by the engine)
         self.R = 0
         self.capacity = 0            # instances the binning arena was last laid out for
         self.hint = 0                # speculative-launch capacity hint for the next forward
+
+    def set_num_gaussians(self, L, P: int):
+        """Per-Gaussian arrays of the slot for a map of P Gaussians: views into allocations that only ever grow (1.25x), so
+        densify / prune churn between iterations does not allocate in the steady state."""
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        if P > self._cap_P:
+            for t in (self._radii, self._n_touched, self._g_means2D, self.scratch):
+                for st in self.streams:
+                    t.record_stream(st)
+            self._cap_P = int(P * 1.25) + 1024
+            self._radii = torch.empty(self._cap_P, dtype=torch.int32, device=self.dev)
+            self._n_touched = torch.empty(self._cap_P, dtype=torch.int32, device=self.dev)
+            self._g_means2D = torch.empty(self._cap_P, 3, **f32)
+            self.scratch = torch.empty(L.lvdgs_backward_scratch_bytes(self._cap_P, 0), dtype=torch.uint8, device=self.dev)
+            for t in (self._radii, self._n_touched, self._g_means2D, self.scratch):
+                for st in self.streams:
+                    t.record_stream(st)
+        self.radii, self.n_touched, self.g_means2D = self._radii[:P], self._n_touched[:P], self._g_means2D[:P]
 
     def _resize(self, _user, which, nbytes):
         buf = self.arena[int(which)]
@@ -129,6 +149,19 @@ class RasterEngine:
                     t.record_stream(st)
         if self.dev.index is not None:
             self.L.lvdgs_set_device(self.dev.index)
+
+    def set_num_gaussians(self, P: int, grad_flat=None):
+        """The map changed size (densify / prune): re-point the per-Gaussian arrays and the gradient block.  `grad_flat`: the
+        caller's block for the new size (lvdgs.mapping.ShardedMapper.new_grad_block()); None allocates one here."""
+        self.P = int(P)
+        for sl in self.slots:
+            sl.set_num_gaussians(self.L, self.P)
+        layout, total = block_layout(self.P, self.M)
+        if grad_flat is None:
+            grad_flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        assert grad_flat.numel() >= total
+        self.grad_flat = grad_flat
+        self.grads = {name: self.grad_flat[off:off + n] for name, (off, n) in layout.items()}
 
     # ---- slot 0 shortcuts (single-view use) ----
     color = property(lambda self: self.slots[0].color)
@@ -182,12 +215,13 @@ class RasterEngine:
             ptr(sl.g_tau), self._stream(stream))
         _native.check(rc, "lvdgs_rasterize_backward")
 
-    def run_views(self, vcs, means3D, opacities, scales, rotations, shs, upstream, on_view=None):
+    def run_views(self, vcs, means3D, opacities, scales, rotations, shs, upstream, on_view=None, before_view=None):
         """Forward + backward of several views with gradients accumulated into `grad_flat`, software-pipelined over the
         forward / backward streams and the buffer slots.  `upstream(k, slot)` is called on the backward stream after
         view k's forward has finished and returns (dL_dcolor, dL_ddepth, dL_dopacity) for it -- the place where a caller
         computes its loss from `slot.color/depth/opacity`.  `on_view(k, slot)` (optional) runs on the backward stream
-        after view k's backward (e.g. densification statistics from slot.g_means2D / slot.radii)."""
+        after view k's backward (e.g. densification statistics from slot.g_means2D / slot.radii).  `before_view(k)`
+        (optional) runs on the host right before view k's forward is queued."""
         cur = torch.cuda.current_stream(self.dev)
         n = len(self.slots)
         start = torch.cuda.Event(); start.record(cur)
@@ -197,6 +231,8 @@ class RasterEngine:
             s = k % n
             if bwd_done[s] is not None:
                 self.s_fwd.wait_event(bwd_done[s])                 # slot s is free again
+            if before_view is not None:
+                before_view(k)                                     # e.g. make the forward stream wait for view k's camera upload
             self.forward(vc, means3D, opacities, scales, rotations, shs, slot=s, stream=self.s_fwd)
             fwd_done = torch.cuda.Event(); fwd_done.record(self.s_fwd)
             self.s_bwd.wait_event(fwd_done)

@@ -95,9 +95,10 @@ class ShardedMapper:
                 off += (ln + 3) & ~3
             self.act_flat = torch.zeros(max(off, 4), dtype=torch.float32, device=self.device)
             self.act = {n: self.act_flat[o:o + ln] for n, (o, ln) in self.act_layout.items()}
-        self.lr_flat = torch.zeros_like(self.param_flat)      # per-element learning rate (stand-in optimisers of the CPU tests)
-        for n, sl in self.slices.items():
-            self.lr_flat[sl] = float(self.lrs[n])
+        if self.optimizer_fn is not None:      # per-element learning rate, only for the stand-in optimisers of the CPU tests
+            self.lr_flat = torch.zeros_like(self.param_flat)
+            for n, sl in self.slices.items():
+                self.lr_flat[sl] = float(self.lrs[n])
         # reduce-scatter slice of this rank
         self.shard_len = self.total // self.world
         self.shard = slice(self.rank * self.shard_len, (self.rank + 1) * self.shard_len)
@@ -306,6 +307,108 @@ class ShardedMapper:
         pad = torch.zeros(k, dtype=torch.float32, device=self.device)
         stats = (torch.cat([self.grad_norm_accum, pad]), torch.cat([self.denom, pad]), torch.cat([self.max_radii2D, pad]))
         self._rebuild(old_P + k, rows, stats)
+        return self.P
+
+    # ---- GaussianModel maintenance on the block (GaussianModel itself is not in /root/reference, the
+    # semantics are those of the 3DGS / MonoGS model its callers assume) ----
+    @staticmethod
+    def _inverse_sigmoid(x):
+        return torch.log(x / (1.0 - x))
+
+    def extend_from_points(self, points: torch.Tensor, colors: torch.Tensor, point_size: float = 1.0,
+                           init_opacity: float = 0.5, kf_id: int = -1) -> int:
+        """GaussianModel.extend_from_pcd_seq (caller utils/slam_backend.py:75-78), after the keyframe has been back-projected:
+        appends one Gaussian per point -- isotropic scale from the mean squared distance to the 3 nearest neighbours
+        (simple_knn.distCUDA2 -> lvdgs_dist2; log(sqrt(clamp_min(d2, 1e-7) * point_size))), identity rotation, opacity
+        inverse_sigmoid(0.5), SH-0 colour (rgb - 0.5) / C0 -- with zero Adam moments.  points [n,3], colors [n,3] in [0,1].
+        Every rank must call it with identical arguments.  Returns the new number of Gaussians."""
+        if not self.param_flat.is_cuda or not self.raw:
+            raise RuntimeError("ShardedMapper.extend_from_points: needs the raw-parameter block on a CUDA device (no CPU path)")
+        from simple_knn._C import distCUDA2
+        pts = points.to(self.device, torch.float32).contiguous()
+        n = pts.shape[0]
+        d2 = torch.clamp_min(distCUDA2(pts), 1e-7) * point_size
+        new = {"means3D": pts, "scales": torch.log(torch.sqrt(d2))[:, None].repeat(1, 3),
+               "rotations": torch.tensor([1.0, 0, 0, 0], device=self.device).repeat(n, 1),
+               "opacity": self._inverse_sigmoid(torch.full((n, 1), float(init_opacity), device=self.device))}
+        shs = torch.zeros(n, self.M, 3, device=self.device)
+        shs[:, 0] = (colors.to(self.device, torch.float32) - 0.5) / 0.28209479177387814
+        new["shs"] = shs.reshape(n, -1)
+        self.gather_moments()
+        old = (self._rows(self.param_flat), self._rows(self.exp_avg), self._rows(self.exp_avg_sq))
+        widths = group_widths(self.M)
+        zero = lambda name: torch.zeros(n, widths[name], dtype=torch.float32, device=self.device)
+        rows = [torch.cat([o, new[name].reshape(n, widths[name])]) for o, name in zip(old[0], GROUPS)]
+        rows += [torch.cat([o, zero(name)]) for o, name in zip(old[1], GROUPS)]
+        rows += [torch.cat([o, zero(name)]) for o, name in zip(old[2], GROUPS)]
+        pad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        stats = (torch.cat([self.grad_norm_accum, pad]), torch.cat([self.denom, pad]), torch.cat([self.max_radii2D, pad]))
+        kf = getattr(self, "unique_kfIDs", torch.full((self.P,), -1, dtype=torch.int32, device=self.device))
+        self._rebuild(self.P + n, rows, stats)
+        self.unique_kfIDs = torch.cat([kf, torch.full((n,), int(kf_id), dtype=torch.int32, device=self.device)])
+        return self.P
+
+    def reset_opacity_nonvisible(self, visibility_filters: Sequence[torch.Tensor], value: float = 0.4):
+        """GaussianModel.reset_opacity_nonvisible (caller utils/slam_backend.py:372-376): every Gaussian that none of the
+        given views saw gets opacity `value` (raw: inverse_sigmoid(0.4)); the opacity group's Adam moments restart from zero
+        (replace_tensor_to_optimizer).  Visibility comes from lvdgs_n_obs over the masks (one launch)."""
+        if not self.param_flat.is_cuda or not self.raw:
+            raise RuntimeError("ShardedMapper.reset_opacity_nonvisible: needs the raw-parameter block on a CUDA device")
+        from .slam_ops import accumulate_n_obs as n_obs
+        seen = n_obs(list(visibility_filters)) > 0 if len(visibility_filters) else torch.zeros(self.P, dtype=torch.bool, device=self.device)
+        raw = self.params["opacity"]
+        raw.copy_(torch.where(seen, raw, self._inverse_sigmoid(torch.full_like(raw, float(value)))))
+        self.gather_moments()
+        self.exp_avg[self.slices["opacity"]].zero_()
+        self.exp_avg_sq[self.slices["opacity"]].zero_()
+        self.activate()
+
+    def densify_and_prune(self, max_grad: float, min_opacity: float, extent: float, max_screen_size: Optional[float],
+                          percent_dense: float = 0.01, n_split: int = 2, generator: Optional[torch.Generator] = None) -> int:
+        """GaussianModel.densify_and_prune (caller utils/slam_backend.py:359-370) on the replicated block, from the all-reduced
+        statistics (call reduce_stats() first when world > 1):
+          grads = grad_norm_accum / denom;  clone where grads >= max_grad and max(scale) <= percent_dense * extent;
+          split (n_split samples from N(0, scale) in the Gaussian's frame, scales / (0.8 n_split)) where grads >= max_grad and
+          max(scale) > percent_dense * extent, the split originals removed;  prune opacity < min_opacity, and -- when
+          max_screen_size is given -- max_radii2D > max_screen_size or max(scale) > 0.1 * extent.
+        `generator`: seeded identically on every rank, so every replica draws the same split samples.  The statistics are
+        reset afterwards.  Returns the new number of Gaussians."""
+        if not self.param_flat.is_cuda or not self.raw:
+            raise RuntimeError("ShardedMapper.densify_and_prune: needs the raw-parameter block on a CUDA device")
+        grads = self.grad_norm_accum / self.denom
+        grads[grads.isnan()] = 0.0
+        max_scale = self.view("scales").max(dim=1).values
+        hot = grads >= max_grad
+        small = max_scale <= percent_dense * extent
+        clone_idx = torch.nonzero(hot & small).reshape(-1)
+        split_idx = torch.nonzero(hot & ~small).reshape(-1)
+        P0 = self.P
+        kf = getattr(self, "unique_kfIDs", torch.full((self.P,), -1, dtype=torch.int32, device=self.device))
+        if clone_idx.numel():
+            self.densify_clone(clone_idx)
+            kf = torch.cat([kf, kf[clone_idx]])
+        if split_idx.numel():
+            rep = split_idx.repeat(n_split)
+            scales = self.view("scales")[rep]
+            samples = torch.randn(scales.shape, generator=generator, device=self.device if generator is None or generator.device.type == "cuda" else "cpu").to(self.device) * scales
+            q = self.view("rotations")[rep]
+            r, x, y, z = q.unbind(1)
+            R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                             2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                             2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).reshape(-1, 3, 3)
+            new_xyz = torch.bmm(R, samples[..., None]).squeeze(-1) + self.view("means3D")[rep]
+            new_scales = torch.log(scales / (0.8 * n_split))
+            self.densify_clone(rep, overrides={"means3D": new_xyz, "scales": new_scales})
+            kf = torch.cat([kf, kf[rep]])
+        keep = torch.ones(self.P, dtype=torch.bool, device=self.device)
+        keep[split_idx] = False                                          # the originals of the split Gaussians go
+        prune = self.view("opacity").reshape(-1) < min_opacity
+        if max_screen_size:
+            prune |= (self.max_radii2D > max_screen_size) | (self.view("scales").max(dim=1).values > 0.1 * extent)
+        keep &= ~prune
+        self.prune(keep)
+        self.unique_kfIDs = kf[keep]
+        self.grad_norm_accum.zero_(); self.denom.zero_(); self.max_radii2D.zero_()
         return self.P
 
     # ---- one mapping iteration ----

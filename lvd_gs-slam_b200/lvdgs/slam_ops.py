@@ -90,6 +90,23 @@ class _FusedLoss(torch.autograd.Function):
         return gi, gd, gop, gea, geb, None, None, None, None, None, None, None
 
 
+def fused_loss_into(image, depth, gt_image, gt_depth, g_image, g_depth, out, *, opacity=None, grad_mask=None, exposure=None,
+                    rgb_boundary_threshold=0.01, w_rgb=1.0, w_depth=0.0, flags=0):
+    """The loss kernel without autograd, for allocation-free loops over the C ABI (lvdgs.engine.RasterEngine.run_views'
+    `upstream` hook): writes dL/dimage into g_image, dL/ddepth into g_depth and {loss, dL/da, dL/db, 0} into out[4] --
+    all caller-owned float32 CUDA tensors."""
+    L = _native.lib()
+    dev = image.device
+    _, H, W = image.shape
+    ws = _workspace(dev, L.lvdgs_fused_loss_workspace_bytes())
+    p = _native.ptr
+    rc = L.lvdgs_fused_loss(W, H, p(image), p(depth), p(opacity), p(gt_image), p(gt_depth), p(grad_mask), p(exposure),
+                            float(rgb_boundary_threshold), float(w_rgb), float(w_depth), int(flags), p(g_image), p(g_depth), None,
+                            p(out), p(ws), ws.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _native.check(rc, "lvdgs_fused_loss")
+    return out
+
+
 def fused_loss(image, depth=None, opacity=None, exposure_a=None, exposure_b=None, *, gt_image, gt_depth=None,
                grad_mask=None, rgb_boundary_threshold=0.01, w_rgb=1.0, w_depth=0.0, flags=0):
     return _FusedLoss.apply(image, depth, opacity, exposure_a, exposure_b, gt_image, gt_depth, grad_mask,
@@ -143,6 +160,54 @@ def get_loss_mapping_rgbd(config, image, depth, viewpoint, initialization=False,
     return fused_loss(image, depth, None, *_exposure, gt_image=viewpoint.original_image.to(image.device),
                       gt_depth=_gt_depth(viewpoint, image.device),
                       rgb_boundary_threshold=config["Training"]["rgb_boundary_threshold"], w_rgb=alpha, w_depth=1 - alpha)
+
+
+# ---- the masked L1 + SSIM + depth mapping loss (utils/slam_backend.py:199-261) ----
+class _MaskedMappingLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, depth, gt_image, static_mask, background, mono_depth, lambda_dssim, depth_lambda):
+        _need_cuda(image, "masked_mapping_loss")
+        L = _native.lib()
+        dev = image.device
+        _, H, W = image.shape
+        img, gt = _f32(image), _f32(gt_image)
+        bg = _f32(background.to(dev))
+        mask = None if static_mask is None else (static_mask.to(dev) != 0).reshape(H, W).contiguous().view(torch.uint8)
+        dep = None if depth is None else _f32(depth).reshape(H, W)
+        mono = None if (mono_depth is None or depth is None) else _f32(mono_depth.to(dev)).reshape(H, W)
+        g_img = torch.empty_like(img)
+        g_dep = torch.empty_like(dep) if dep is not None else None
+        out = torch.empty(8, dtype=torch.float32, device=dev)
+        nbytes = L.lvdgs_masked_ssim_loss_workspace_bytes(W, H)
+        key = ("ssim", dev.index, torch.cuda.current_stream(dev).cuda_stream, W, H)
+        ws = _ws.get(key)
+        if ws is None:
+            ws = _ws[key] = torch.zeros(int(nbytes), dtype=torch.uint8, device=dev)
+        p = _native.ptr
+        rc = L.lvdgs_masked_ssim_loss(W, H, p(img), p(gt), p(mask), p(bg), p(dep), p(mono), float(lambda_dssim), float(depth_lambda),
+                                      p(g_img), p(g_dep), p(out), p(ws), ws.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _native.check(rc, "lvdgs_masked_ssim_loss")
+        ctx.save_for_backward(g_img, g_dep)
+        ctx.shapes = (image.shape, None if depth is None else depth.shape)
+        ctx.mark_non_differentiable(out)
+        return out[0], out
+
+    @staticmethod
+    def backward(ctx, go, _gout):
+        g_img, g_dep = ctx.saved_tensors
+        s_img, s_dep = ctx.shapes
+        gi = (g_img * go).view(s_img) if ctx.needs_input_grad[0] else None
+        gd = (g_dep * go).view(s_dep) if (ctx.needs_input_grad[1] and g_dep is not None) else None
+        return gi, gd, None, None, None, None, None, None
+
+
+def masked_mapping_loss(image, gt_image, static_mask, background, depth=None, mono_depth=None, lambda_dssim=0.2,
+                        depth_lambda=0.1, return_terms=False):
+    """The per-keyframe loss of utils/slam_backend.py:199-261 (dynamic pixels painted with the background in render and
+    ground truth; (1 - lambda) L1 + lambda (1 - SSIM); + depth_lambda * masked mean |depth - mono_depth|) -- value and
+    gradients from two tiled kernels (lvdgs_masked_ssim_loss).  static_mask: bool [H,W], True = static (kept) pixel."""
+    loss, terms = _MaskedMappingLoss.apply(image, depth, gt_image, static_mask, background, mono_depth, lambda_dssim, depth_lambda)
+    return (loss, terms) if return_terms else loss
 
 
 # ---- covisibility ----

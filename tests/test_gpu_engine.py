@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from lvdgs import synth
+from lvdgs import synth, _native
 from lvdgs.engine import RasterEngine, ViewCamera
 from gpu_harness import run_cuda, rel_err
 
@@ -59,3 +59,29 @@ def test_pipelined_views_match_sequential_plugin():
             np.testing.assert_array_equal(seen[k][0].cpu().numpy(), out["color"])
             np.testing.assert_array_equal(seen[k][1].cpu().numpy(), out["radii"])
             np.testing.assert_array_equal(seen[k][2].cpu().numpy(), out["n_touched"])
+
+
+def test_alternating_image_sizes_never_rerun_the_speculative_tail():
+    """tracking renders 1241x376 and, per frame, one 512x144 depth image (utils/init_pose.py:145) on the
+    same thread.  The long-list history is kept per (device, image size), so after warm-up neither shape disturbs the
+    other's speculation: zero repeated tails, and a second engine of another size on the same thread changes nothing."""
+    dev = torch.device("cuda")
+    L = _native.lib()
+    big, small = synth.make_camera("kitti"), synth.make_camera("mast3r_kitti")
+    N = 120_000
+    sc = synth.make_scene(N, big, seed=4)
+    sc["scales"] *= 2.5                                        # long tile lists at full resolution, short ones at 512x144
+    t = lambda a: torch.tensor(a, device=dev)
+    args = [t(sc[k]) for k in ("means3D", "opacities", "scales", "rotations", "shs")]
+    e_big = RasterEngine(N, big.image_width, big.image_height, device=dev, slots=1)
+    e_small = RasterEngine(N, small.image_width, small.image_height, device=dev, slots=1)
+    v_big, v_small = ViewCamera(big, dev), ViewCamera(small, dev)
+    for _ in range(3):                                         # warm-up: capacity hints and list-length histories settle
+        e_big.forward(v_big, *args); e_small.forward(v_small, *args)
+    ref_big, ref_small = e_big.color.clone(), e_small.depth.clone()
+    before = L.lvdgs_tail_rerun_count()
+    for _ in range(6):
+        e_big.forward(v_big, *args); e_small.forward(v_small, *args)
+    torch.cuda.synchronize()
+    assert L.lvdgs_tail_rerun_count() == before
+    assert torch.equal(e_big.color, ref_big) and torch.equal(e_small.depth, ref_small)

@@ -138,5 +138,6 @@ def test_gpu_adam_matches_torch():
         grad = torch.randn(init.numel(), generator=g) * (10.0 ** (it - 2))
         a.adam_step(grad.cuda()); b.adam_step(grad.clone())
     torch.cuda.synchronize()
-    assert torch.allclose(a.param_flat.cpu(), b.param_flat, rtol=1e-5, atol=1e-7)
-    assert torch.allclose(a.exp_avg_sq.cpu(), b.exp_avg_sq, rtol=1e-5, atol=0)
+    for sl in a.slices.values():              # group by group: the alignment padding between groups is nobody's parameter
+        assert torch.allclose(a.param_flat[sl].cpu(), b.param_flat[sl], rtol=1e-5, atol=1e-7)
+        assert torch.allclose(a.exp_avg_sq[sl].cpu(), b.exp_avg_sq[sl], rtol=1e-5, atol=0)
