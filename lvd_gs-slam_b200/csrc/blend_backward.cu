@@ -50,35 +50,44 @@ __device__ __forceinline__ int red10_index(int lane) {
     else k = b2 ? -1 : 3 + b1;                     // last two: 3, 4
     return k < 0 ? -1 : 5 * ((lane >> 4) & 1) + k;
 }
-__device__ __forceinline__ float transpose_reduce10(const float (&v)[10], int lane) {
+// lane-constant all-ones / zero masks of lane bits 4, 3, 2, 1: the exchanges select with one LOP3 each, no predicate
+struct LaneMasks { uint32_t m16, m8, m4, m2; };
+__device__ __forceinline__ LaneMasks lane_masks(int lane) {
+    LaneMasks m;
+    m.m16 = (lane & 16) ? 0xffffffffu : 0u; m.m8 = (lane & 8) ? 0xffffffffu : 0u;
+    m.m4 = (lane & 4) ? 0xffffffffu : 0u; m.m2 = (lane & 2) ? 0xffffffffu : 0u;
+    return m;
+}
+__device__ __forceinline__ float bsel(uint32_t m, float a, float b) {      // m ? a : b
+    float d;      // one LOP3 ((a & m) | (b & ~m)); spelled in PTX so that nvcc does not turn it back into predicate + FSEL
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=f"(d) : "f"(a), "f"(b), "r"(m));
+    return d;
+}
+#define LVDGS_SHX(x, d) __shfl_xor_sync(0xffffffffu, (x), (d))
+// returns MINUS the warp-wide sum (the visit's values are negated sums, see the hot loop)
+__device__ __forceinline__ float transpose_reduce10(const float (&v)[10], const LaneMasks &L) {
     float w[5], x[3], y[2];
-    {
-        const bool up = lane & 16;
+    {   // packed adds: (keep0, keep1) + (recv0, recv1) as one FADD2
+        float k[5], r[5];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const float send = up ? v[i] : v[i + 5];
-            const float keep = up ? v[i + 5] : v[i];
-            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
+        for (int i = 0; i < 5; ++i) { k[i] = bsel(L.m16, v[i + 5], v[i]); r[i] = LVDGS_SHX(bsel(L.m16, v[i], v[i + 5]), 16); }
+        const f32x2 a = add2(pk(k[0], k[1]), pk(r[0], r[1])), b = add2(pk(k[2], k[3]), pk(r[2], r[3]));
+        w[0] = lo_of(a); w[1] = hi_of(a); w[2] = lo_of(b); w[3] = hi_of(b); w[4] = k[4] + r[4];
     }
-    {
-        const bool up = lane & 8;      // lower lanes keep w0 w1 w2, upper lanes w3 w4
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float send = up ? w[k] : (k < 2 ? w[3 + k] : 0.f);
-            const float keep = up ? (k < 2 ? w[3 + k] : 0.f) : w[k];
-            x[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
+    {   // lower lanes keep w0 w1 w2, upper lanes w3 w4
+        const float k0 = bsel(L.m8, w[3], w[0]), k1 = bsel(L.m8, w[4], w[1]), k2 = bsel(L.m8, 0.f, w[2]);
+        const float r0 = LVDGS_SHX(bsel(L.m8, w[0], w[3]), 8), r1 = LVDGS_SHX(bsel(L.m8, w[1], w[4]), 8), r2 = LVDGS_SHX(bsel(L.m8, w[2], 0.f), 8);
+        const f32x2 a = add2(pk(k0, k1), pk(r0, r1));
+        x[0] = lo_of(a); x[1] = hi_of(a); x[2] = k2 + r2;
     }
-    {
-        const bool up = lane & 4;      // lower lanes keep x0 x1, upper lanes x2
-        y[0] = (up ? x[2] : x[0]) + __shfl_xor_sync(0xffffffffu, up ? x[0] : x[2], 4);
-        y[1] = (up ? 0.f : x[1]) + __shfl_xor_sync(0xffffffffu, up ? x[1] : 0.f, 4);
+    {   // lower lanes keep x0 x1, upper lanes x2
+        const float k0 = bsel(L.m4, x[2], x[0]), k1 = bsel(L.m4, 0.f, x[1]);
+        const float r0 = LVDGS_SHX(bsel(L.m4, x[0], x[2]), 4), r1 = LVDGS_SHX(bsel(L.m4, x[1], 0.f), 4);
+        const f32x2 a = add2(pk(k0, k1), pk(r0, r1));
+        y[0] = lo_of(a); y[1] = hi_of(a);
     }
-    const bool up = lane & 2;
-    float z = (up ? y[1] : y[0]) + __shfl_xor_sync(0xffffffffu, up ? y[0] : y[1], 2);
-    z += __shfl_xor_sync(0xffffffffu, z, 1);
-    return z;
+    const float z = bsel(L.m2, y[1], y[0]) + LVDGS_SHX(bsel(L.m2, y[0], y[1]), 2);
+    return -z - LVDGS_SHX(z, 1);
 }
 
 // The same for the six geometric moments alone (3 + 2 + 1 + 1 + 1 = 8 shuffles): value 3 g + k, g = lane bit 4.
@@ -88,30 +97,22 @@ __device__ __forceinline__ int red6_index(int lane) {
     const int k = b3 ? (b2 ? -1 : 2) : b2;
     return k < 0 ? -1 : 3 * ((lane >> 4) & 1) + k;
 }
-__device__ __forceinline__ float transpose_reduce6(const float (&v)[10], int lane) {
+__device__ __forceinline__ float transpose_reduce6(const float (&v)[10], const LaneMasks &L) {     // also negated
     float w[3];
-    {
-        const bool up = lane & 16;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) w[i] = (up ? v[i + 3] : v[i]) + __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 3], 16);
-    }
-    float x0, x1;
-    {
-        const bool up = lane & 8;      // lower lanes keep w0 w1, upper lanes w2
-        x0 = (up ? w[2] : w[0]) + __shfl_xor_sync(0xffffffffu, up ? w[0] : w[2], 8);
-        x1 = (up ? 0.f : w[1]) + __shfl_xor_sync(0xffffffffu, up ? w[1] : 0.f, 8);
-    }
-    const bool up = lane & 4;
-    float y = (up ? x1 : x0) + __shfl_xor_sync(0xffffffffu, up ? x0 : x1, 4);
-    y += __shfl_xor_sync(0xffffffffu, y, 2);
-    y += __shfl_xor_sync(0xffffffffu, y, 1);
-    return y;
+    for (int i = 0; i < 3; ++i) w[i] = bsel(L.m16, v[i + 3], v[i]) + LVDGS_SHX(bsel(L.m16, v[i], v[i + 3]), 16);
+    // lower lanes keep w0 w1, upper lanes w2
+    const float x0 = bsel(L.m8, w[2], w[0]) + LVDGS_SHX(bsel(L.m8, w[0], w[2]), 8);
+    const float x1 = bsel(L.m8, 0.f, w[1]) + LVDGS_SHX(bsel(L.m8, w[1], 0.f), 8);
+    float y = bsel(L.m4, x1, x0) + LVDGS_SHX(bsel(L.m4, x0, x1), 4);
+    y += LVDGS_SHX(y, 2);
+    return -y - LVDGS_SHX(y, 1);
 }
 
 // MOMENTS_ONLY: the colour and depth sums are not needed (pose-only backward at SH degree 0 without a depth gradient --
 // the tracking loop): six values per (warp, Gaussian) instead of ten.
 #ifndef LVDGS_BB_MINBLOCKS
-#define LVDGS_BB_MINBLOCKS 1
+#define LVDGS_BB_MINBLOCKS 8      // <= 64 registers, 8 CTAs per SM: 0.587 against 0.596 ms fwd+bwd on the headline view (measured)
 #endif
 template <bool MOMENTS_ONLY>
 __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward_kernel(
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
 
     // per-pixel state, packed (lo = row py0, hi = row py0 + 4)
     uint32_t last[2];
-    f32x2 npfy2, T2, Tfbgd2, dp0_2, dp1_2, dp2_2, dpd_2, S2 = bc(0.f);
+    f32x2 npfy2, Tfbgd2, dp0_2, dp1_2, dp2_2, dpd_2; float Ta, Tb, Sa = 0.f, Sb = 0.f;
     {
         float pfy[2], Tf[2], dp0[2], dp1[2], dp2[2], dpd[2], bgd[2];
         const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
             if (inside && dL_dout_opacity) bgd[q] -= dL_dout_opacity[pix];   // d(1 - T_final)/dalpha = +T_final/(1-alpha)
         }
         npfy2 = pk(-pfy[0], -pfy[1]);
-        T2 = pk(Tf[0], Tf[1]);
+        Ta = Tf[0]; Tb = Tf[1];
         Tfbgd2 = pk(Tf[0] * bgd[0], Tf[1] * bgd[1]);
         dp0_2 = pk(dp0[0], dp0[1]); dp1_2 = pk(dp1[0], dp1[1]); dp2_2 = pk(dp2[0], dp2[1]); dpd_2 = pk(dpd[0], dpd[1]);
     }
@@ -179,9 +180,13 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
     const int red_i = MOMENTS_ONLY ? red6_index(lane) : red10_index(lane);
     const bool commits = red_i >= 0;
     const int slot = red_i < 7 ? red_i : red_i + 1;           // values 0..6 -> slots 0..6, 7..9 -> rgb slots 8..10
+    float *const acc_lane = acc + (commits ? slot : 0);
+    const LaneMasks LM = lane_masks(lane);
 
     // entries are visited in decreasing contributor index k = top-1 ... 0
-    for (int remaining = (int)top; remaining > 0; remaining -= BB_BATCH) {
+    // entry j of a batch has contributor index k = remaining - 1 - j; "k < n_contrib" is tested as j >= thr
+    int thr0 = (int)top - (int)last[0], thr1 = (int)top - (int)last[1];
+    for (int remaining = (int)top; remaining > 0; remaining -= BB_BATCH, thr0 -= BB_BATCH, thr1 -= BB_BATCH) {
         __syncthreads();
         const int nb = min(BB_BATCH, remaining);
 #pragma unroll
@@ -235,7 +240,6 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
                 const int b = __ffs(mask) - 1;
                 mask &= mask - 1;
                 const int j = wp * 32 + b;
-                const uint32_t k = (uint32_t)(remaining - 1 - j);    // contributor index (0-based) of this entry
                 const uint32_t a_j = a_rec + (uint32_t)j * (uint32_t)sizeof(BlendRec);
                 const float2 xy = lds64(a_j);
                 const float4 co = lds128(a_j + 16);
@@ -251,8 +255,8 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
                 // co.w = -opacity; the recurrences below are written in -alpha, and every sum of this visit comes out
                 // NEGATED (m = G dL/dalpha and the blend weight both carry the sign), which the commit undoes for free
                 const float naa = fmaxf(-0.99f, co.w * ga), nab = fmaxf(-0.99f, co.w * gb);
-                const bool oka = k < last[0] && p2a <= 0.f && naa <= -1.f / 255.f;
-                const bool okb = k < last[1] && p2b <= 0.f && nab <= -1.f / 255.f;
+                const bool oka = j >= thr0 && p2a <= 0.f && naa <= -1.f / 255.f;
+                const bool okb = j >= thr1 && p2b <= 0.f && nab <= -1.f / 255.f;
                 const bool valid = oka || okb;
                 const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
                 if (!vmask) continue;
@@ -260,14 +264,15 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
                 const f32x2 nal2 = pk(oka ? naa : 0.f, okb ? nab : 0.f);
                 const f32x2 one_m2 = add2(nal2, bc(1.f));
                 const f32x2 inv2 = pk(rcp_approx(lo_of(one_m2)), rcp_approx(hi_of(one_m2)));   // 1 - alpha >= 0.01
-                T2 = mul2(T2, inv2);
+                const f32x2 T2 = mul2(pk(Ta, Tb), inv2); Ta = lo_of(T2); Tb = hi_of(T2);
+                const f32x2 S2o = pk(Sa, Sb);
                 // the colour / depth blended BEHIND this Gaussian enters only through its dot product with dL/dpixel:
                 // S = <B, dp> obeys the same recurrence as B itself (S <- S + alpha (<c, dp> - S))
                 const f32x2 cdp2 = fma2(bc(cd.w), dpd_2, fma2(bc(cd.z), dp2_2, fma2(bc(cd.y), dp1_2, mul2(bc(cd.x), dp0_2))));
-                const f32x2 ne2 = fma2(cdp2, bc(-1.f), S2);       // S - <c, dp>
+                const f32x2 ne2 = fma2(cdp2, bc(-1.f), S2o);       // S - <c, dp>
                 f32x2 ndL2 = mul2(ne2, T2);                       // -dL/dalpha, first term
                 ndL2 = fma2(inv2, Tfbgd2, ndL2);                  // + T_final / (1 - alpha) * <bg, dp>
-                S2 = fma2(nal2, ne2, S2);
+                const f32x2 S2n = fma2(nal2, ne2, S2o); Sa = lo_of(S2n); Sb = hi_of(S2n);
                 const f32x2 m2 = mul2(G2, ndL2);                  // -m
                 const f32x2 mdx2 = mul2(m2, bc(dx)), mdy2 = mul2(m2, dy2);
                 float v[10];      // NEGATED accumulator-row slots 0..6, 8..10 (ACC_STRIDE layout in common.cuh)
@@ -283,11 +288,12 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
                     v[6] = v[7] = v[8] = v[9] = 0.f;
                 }
                 if (vmask) {
-                    float *row = acc + (size_t)lds32(a_j + 8) * ACC_STRIDE;
+                    const uint32_t id = lds32(a_j + 8);
                     if (__popc(vmask) <= BB_DIRECT_MAX) {
                         // a Gaussian's edge often reaches only one or two threads of the block: their partial sums go
                         // straight to the accumulator row (10 REDs) instead of through the 60-instruction reduction
                         if (valid) {
+                            float *row = acc + (size_t)id * ACC_STRIDE;
                             atomicAdd(row + 0, -v[0]); atomicAdd(row + 1, -v[1]); atomicAdd(row + 2, -v[2]); atomicAdd(row + 3, -v[3]);
                             atomicAdd(row + 4, -v[4]); atomicAdd(row + 5, -v[5]);
                             if (!MOMENTS_ONLY) {
@@ -296,8 +302,8 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
                             }
                         }
                     } else {
-                        const float sum = MOMENTS_ONLY ? transpose_reduce6(v, lane) : transpose_reduce10(v, lane);
-                        if (commits) atomicAdd(row + slot, -sum);
+                        const float sum = MOMENTS_ONLY ? transpose_reduce6(v, LM) : transpose_reduce10(v, LM);
+                        if (commits) atomicAdd(acc_lane + (size_t)id * ACC_STRIDE, sum);
                     }
                 }
             }

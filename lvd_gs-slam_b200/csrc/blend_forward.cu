@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(BF_THREADS, LVDGS_BF_MINBLOCKS) blend_forward_
     const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
     const float pfx = (float)px;
     // a finished / out-of-image pixel is parked: its -y is -1e18, every Gaussian then evaluates to alpha = 0
-    f32x2 npfy2 = pk(in0 ? -(float)py0 : -PIX_PARKED, in1 ? -(float)py1 : -PIX_PARKED);
+    float nya = in0 ? -(float)py0 : -PIX_PARKED, nyb = in1 ? -(float)py1 : -PIX_PARKED;
     const uint32_t a_rec = smem_u32(s_rec);
     const float tx0 = (float)(tile_x * TILE), ty0 = (float)(tile_y * TILE);
 
@@ -60,11 +60,12 @@ __global__ void __launch_bounds__(BF_THREADS, LVDGS_BF_MINBLOCKS) blend_forward_
     if (n_dev && __ldg(n_dev) > capacity) return;
     const uint2 range = ranges[tile];
     int todo = (int)(range.y - range.x);
-    f32x2 T2 = bc(1.f), C0 = bc(0.f), C1 = bc(0.f), C2 = bc(0.f), D = bc(0.f);
+    float Ta = 1.f, Tb = 1.f;
+    float C0a = 0.f, C0b = 0.f, C1a = 0.f, C1b = 0.f, C2a = 0.f, C2b = 0.f, Da = 0.f, Db = 0.f;
     uint32_t last0 = 0, last1 = 0;
     uint32_t batch_first = 0;
     int warp_hi = 1;
-    auto parked = [&]() { return lo_of(npfy2) == -PIX_PARKED && hi_of(npfy2) == -PIX_PARKED; };
+    auto parked = [&]() { return nya == -PIX_PARKED && nyb == -PIX_PARKED; };
 
     for (uint32_t base = range.x; todo > 0; base += BF_BATCH, todo -= BF_BATCH, batch_first += BF_BATCH) {
         if (__syncthreads_count(parked()) == BF_THREADS) break;
@@ -110,8 +111,8 @@ __global__ void __launch_bounds__(BF_THREADS, LVDGS_BF_MINBLOCKS) blend_forward_
         for (int wp = 0; wp < BF_BATCH / 32; ++wp) {
             uint32_t m = s_mask[wp][warp];
             if (__all_sync(0xffffffffu, parked())) break;
-            if (warp_hi) warp_hi = __any_sync(0xffffffffu, (lo_of(npfy2) != -PIX_PARKED && lo_of(T2) > 0.5f) ||
-                                                           (hi_of(npfy2) != -PIX_PARKED && hi_of(T2) > 0.5f));
+            if (warp_hi) warp_hi = __any_sync(0xffffffffu, (nya != -PIX_PARKED && Ta > 0.5f) ||
+                                                           (nyb != -PIX_PARKED && Tb > 0.5f));
             while (m) {
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
@@ -121,25 +122,29 @@ __global__ void __launch_bounds__(BF_THREADS, LVDGS_BF_MINBLOCKS) blend_forward_
                 const float4 q = lds128(a_j + 16);
                 const float4 cd = lds128(a_j + 32);
                 const float dx = xy.x - pfx;
-                const f32x2 dy2 = add2(bc(xy.y), npfy2);
+                const f32x2 dy2 = add2(bc(xy.y), pk(nya, nyb));
                 const f32x2 p2 = fma2(mul2(bc(q.z), dy2), dy2, mul2(bc(dx), fma2(bc(q.y), dy2, bc(q.x * dx))));
                 const float p2a = lo_of(p2), p2b = hi_of(p2);
                 // q.w = -opacity: everything downstream wants -alpha (T - alpha T as ONE fma, weights that accumulate
                 // MINUS the colour), so no negation is ever issued
                 const float naa = fmaxf(-0.99f, q.w * ex2_approx(p2a)), nab = fmaxf(-0.99f, q.w * ex2_approx(p2b));
                 const bool oka = p2a <= 0.f && naa <= -1.f / 255.f, okb = p2b <= 0.f && nab <= -1.f / 255.f;
+                const f32x2 T2 = pk(Ta, Tb);
                 const f32x2 tT2 = fma2(pk(naa, nab), T2, T2);      // T (1 - alpha)
                 const float tTa = lo_of(tT2), tTb = hi_of(tT2);
-                const bool terma = oka && tTa < 0.0001f, termb = okb && tTb < 0.0001f;
-                const bool ca = oka && !terma, cb = okb && !termb;
+                const bool ca = oka && !(tTa < 0.0001f), cb = okb && !(tTb < 0.0001f);     // blends; ok && !c = terminates here
                 // one select per pixel (-alpha or 0); weight and T follow arithmetically (alpha = 0 leaves T untouched)
                 const f32x2 nae2 = pk(ca ? naa : 0.f, cb ? nab : 0.f);
                 const f32x2 nw2 = mul2(nae2, T2);
-                C0 = fma2(bc(cd.x), nw2, C0); C1 = fma2(bc(cd.y), nw2, C1); C2 = fma2(bc(cd.z), nw2, C2); D = fma2(bc(cd.w), nw2, D);
-                T2 = fma2(nae2, T2, T2);
+                { const f32x2 c = fma2(bc(cd.x), nw2, pk(C0a, C0b)); C0a = lo_of(c); C0b = hi_of(c); }
+                { const f32x2 c = fma2(bc(cd.y), nw2, pk(C1a, C1b)); C1a = lo_of(c); C1b = hi_of(c); }
+                { const f32x2 c = fma2(bc(cd.z), nw2, pk(C2a, C2b)); C2a = lo_of(c); C2b = hi_of(c); }
+                { const f32x2 c = fma2(bc(cd.w), nw2, pk(Da, Db)); Da = lo_of(c); Db = hi_of(c); }
+                { const f32x2 Tn = fma2(nae2, T2, T2); Ta = lo_of(Tn); Tb = hi_of(Tn); }
                 const uint32_t idx = batch_first + (uint32_t)j + 1u;
                 last0 = ca ? idx : last0; last1 = cb ? idx : last1;
-                npfy2 = pk(terma ? -PIX_PARKED : lo_of(npfy2), termb ? -PIX_PARKED : hi_of(npfy2));
+                if (oka) nya = ca ? nya : -PIX_PARKED;
+                if (okb) nyb = cb ? nyb : -PIX_PARKED;
                 if (warp_hi) {
                     const uint32_t ba = __ballot_sync(0xffffffffu, ca && tTa > 0.5f), bb = __ballot_sync(0xffffffffu, cb && tTb > 0.5f);
                     if ((ba | bb) && lane == 0) atomicAdd(n_touched + lds32(a_j + 8), __popc(ba) + __popc(bb));
@@ -153,13 +158,13 @@ __global__ void __launch_bounds__(BF_THREADS, LVDGS_BF_MINBLOCKS) blend_forward_
     for (int qi = 0; qi < 2; ++qi) {
         if (!(qi ? in1 : in0)) continue;
         const size_t pix = (size_t)(qi ? py1 : py0) * W + px;
-        const float T = qi ? hi_of(T2) : lo_of(T2);
+        const float T = qi ? Tb : Ta;
         final_T[pix] = T;
         n_contrib[pix] = qi ? last1 : last0;
-        out_color[pix] = T * bg0 - (qi ? hi_of(C0) : lo_of(C0));      // the accumulators hold minus the sums
-        out_color[HW + pix] = T * bg1 - (qi ? hi_of(C1) : lo_of(C1));
-        out_color[2 * HW + pix] = T * bg2 - (qi ? hi_of(C2) : lo_of(C2));
-        out_depth[pix] = -(qi ? hi_of(D) : lo_of(D));
+        out_color[pix] = T * bg0 - (qi ? C0b : C0a);      // the accumulators hold minus the sums
+        out_color[HW + pix] = T * bg1 - (qi ? C1b : C1a);
+        out_color[2 * HW + pix] = T * bg2 - (qi ? C2b : C2a);
+        out_depth[pix] = -(qi ? Db : Da);
         out_opacity[pix] = 1.f - T;
     }
 }
