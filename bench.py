@@ -296,6 +296,16 @@ def main():
         per_view = {"ms_fwd_bwd": float(np.median(ts_)), "mpix_per_s": H * W / (float(np.median(ts_)) * 1e-3) / 1e6,
                     "what": "one view at a time on one stream (no overlap between views), median over this rank's first views"}
 
+    # where a step's time goes on THIS rank count: the rendering of the rank's views alone and the exchange step alone
+    # (raw-parameter chain rule, NCCL reduce-scatter, Adam on the slice, all-gather, activations), each as the max over ranks
+    def views_only():
+        eng.run_views(my_vcs, *[mapper.view(k) for k in ("means3D", "opacity", "scales", "rotations", "shs")], fixed_upstream)
+    ms_views, ms_views_ranks = time_steps(views_only, max(5, args.steps // 2), 2)
+    ms_exch, _ = time_steps(lambda: mapper.exchange_and_update(eng.grad_flat), max(5, args.steps // 2), 2)
+    step_split = {"views_ms": ms_views, "views_ms_by_rank": ms_views_ranks, "exchange_ms": ms_exch,
+                  "what": "timed apart, max over ranks: this rank's views through RasterEngine.run_views; "
+                          "ShardedMapper.exchange_and_update (activation chain rule, reduce-scatter, Adam, all-gather, activations)"}
+
     # BASELINE configs[2] names 1 M Gaussians for the mapping window: the same step on that map (extra key; the headline
     # metric is quoted at 500 k)
     mapping_1m = None
@@ -327,17 +337,23 @@ def main():
     d2h = res_host.numel() * 4
 
     copy_stream = torch.cuda.Stream(dev)
+    # one staging slot per view of the rank (7.5 MB each): a step queues every upload on the copy stream up front -- the
+    # cameras first (a render needs only its camera), then the target image / depth of each view (needed by its loss)
     stage = [dict(img=torch.empty(3, H, W, device=dev), dep=torch.empty(1, H, W, device=dev), cam=torch.empty(52, device=dev),
-                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+                  cam_ready=torch.cuda.Event(), ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in my_views]
 
-    def prefetch(j):
-        """H2D of view j's target image / depth / camera on the copy stream into staging slot j % 2."""
-        st, hb = stage[j % 2], host[my_views[j]]
-        copy_stream.wait_event(st["free"])                      # the previous user of the slot has consumed it
+    def prefetch_all():
+        """H2D of every view's camera, then target image / depth, on the copy stream (slot j = view j of this rank)."""
         with torch.cuda.stream(copy_stream):
-            st["img"].copy_(hb["img"], non_blocking=True); st["dep"].copy_(hb["dep"], non_blocking=True)
-            st["cam"].copy_(hb["cam"], non_blocking=True)
-            st["ready"].record(copy_stream)
+            for j, k in enumerate(my_views):
+                st = stage[j]
+                copy_stream.wait_event(st["free"])              # the previous step has consumed the slot
+                st["cam"].copy_(host[k]["cam"], non_blocking=True)
+                st["cam_ready"].record(copy_stream)
+            for j, k in enumerate(my_views):
+                st = stage[j]
+                st["img"].copy_(host[k]["img"], non_blocking=True); st["dep"].copy_(host[k]["dep"], non_blocking=True)
+                st["ready"].record(copy_stream)
 
     torch_loss = os.environ.get("LVDGS_E2E_TORCH_LOSS", "0") == "1"
 
@@ -346,15 +362,12 @@ def main():
         per-view losses (`loss_mapping +=`), ONE backward through all of them, one optimiser step."""
         cur = torch.cuda.current_stream()
         e2e_opt.zero_grad(set_to_none=True)
-        prefetch(0)
+        prefetch_all()
         total, poses = None, []
         for j, k in enumerate(my_views):
-            if j + 1 < len(my_views):
-                prefetch(j + 1)                                 # overlaps with this view's render
-            st = stage[j % 2]
-            cur.wait_event(st["ready"])
-            img, dep, cm = st["img"], st["dep"], st["cam"]
-            cmv = cm.clone()                                    # the staging slot is reused two views later; the backward reads the camera
+            st = stage[j]
+            cur.wait_event(st["cam_ready"])
+            img, dep, cmv = st["img"], st["dep"], st["cam"]     # the slot is not rewritten before the step's backward has run
             rs = dgr.GaussianRasterizationSettings(
                 image_height=H, image_width=W, tanfovx=cams[k].tanfovx, tanfovy=cams[k].tanfovy, bg=bgt, scale_modifier=1.0,
                 viewmatrix=cmv[0:16].view(4, 4), projmatrix=cmv[16:32].view(4, 4), projmatrix_raw=cmv[32:48].view(4, 4),
@@ -366,12 +379,12 @@ def main():
                 theta=theta, rho=rho)
             # mapping loss of utils/slam_utils.py:107-121 (0.9 L1 rgb + 0.1 L1 depth on the valid pixels) through the
             # package's fused loss op (lvdgs.slam_ops); LVDGS_E2E_TORCH_LOSS=1 uses the torch expression
+            cur.wait_event(st["ready"])                         # the loss is the first consumer of the targets
             if torch_loss:
                 loss = 0.9 * (color - img).abs().mean() + 0.1 * (depth - dep).abs().mean()
             else:
                 loss = slam_ops.fused_loss(color, depth, gt_image=img, gt_depth=dep, rgb_boundary_threshold=-1.0,
                                            w_rgb=0.9, w_depth=0.1)
-            st["free"].record(cur)                              # the loss forward has consumed the targets (autograd keeps its own tensors)
             total = loss if total is None else total + loss
             poses.append((loss, rho, theta, st))
         total.backward()
@@ -383,6 +396,8 @@ def main():
             for p_ in params:
                 dist.all_reduce(p_.grad)
         e2e_opt.step()
+        for st in stage:
+            st["free"].record(cur)                              # cameras (read by the backward) and targets consumed
         torch.cuda.current_stream().synchronize()               # the step's result is on the host
 
     for _ in range(max(3, args.warmup)):
@@ -601,10 +616,10 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "path": "diff_gaussian_rasterization.GaussianRasterizer (autograd) + "
                                 + ("torch L1 loss" if torch_loss else "lvdgs.slam_ops.fused_loss (mapping rgbd loss)") + ", losses summed over the window and one backward (as utils/slam_backend.py:167-306) + torch Adam; "
-                                "H2D of the next view prefetched on a copy stream"},
+                                "every view's H2D (camera, then target image / depth) queued on a copy stream at the start of the step"},
                 "e2e_c_abi": e2e_c_abi,
                 "gpu_launches": launches, "mapping_iters_per_s": 1e3 / ms, "ms_per_step_by_rank": ms_per_rank,
-                "per_view_unpipelined": per_view, "mapping_1m": mapping_1m, "clocks": clocks, "roofline": roof,
+                "per_view_unpipelined": per_view, "step_split": step_split, "mapping_1m": mapping_1m, "clocks": clocks, "roofline": roof,
                 "kernels": kernels, "cpu_baseline": cpu, "tracking": tracking}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -213,12 +213,13 @@ static int launch_bin_and_blend(const lvdgs_raster_params &p, const GeomPtrs &g,
     const int W = p.width, H = p.height;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const uint32_t *R_dev = g.num_instances;
-    LVDGS_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * (size_t)p.P, s));
+    // n_touched was zeroed by preprocess_forward; a re-run after a failed speculative launch counts again
+    if (rerun) LVDGS_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * (size_t)p.P, s));
     int sel = 0;
     // a re-run after a failed speculative launch: the emission counts the visible list (and claims tile slots) again
     if (rerun) LVDGS_CHECK(cudaMemsetAsync(g.num_instances + 2, 0, sizeof(uint32_t), s));
     if (p.flags & LVDGS_FLAG_GLOBAL_SORT) {
-        if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], b.vals[0], nullptr, nullptr, s)) return 1;
+        if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], b.vals[0], nullptr, nullptr, nullptr, s)) return 1;
         const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
         if (launch_sort_pairs(capacity, R_dev, b.keys[0], b.keys[1], b.vals[0], b.vals[1], end_bit, b.sort_ws,
                               sort_workspace_bytes(capacity), im.sort_hist, &sel, s)) return 1;
@@ -226,11 +227,13 @@ static int launch_bin_and_blend(const lvdgs_raster_params &p, const GeomPtrs &g,
         // instances go straight into their tile's segment of keys[0]; one CTA per tile sorts it into keys[1] / vals[1].
         // The cursors were zeroed together with the tile grid
         if (rerun) LVDGS_CHECK(cudaMemsetAsync(im.tile_cursor, 0, sizeof(uint32_t) * CURSOR_STRIDE * (size_t)gx * gy, s));
-        if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], nullptr, im.tile_cursor, im.ranges, s)) return 1;
+        if (launch_emit_keys(p.P, W, H, g, capacity, b.keys[0], nullptr, im.tile_cursor, im.ranges, b.sorted_sel, s)) return 1;
         if (launch_tile_sort(gx * gy, capacity, R_dev, im.ranges, im.tile_order, b.keys[0], b.keys[1], b.vals[1], long_lists, s)) return 1;
         sel = 1;
     }
-    LVDGS_CHECK(cudaMemcpyAsync(b.sorted_sel, &sel, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    // which of the two key / value buffers holds the sorted list (read by the tests' introspection only): the tile-segment
+    // path's emission kernel wrote it; the onesweep selector is known here
+    if (p.flags & LVDGS_FLAG_GLOBAL_SORT) LVDGS_CHECK(cudaMemcpyAsync(b.sorted_sel, &sel, sizeof(int32_t), cudaMemcpyHostToDevice, s));
     return launch_blend_forward(W, H, capacity, R_dev, im.ranges, b.vals[sel], g, im.tile_order, background, out_color, out_depth, out_opacity,
                                 im.final_T, im.n_contrib, n_touched, s);
 }
@@ -292,7 +295,7 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     // the tile grid + digit histograms are accumulated with atomics: one memset
     LVDGS_CHECK(cudaMemsetAsync(im.tile_grid, 0, il.total - il.tile_grid, s));
     if (launch_preprocess_forward(p, means3D, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
-                                  projmatrix, shs, campos, radii, g, im, s)) return 1;
+                                  projmatrix, shs, campos, radii, n_touched, g, im, s)) return 1;
     // block offsets, R, tile ranges and all digit histograms of the sort, from the block sums and per-tile counts
     if (launch_binning_prep(p.P, W, H, (p.flags & LVDGS_FLAG_GLOBAL_SORT) ? 32 + tile_bits((uint32_t)(gx * gy)) : 0, g, im, s)) return 1;
     LVDGS_CHECK(cudaMemcpyAsync(t_pinned_R, g.num_instances, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

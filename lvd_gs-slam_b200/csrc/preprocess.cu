@@ -148,6 +148,7 @@ struct PreArgs {
     float tanfovx, tanfovy, fx, fy, mod;
     const float *means3D, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp, *view, *proj, *shs, *campos;
     int32_t *radii;
+    int32_t *n_touched;        // zeroed here (the blend forward counts into it)
     GeomPtrs g;
 };
 
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(PRE_THREADS, LVDGS_PF_MINBLOCKS) preprocess_fo
         a.g.rect[i] = rect;
         a.g.tiles_touched[i] = touched;
         a.g.clamped[i] = clamped;
+        a.n_touched[i] = 0;
     }
     // ---- K2, first half: this block's instance count (binning_prep scans the block sums, emit_keys scans inside) ----
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -284,9 +286,10 @@ __global__ void __launch_bounds__(PRE_THREADS, LVDGS_PF_MINBLOCKS) preprocess_fo
 int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D, const float *colors_precomp,
                               const float *opacities, const float *scales, const float *rotations,
                               const float *cov3D_precomp, const float *view, const float *proj, const float *shs,
-                              const float *campos, int32_t *radii, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s) {
+                              const float *campos, int32_t *radii, int32_t *n_touched, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s) {
     PreArgs a;
     (void)im;
+    a.n_touched = n_touched;
     a.P = p.P; a.D = p.sh_degree; a.M = p.sh_coeffs; a.W = p.width; a.H = p.height;
     a.gx = (p.width + TILE - 1) / TILE; a.gy = (p.height + TILE - 1) / TILE;
     a.tanfovx = p.tan_fovx; a.tanfovy = p.tan_fovy;
@@ -351,6 +354,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) binning_count_kernel(int P, int
 }
 
 constexpr int PREP_THREADS = 1024;
+constexpr int PREP_VPT = 4;             // values per thread and scan round
 constexpr int WORK_BUCKETS = 128;
 // bucket 0 = heaviest: 4 buckets per octave of the list length, descending
 __device__ __forceinline__ int work_bucket(uint32_t c) {
@@ -399,26 +403,41 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
     if (tid == 0) s_longest = 0;
     const bool in_smem = cells <= PREP_GRID_SMEM;
     int32_t *grid = in_smem ? s_grid : grid_g;
-    for (int k = tid; k < SORT_MAX_PASSES * SORT_BINS; k += PREP_THREADS) s_h[k] = k < 4 * SORT_BINS ? hist[k] : 0u;
+    if (passes)      // the digit histograms exist only on the onesweep path
+        for (int k = tid; k < SORT_MAX_PASSES * SORT_BINS; k += PREP_THREADS) s_h[k] = k < 4 * SORT_BINS ? hist[k] : 0u;
     if (in_smem)
         for (int k = tid; k < cells; k += PREP_THREADS) s_grid[k] = grid_g[k];
     // (a) exclusive scan of the preprocess blocks' instance counts -> per-block key offsets, and R
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < nblocks; base += PREP_THREADS) {
-        const int b = base + tid;
-        const uint32_t c = b < nblocks ? block_sums[b] : 0u;
-        const uint32_t incl = prep_incl_scan(c, s_ws);
-        if (b < nblocks) block_sums[b] = s_carry + incl - c;
+    for (int base = 0; base < nblocks; base += PREP_THREADS * PREP_VPT) {      // four consecutive values per thread and round
+        const int b0 = base + tid * PREP_VPT;
+        uint32_t c[PREP_VPT], tsum = 0;
+#pragma unroll
+        for (int u = 0; u < PREP_VPT; ++u) { c[u] = b0 + u < nblocks ? block_sums[b0 + u] : 0u; tsum += c[u]; }
+        uint32_t run = s_carry + prep_incl_scan(tsum, s_ws) - tsum;
+#pragma unroll
+        for (int u = 0; u < PREP_VPT; ++u) { if (b0 + u < nblocks) block_sums[b0 + u] = run; run += c[u]; }
         __syncthreads();
         if (tid == 0) s_carry += s_ws[31];
         __syncthreads();
     }
     if (tid == 0) { *R_out = s_carry; s_carry = 0; }
     // (b) 2-D inclusive prefix sum of the difference array: along x per row, then along y per column
-    for (int y = tid; y <= gy; y += PREP_THREADS) {
-        int run = 0;
-        for (int x = 0; x <= gx; ++x) { run += grid[y * gw + x]; grid[y * gw + x] = run; }
+    for (int y = warp; y <= gy; y += PREP_THREADS / 32) {        // a warp per row, 32 cells per shuffle scan
+        int carry = 0;
+        for (int x0 = 0; x0 <= gx; x0 += 32) {
+            const int x = x0 + lane;
+            int v = x <= gx ? grid[y * gw + x] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += n;
+            }
+            v += carry;
+            if (x <= gx) grid[y * gw + x] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
     }
     __syncthreads();
     for (int x = tid; x <= gx; x += PREP_THREADS) {
@@ -428,22 +447,31 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
     __syncthreads();
     // (c) exclusive scan of the counts in tile order -> ranges; histograms of the key digits that hold the tile id
     const int tiles = gx * gy;
-    for (int base = 0; base < tiles; base += PREP_THREADS) {
-        const int t = base + tid;
-        uint32_t c = 0;
-        if (t < tiles) c = (uint32_t)grid[(t / gx) * gw + (t % gx)];
-        const uint32_t incl = prep_incl_scan(c, s_ws);
-        const uint32_t start = s_carry + incl - c;
-        if (t < tiles) {
-            ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
-            atomicAdd(&s_bucket[work_bucket(c)], 1u);
-            if (c >= 1536u) atomicMax(&s_longest, c);       // only long lists matter to the reader (tile_sort's class choice)
-            if (c) {
-                for (int q = 4; q < passes; ++q) {
-                    const int shift = 8 * (q - 4), nb = min(8, end_bit - 8 * q);
-                    atomicAdd(&s_h[q * SORT_BINS + (((uint32_t)t >> shift) & ((1u << nb) - 1u))], c);
+    for (int base = 0; base < tiles; base += PREP_THREADS * PREP_VPT) {
+        const int t0 = base + tid * PREP_VPT;
+        uint32_t c[PREP_VPT], tsum = 0;
+#pragma unroll
+        for (int u = 0; u < PREP_VPT; ++u) {
+            const int t = t0 + u;
+            c[u] = t < tiles ? (uint32_t)grid[(t / gx) * gw + (t % gx)] : 0u;
+            tsum += c[u];
+        }
+        uint32_t start = s_carry + prep_incl_scan(tsum, s_ws) - tsum;
+#pragma unroll
+        for (int u = 0; u < PREP_VPT; ++u) {
+            const int t = t0 + u;
+            if (t < tiles) {
+                ranges[t] = c[u] ? make_uint2(start, start + c[u]) : make_uint2(0u, 0u);
+                atomicAdd(&s_bucket[work_bucket(c[u])], 1u);
+                if (c[u] >= 1536u) atomicMax(&s_longest, c[u]);       // only long lists matter to the reader (tile_sort's class choice)
+                if (c[u]) {
+                    for (int q = 4; q < passes; ++q) {
+                        const int shift = 8 * (q - 4), nb = min(8, end_bit - 8 * q);
+                        atomicAdd(&s_h[q * SORT_BINS + (((uint32_t)t >> shift) & ((1u << nb) - 1u))], c[u]);
+                    }
                 }
             }
+            start += c[u];
         }
         __syncthreads();
         if (tid == 0) s_carry += s_ws[31];
@@ -451,11 +479,23 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
     }
     // (c') tile launch order for the blend kernels: heaviest lists first (longest-processing-time-first keeps the tail of
     // the launch short); a counting sort over ~quarter-octave buckets of the list length is plenty
-    if (tid == 0) {
-        uint32_t run = 0;
-        for (int b = 0; b < WORK_BUCKETS; ++b) { const uint32_t n = s_bucket[b]; s_bucket[b] = run; run += n; }
-        R_out[1] = s_longest;            // longest tile list (0 if below 1024), read back together with R
-        R_out[2] = 0u;                   // visible-Gaussian counter of the key emission that follows
+    if (warp == 0) {         // exclusive scan of the 128 bucket counts: 4 per lane
+        uint32_t n[WORK_BUCKETS / 32], sum = 0;
+#pragma unroll
+        for (int k = 0; k < WORK_BUCKETS / 32; ++k) { n[k] = s_bucket[lane * (WORK_BUCKETS / 32) + k]; sum += n[k]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < WORK_BUCKETS / 32; ++k) { s_bucket[lane * (WORK_BUCKETS / 32) + k] = run; run += n[k]; }
+        if (lane == 0) {
+            R_out[1] = s_longest;            // longest tile list (0 if below 1024), read back together with R
+            R_out[2] = 0u;                   // visible-Gaussian counter of the key emission that follows
+        }
     }
     __syncthreads();
     for (int t = tid; t < tiles; t += PREP_THREADS) {
@@ -463,7 +503,7 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
         tile_order[atomicAdd(&s_bucket[work_bucket(c)], 1u)] = (uint32_t)t;
     }
     // (d) exclusive scan of every digit histogram: one warp per pass, 8 bins per lane
-    if (warp < passes) {
+    if (warp < passes) {     // (after the tile loop's last barrier: s_h is complete)
         uint32_t v[8], sum = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { v[k] = s_h[warp * SORT_BINS + lane * 8 + k]; sum += v[k]; }
@@ -486,7 +526,8 @@ int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, con
     const bool onesweep = end_bit > 0;
     const int cells = (gx + 1) * (gy + 1);
     const size_t dyn = cells <= PREP_GRID_SMEM ? (size_t)cells * sizeof(int32_t) : 0;
-    {
+    {   // (fusing the four corner updates into preprocess_forward as global REDs was measured: 0.031 -> 0.070 ms there, the
+        // ~2 k cells serialise in L2; these few CTAs with shared-memory tables cost 0.010 ms)
         const int blocks = min(148, ceil_div(P, COUNT_THREADS * 2));
         LVDGS_PRE(s);
         binning_count_kernel<<<blocks, COUNT_THREADS, 4 * SORT_BINS * sizeof(uint32_t) + dyn, s>>>(
@@ -520,7 +561,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
                                                                  const float *__restrict__ depths,
                                                                  uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
                                                                  uint32_t *__restrict__ tile_cursor, const uint2 *__restrict__ ranges,
-                                                                 uint32_t *__restrict__ visible_list, uint32_t *__restrict__ num_visible) {
+                                                                 uint32_t *__restrict__ visible_list, uint32_t *__restrict__ num_visible, int32_t *__restrict__ sel_out) {
     __shared__ uint32_t s_end[EMIT_THREADS];      // inclusive offsets of this block's Gaussians
     __shared__ uint32_t s_vcnt[EMIT_THREADS / 32];
     __shared__ uint32_t s_vbase;
@@ -529,6 +570,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
     __shared__ uint32_t s_wsum[EMIT_THREADS / 32];
     const int g0 = blockIdx.x * EMIT_THREADS;
     const int i = g0 + threadIdx.x;
+    if (BUCKET && sel_out && i == 0) *sel_out = 1;              // the tile-segment sort leaves its result in keys[1] / vals[1]
     const uint32_t span_begin = block_offsets[blockIdx.x];      // exclusive prefix over the preceding blocks (binning_prep)
     // K2, second half: inclusive scan of this block's tile counts
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -567,6 +609,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
     if (is_vis) visible_list[s_vbase + s_vcnt[warp] + __popc(vis_ballot & ((1u << lane) - 1u))] = (uint32_t)i;
     const int last = min(EMIT_THREADS, P - g0) - 1;
     const uint32_t span_end = BUCKET ? s_end[last] : min(s_end[last], capacity);      // never write past the arena the launch was sized for
+    // (four instances per thread and round with their atomics in flight together was measured slower, 0.049 vs 0.045 ms: the
+    // kernel is bound by the L2 atomic units' throughput, not by the round trip)
     for (uint32_t r = span_begin + threadIdx.x; r < span_end; r += EMIT_THREADS) {
         // smallest j with s_end[j] > r
         int lo = 0, hi = last;
@@ -591,15 +635,15 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
 }
 
 int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, int64_t capacity, uint64_t *keys, uint32_t *vals,
-                     uint32_t *tile_cursor, const uint2 *ranges, cudaStream_t s) {
+                     uint32_t *tile_cursor, const uint2 *ranges, int32_t *sel_out, cudaStream_t s) {
     (void)H;
     const int gx = (W + TILE - 1) / TILE;
     const uint32_t cap = (uint32_t)min(capacity, (int64_t)0xffffffffll);
     LVDGS_PRE(s);
     if (tile_cursor)
-        emit_keys_kernel<true><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, tile_cursor, ranges, g.visible_list, g.num_instances + 2);
+        emit_keys_kernel<true><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, tile_cursor, ranges, g.visible_list, g.num_instances + 2, sel_out);
     else
-        emit_keys_kernel<false><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, nullptr, nullptr, g.visible_list, g.num_instances + 2);
+        emit_keys_kernel<false><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, nullptr, nullptr, g.visible_list, g.num_instances + 2, nullptr);
     LVDGS_LAUNCHED(s, "emit_keys");
     return 0;
 }

@@ -127,11 +127,13 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if _stale() and _nvcc() is not None:
+    # LVDGS_SO=<path>: load a variant built by scripts/build_variant.py (kernel-tuning experiments), no staleness check
+    so = os.environ.get("LVDGS_SO") or SO_PATH
+    if so == SO_PATH and _stale() and _nvcc() is not None:
         build()
-    if not os.path.exists(SO_PATH):
-        raise RuntimeError(f"{SO_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
-    L = C.CDLL(SO_PATH)
+    if not os.path.exists(so):
+        raise RuntimeError(f"{so} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(so)
     vp, i32, i64, sz, f = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float
     L.lvdgs_version.restype = C.c_int
     L.lvdgs_last_error.restype = C.c_char_p
