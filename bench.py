@@ -612,7 +612,9 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": bench_config(args, wl, W, H, world, len(my_views)),
                 "layout": {"views_per_rank": len(my_views),
-                           "parallelism": f"keyframes sharded over {world} rank(s), NCCL reduce-scatter of the [P,14] gradients + Adam on the shard + all-gather" if world > 1 else "1 GPU"},
+                           "parallelism": (f"keyframes sharded over {world} rank(s); exchange = " +
+                                           ("ONE kernel over NVLink peer memory (lvdgs_exchange_adam: peer loads of the gradient slice, chain rule, Adam on the shard, peer stores of parameters + activations)"
+                                            if mapper._p2p else "NCCL reduce-scatter of the [P,14] gradients + Adam on the shard + all-gather")) if world > 1 else "1 GPU"},
                 "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "path": "diff_gaussian_rasterization.GaussianRasterizer (autograd) + "
                                 + ("torch L1 loss" if torch_loss else "lvdgs.slam_ops.fused_loss (mapping rgbd loss)") + ", losses summed over the window and one backward (as utils/slam_backend.py:167-306) + torch Adam; "

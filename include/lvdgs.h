@@ -200,6 +200,23 @@ int lvdgs_adam_step(int64_t n, float *params, const float *grads, float *exp_avg
                     void *stream);
 
 /*
+ * The exchange step of the keyframe-sharded mapping iteration as ONE kernel over NVLink peer memory (the
+ * single-GPU reference calls GaussianModel.optimizer.step(), utils/slam_backend.py:378-380).  grad_ptrs / param_ptrs /
+ * act_ptrs: HOST arrays of `world` device pointers, entry r = rank r's gradient block / raw parameter block / activated
+ * block (opacity | scales | rotations) mapped into this process (peer access); act_ptrs NULL = the block holds no raw
+ * parameters.  For elements [lo, hi) of the block (this rank's slice, float4 aligned) the kernel sums the gradient over
+ * the ranks, applies the activation chain rule, Adam (moments exp_avg / exp_avg_sq are LOCAL full-size arrays, only the
+ * slice is touched) and stores the new raw values and activations into every rank's blocks.  group_end / lr as in
+ * lvdgs_adam_step (5 groups: means3D, shs, opacity, scales, rotations; every group starts 16-byte aligned);
+ * act_offsets[3]: starts of opacity / scales / rotations inside the activated block (floats), act_total its size.
+ * The caller provides the two cross-rank barriers around the launch.
+ */
+int lvdgs_exchange_adam(int32_t world, int32_t rank, const float *const *grad_ptrs, float *const *param_ptrs, float *const *act_ptrs,
+                        int64_t lo, int64_t hi, float *exp_avg, float *exp_avg_sq, int32_t groups, const int64_t *group_end,
+                        const float *lr, const int64_t *act_offsets, int64_t act_total, double beta1, double beta2, double eps,
+                        int32_t step, void *stream);
+
+/*
  * The binning sort on its own (stable LSD radix sort of u64 keys with u32 values over key bits
  * [0, end_bit)), exposed for parity tests and for the comparison against cub::DeviceRadixSort, the
  * library call upstream makes.  keys/vals: two buffers each of n elements; input in [0];

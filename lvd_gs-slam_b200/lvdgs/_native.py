@@ -15,7 +15,7 @@ SRC_DIR = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 SO_PATH = os.path.join(PKG_DIR, "liblvdgs.so")
 SOURCES = ["api.cu", "preprocess.cu", "radix_sort.cu", "tile_sort.cu", "slam_ops.cu", "blend_forward.cu", "blend_backward.cu",
-           "preprocess_backward.cu", "knn.cu", "adam.cu", "cub_compare.cu", "peak.cu", "ssim_loss.cu"]
+           "preprocess_backward.cu", "knn.cu", "adam.cu", "exchange.cu", "cub_compare.cu", "peak.cu", "ssim_loss.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("LVDGS_NVCC_DEFS", "").split()
 
@@ -119,7 +119,7 @@ EXPORTS = ["lvdgs_version", "lvdgs_last_error", "lvdgs_set_device", "lvdgs_launc
            "lvdgs_fused_loss_workspace_bytes", "lvdgs_fused_loss", "lvdgs_covis_counts", "lvdgs_n_obs",
            "lvdgs_compact_workspace_bytes", "lvdgs_compact_count", "lvdgs_compact_move", "lvdgs_pose_step", "lvdgs_gather_rows",
            "lvdgs_fp32_peak", "lvdgs_gaussian_activate", "lvdgs_gaussian_activation_backward",
-           "lvdgs_masked_ssim_loss_workspace_bytes", "lvdgs_masked_ssim_loss"]
+           "lvdgs_masked_ssim_loss_workspace_bytes", "lvdgs_masked_ssim_loss", "lvdgs_exchange_adam"]
 
 
 def lib():
@@ -156,6 +156,8 @@ def lib():
     L.lvdgs_dist2_workspace_bytes.restype = sz
     L.lvdgs_dist2.argtypes = [i32, vp, vp, vp, sz, vp]
     L.lvdgs_adam_step.argtypes = [i64, vp, vp, vp, vp, i32, C.POINTER(i64), C.POINTER(f), C.c_double, C.c_double, C.c_double, i32, vp]
+    L.lvdgs_exchange_adam.argtypes = [i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64, i64, vp, vp, i32, C.POINTER(i64),
+                                      C.POINTER(f), C.POINTER(i64), i64, C.c_double, C.c_double, C.c_double, i32, vp]
     L.lvdgs_sort_workspace_bytes.argtypes = [i64]
     L.lvdgs_sort_workspace_bytes.restype = sz
     L.lvdgs_sort_pairs.argtypes = [i64, vp, vp, vp, vp, i32, vp, sz, C.POINTER(i32), vp]

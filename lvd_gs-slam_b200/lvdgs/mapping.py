@@ -12,7 +12,12 @@ backward kernel adds into it, there is no pack kernel).  The exchange step per i
     updated parameters,
 
 i.e. the optimiser state is sharded (ZeRO-1): the same bytes cross NVLink as in an all-reduce, but the Adam kernel
-touches 1/world of the block on every rank and the gradient block is re-zeroed off the critical path.  With a backend
+touches 1/world of the block on every rank and the gradient block is re-zeroed off the critical path.
+On NVLink-connected GPUs of one node the three steps (plus the activation chain rule before and the activations after)
+are ONE kernel over peer memory (lvdgs_exchange_adam, csrc/exchange.cu): the parameter, activation and gradient blocks
+live in symmetric memory (torch.distributed._symmetric_memory), every rank reads its slice of all gradient blocks
+directly from its peers, updates it and stores the result into every peer's blocks; two device-side barriers bracket the
+launch.  LVDGS_P2P_EXCHANGE=0, or a failed rendezvous, selects the NCCL sequence above.  With a backend
 that has no reduce-scatter (gloo, the CPU tests) the block is all-reduced and every rank runs the identical full update.
 Either way the replicas stay bit-identical without a broadcast.
 
@@ -68,6 +73,8 @@ class ShardedMapper:
         # 3DGS / MonoGS default learning rates (the reference reads them from configs/mono/*/base_config.yaml opt_params)
         self.lrs = dict(lrs or {"means3D": 1.6e-4, "shs": 2.5e-3, "opacity": 5e-2, "scales": 1e-3, "rotations": 1e-3})
         self.betas, self.eps, self.t = betas, eps, 0
+        self._p2p = None           # symmetric-memory handles of the peer-memory exchange (None: NCCL sequence)
+        self._grad_block = None
         self._alloc(P)
         self.grad_norm_accum = torch.zeros(P, dtype=torch.float32, device=self.device)
         self.denom = torch.zeros(P, dtype=torch.float32, device=self.device)
@@ -76,11 +83,34 @@ class ShardedMapper:
         self._zero_done = None
 
     # ---- storage ----
+    def _want_p2p(self) -> bool:
+        import os
+        return (self.world > 1 and self.device.type == "cuda" and self.raw and self.optimizer_fn is None
+                and os.environ.get("LVDGS_P2P_EXCHANGE", "1") != "0" and dist.is_initialized()
+                and dist.get_backend(self.group) == "nccl")
+
     def _alloc(self, P: int):
         self.P = P
         self.layout, self.total = block_layout(P, self.M, multiple=4 * self.world)
         z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)
-        self.param_flat, self.exp_avg, self.exp_avg_sq = z(self.total), z(self.total), z(self.total)
+        self.exp_avg, self.exp_avg_sq = z(self.total), z(self.total)
+        self._p2p, self._grad_block = None, None
+        self._symm = {}
+        if self._want_p2p():
+            # parameter / activation / gradient blocks in symmetric memory: every rank can address every rank's copy
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                act_len = sum((self.layout[n][1] + 3) & ~3 for n in ACTIVATED) + 4 * self.world
+                for name, n in (("param", self.total), ("act", max(act_len, 4)), ("grad", self.total)):
+                    t = symm_mem.empty(n, dtype=torch.float32, device=self.device)
+                    t.zero_()
+                    self._symm[name] = (t, symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD))
+                self._p2p = {k: h for k, (t, h) in self._symm.items()}
+            except Exception as e:       # no peer access / no symmetric-memory support on this box: NCCL sequence
+                import warnings
+                warnings.warn(f"lvdgs: peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL reduce-scatter / all-gather")
+                self._symm, self._p2p = {}, None
+        self.param_flat = self._symm["param"][0] if self._p2p else z(self.total)
         self._bind()
         self.moments_sharded = False
 
@@ -93,7 +123,7 @@ class ShardedMapper:
                 ln = self.layout[n][1]
                 self.act_layout[n] = (off, ln)
                 off += (ln + 3) & ~3
-            self.act_flat = torch.zeros(max(off, 4), dtype=torch.float32, device=self.device)
+            self.act_flat = self._symm["act"][0] if self._p2p else torch.zeros(max(off, 4), dtype=torch.float32, device=self.device)
             self.act = {n: self.act_flat[o:o + ln] for n, (o, ln) in self.act_layout.items()}
         if self.optimizer_fn is not None:      # per-element learning rate, only for the stand-in optimisers of the CPU tests
             self.lr_flat = torch.zeros_like(self.param_flat)
@@ -105,6 +135,10 @@ class ShardedMapper:
 
     def new_grad_block(self) -> torch.Tensor:
         """A zeroed gradient block with this mapper's layout and padding (hand it to RasterEngine(grad_flat=...))."""
+        if self._p2p:              # the symmetric gradient block (one per mapper): the peer-memory exchange reads it remotely
+            self._grad_block = self._symm["grad"][0]
+            self._grad_block.zero_()
+            return self._grad_block
         return torch.zeros(self.total, dtype=torch.float32, device=self.device)
 
     # ---- views of the parameter block in the rasterizer's input layout ----
@@ -216,6 +250,8 @@ class ShardedMapper:
         """The exchange step of one iteration: raw-parameter chain rule, gradient SUM over the ranks, Adam, activations.
         NCCL: reduce-scatter -> Adam on this rank's slice -> all-gather of the parameters; the gradient block is zeroed
         for the next iteration on a side stream while the all-gather runs."""
+        if self._p2p and grad_flat is self._grad_block:
+            return self._exchange_p2p(grad_flat)
         self.activation_backward(grad_flat)
         if not self._can_scatter():
             self.reduce_gradients(grad_flat)
@@ -239,6 +275,32 @@ class ShardedMapper:
         dist.all_gather_into_tensor(self.param_flat, self.param_flat[self.shard], group=self.group)   # in place
         self.activate()
         cur.wait_event(self._zero_done)
+
+    def _exchange_p2p(self, grad_flat: torch.Tensor):
+        """barrier | ONE kernel: peer reads of the gradient slice, chain rule, Adam, peer stores of parameters + activations | barrier."""
+        C, _native, L = self._lib()
+        self.t += 1
+        hp, ha, hg = self._p2p["param"], self._p2p["act"], self._p2p["grad"]
+        if not hasattr(self, "_p2p_args") or self._p2p_args[0] is not hp:
+            W = self.world
+            arr = lambda h: (C.c_void_p * W)(*[int(x) for x in h.buffer_ptrs])
+            ends, lr = [], []
+            for n in GROUPS:
+                off, _ = self.layout[n]
+                ends.append(min((o for o, _ in self.layout.values() if o > off), default=self.total))
+            ends[-1] = self.total
+            act_off = (C.c_int64 * 3)(*[self.act_layout[n][0] for n in ACTIVATED])
+            self._p2p_args = (hp, arr(hg), arr(hp), arr(ha), (C.c_int64 * len(GROUPS))(*ends), act_off)
+        _, g_arr, p_arr, a_arr, ends, act_off = self._p2p_args
+        lr = (C.c_float * len(GROUPS))(*[float(self.lrs[n]) for n in GROUPS])
+        hg.barrier(channel=0)                                  # every rank's views have accumulated into its gradient block
+        rc = L.lvdgs_exchange_adam(self.world, self.rank, g_arr, p_arr, a_arr, self.shard.start, self.shard.stop,
+                                   _native.ptr(self.exp_avg), _native.ptr(self.exp_avg_sq), len(GROUPS), ends, lr, act_off,
+                                   self.act_flat.numel(), self.betas[0], self.betas[1], self.eps, self.t, self._stream())
+        _native.check(rc, "lvdgs_exchange_adam")
+        self.moments_sharded = True
+        hg.barrier(channel=1)                                  # all stores have landed, all gradient slices have been read
+        grad_flat.zero_()
 
     def gather_moments(self):
         """Makes exp_avg / exp_avg_sq complete on every rank again (before prune / densify move rows around)."""

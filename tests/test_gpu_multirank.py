@@ -42,8 +42,9 @@ def _job(device, world, rank):
     return mapper
 
 
-def _rank_main(rank, world, port, out_dir):
+def _rank_main(rank, world, port, out_dir, p2p):
     import sys
+    os.environ["LVDGS_P2P_EXCHANGE"] = "1" if p2p else "0"
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [root, os.path.join(root, "lvd_gs-slam_b200")]
     import torch.distributed as dist
@@ -55,8 +56,9 @@ def _rank_main(rank, world, port, out_dir):
         mapper = _job(dev, world, rank)
         assert mapper.moments_sharded
         mapper.gather_moments()
-        torch.save(dict(params=mapper.param_flat.cpu(), exp_avg=mapper.exp_avg.cpu(), layout=mapper.layout, t=mapper.t),
-                   os.path.join(out_dir, f"r{rank}.pt"))
+        torch.save(dict(params=mapper.param_flat.cpu(), exp_avg=mapper.exp_avg.cpu(), layout=mapper.layout, t=mapper.t,
+                        act=mapper.act_flat[:sum(ln for _, ln in mapper.act_layout.values())].cpu(), p2p=bool(mapper._p2p)),
+                   os.path.join(out_dir, f"r{rank}_{int(p2p)}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -67,9 +69,22 @@ def test_two_gpu_sharded_mapping_equals_single_gpu(tmp_path):
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    # the NCCL sequence (chain rule, reduce-scatter, Adam, all-gather, activate) ...
+    mp.spawn(_rank_main, args=(2, port, str(tmp_path), False), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "r0_0.pt"), torch.load(tmp_path / "r1_0.pt")
+    assert not r0["p2p"]
     assert torch.equal(r0["params"], r1["params"]) and torch.equal(r0["exp_avg"], r1["exp_avg"])      # replicas bit-identical
+    # ... and the same step as ONE kernel over peer memory (lvdgs_exchange_adam).  It sums the ranks' gradients first and
+    # applies the activation chain rule once (what autograd does on one GPU); the NCCL sequence applies it per rank and
+    # sums after, so the two agree up to float32 association (same criterion as against the single-GPU run below)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_rank_main, args=(2, port, str(tmp_path), True), nprocs=2, join=True)
+    q0, q1 = torch.load(tmp_path / "r0_1.pt"), torch.load(tmp_path / "r1_1.pt")
+    assert q0["p2p"] and q1["p2p"], "symmetric-memory rendezvous failed on this box: the peer-memory exchange did not run"
+    for key in ("params", "exp_avg", "act"):
+        assert torch.equal(q0[key], q1[key]), key                  # replicas bit-identical
+        bad = ~torch.isclose(q0[key], r0[key], rtol=1e-4, atol=1e-6)
+        assert float(bad.float().mean()) < 1e-3, (key, float(bad.float().mean()))
     single = _job(torch.device("cuda", 0), 1, 0)
     moved = 0.0
     for name, (off, ln) in single.layout.items():
