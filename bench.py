@@ -302,7 +302,13 @@ def main():
         eng.run_views(my_vcs, *[mapper.view(k) for k in ("means3D", "opacity", "scales", "rotations", "shs")], fixed_upstream)
     ms_views, ms_views_ranks = time_steps(views_only, max(5, args.steps // 2), 2)
     ms_exch, _ = time_steps(lambda: mapper.exchange_and_update(eng.grad_flat), max(5, args.steps // 2), 2)
-    step_split = {"views_ms": ms_views, "views_ms_by_rank": ms_views_ranks, "exchange_ms": ms_exch,
+    exch_phases = None
+    if mapper._p2p:       # device time of the phases of the peer-memory exchange on this rank (CUDA events around each)
+        mapper.time_exchange = True
+        time_steps(lambda: mapper.exchange_and_update(eng.grad_flat), max(5, args.steps // 2), 0)
+        mapper.time_exchange = False
+        exch_phases = mapper.exchange_phase_ms()
+    step_split = {"views_ms": ms_views, "views_ms_by_rank": ms_views_ranks, "exchange_ms": ms_exch, "exchange_phases_ms_rank0": exch_phases,
                   "what": "timed apart, max over ranks: this rank's views through RasterEngine.run_views; "
                           "ShardedMapper.exchange_and_update (activation chain rule, reduce-scatter, Adam, all-gather, activations)"}
 
@@ -613,7 +619,9 @@ def main():
                 "config": bench_config(args, wl, W, H, world, len(my_views)),
                 "layout": {"views_per_rank": len(my_views),
                            "parallelism": (f"keyframes sharded over {world} rank(s); exchange = " +
-                                           ("ONE kernel over NVLink peer memory (lvdgs_exchange_adam: peer loads of the gradient slice, chain rule, Adam on the shard, peer stores of parameters + activations)"
+                                           (("ONE kernel over NVSwitch multicast memory (lvdgs_exchange_adam: in-switch multimem.ld_reduce of the gradient slice, chain rule, Adam on the shard, multimem.st of parameters + activations to every rank)"
+                                             if mapper.exchange_mode == "multicast" else
+                                             "ONE kernel over NVLink peer memory (lvdgs_exchange_adam: peer loads of the gradient slice, chain rule, Adam on the shard, peer stores of parameters + activations)")
                                             if mapper._p2p else "NCCL reduce-scatter of the [P,14] gradients + Adam on the shard + all-gather")) if world > 1 else "1 GPU"},
                 "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "path": "diff_gaussian_rasterization.GaussianRasterizer (autograd) + "

@@ -14,6 +14,14 @@
 // groups) out, the same as reduce-scatter + all-gather, but there is one launch instead of five (chain rule, NCCL
 // reduce-scatter, Adam, NCCL all-gather, activate) and no staging copy.  The caller brackets the launch with two
 // cross-rank barriers (all gradients complete before; all stores landed and all gradient slices consumed after).
+//
+// With NVSwitch multicast mappings of the three blocks (mc_* != nullptr; torch symmetric memory's multicast_ptr) steps 1
+// and 4 run INSIDE the switch: one `multimem.ld_reduce.add.v4.f32` returns the sum of the slice over all ranks (the
+// switch pulls and adds the eight copies; 1/w of the unicast read traffic arrives at this GPU), and one `multimem.st`
+// per value is replicated by the switch to every rank (this GPU sends each byte once instead of w-1 times): per rank
+// and step block/w bytes in and (parameters + activated groups)/w bytes out, against (w-1) times that for peer loads
+// and stores.  The order of the in-switch sum is the switch's; replicas stay bit-identical because only the slice's
+// owner reduces and every rank receives the owner's result.
 #include "common.cuh"
 #include <cmath>
 
@@ -25,6 +33,8 @@ struct ExchangeArgs {
     const float *grad[EX_MAX_WORLD];     // every rank's gradient block (peer-mapped device pointers)
     float *param[EX_MAX_WORLD];          // every rank's raw parameter block
     float *act[EX_MAX_WORLD];            // every rank's activated block (opacity | scales | rotations), or nullptr (no activations)
+    const float *mc_grad;                // NVSwitch multicast mappings of the same three blocks, or nullptr (peer loads / stores)
+    float *mc_param, *mc_act;
     int world;
     int64_t lo4, hi4;                    // this rank's slice in float4 units
     int64_t group_end4[8];               // exclusive end of each parameter group in float4 units (means3D, shs, opacity, scales, rotations)
@@ -35,6 +45,17 @@ struct ExchangeArgs {
     int64_t act_total4;                                     // size of the activated block (the block's tail padding has no activation)
     float b1, b2, omb1, omb2, eps, inv_bc1, inv_sqrt_bc2;
 };
+
+__device__ __forceinline__ float4 multimem_sum4(const float4 *p) {        // in-switch reduction over every rank's copy
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_store4(float4 *p, float4 v) {     // one store, replicated by the switch to every rank
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 __device__ __forceinline__ float adam_update(float p, float g, float &m, float &v, float lr, const ExchangeArgs &a) {
     const float mi = a.b1 * m + a.omb1 * g;                  // same expressions as adam_step_kernel (adam.cu)
@@ -47,15 +68,20 @@ __device__ __forceinline__ float adam_update(float p, float g, float &m, float &
 __global__ void __launch_bounds__(256) exchange_adam_kernel(float4 *__restrict__ exp_avg, float4 *__restrict__ exp_avg_sq, const ExchangeArgs a) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = a.lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.hi4; i += stride) {
-        // 1. reduce: this element's gradient from every rank, summed in rank order (deterministic)
-        float4 gr[EX_MAX_WORLD];
+        // 1. reduce: this element's gradient from every rank -- in the switch, or summed here in rank order
+        float4 g;
+        if (a.mc_grad) {
+            g = multimem_sum4(reinterpret_cast<const float4 *>(a.mc_grad) + i);
+        } else {
+            float4 gr[EX_MAX_WORLD];
 #pragma unroll
-        for (int r = 0; r < EX_MAX_WORLD; ++r)
-            if (r < a.world) gr[r] = __ldcg(reinterpret_cast<const float4 *>(a.grad[r]) + i);      // L2 only: the line is remote and read once
-        float4 g = gr[0];
+            for (int r = 0; r < EX_MAX_WORLD; ++r)
+                if (r < a.world) gr[r] = __ldcg(reinterpret_cast<const float4 *>(a.grad[r]) + i);      // L2 only: the line is remote and read once
+            g = gr[0];
 #pragma unroll
-        for (int r = 1; r < EX_MAX_WORLD; ++r)
-            if (r < a.world) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }
+            for (int r = 1; r < EX_MAX_WORLD; ++r)
+                if (r < a.world) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }
+        }
         int grp = 0;
 #pragma unroll
         for (int k = 1; k < 8; ++k)
@@ -98,19 +124,24 @@ __global__ void __launch_bounds__(256) exchange_adam_kernel(float4 *__restrict__
             av = make_float4(p.x / n, p.y / n, p.z / n, p.w / n);
             ai = a.act_rot4 + (i - a.off_rot4);
         }
+        if (a.mc_param) {
+            multimem_store4(reinterpret_cast<float4 *>(a.mc_param) + i, p);
+            if (ai >= 0 && ai < a.act_total4) multimem_store4(reinterpret_cast<float4 *>(a.mc_act) + ai, av);
+        } else {
 #pragma unroll
-        for (int r = 0; r < EX_MAX_WORLD; ++r)
-            if (r < a.world) {
-                __stcg(reinterpret_cast<float4 *>(a.param[r]) + i, p);
-                if (ai >= 0 && ai < a.act_total4) __stcg(reinterpret_cast<float4 *>(a.act[r]) + ai, av);
-            }
+            for (int r = 0; r < EX_MAX_WORLD; ++r)
+                if (r < a.world) {
+                    __stcg(reinterpret_cast<float4 *>(a.param[r]) + i, p);
+                    if (ai >= 0 && ai < a.act_total4) __stcg(reinterpret_cast<float4 *>(a.act[r]) + ai, av);
+                }
+        }
     }
 }
 
 int launch_exchange_adam(int world, int rank, const float *const *grad_ptrs, float *const *param_ptrs, float *const *act_ptrs,
                          int64_t lo, int64_t hi, float *exp_avg, float *exp_avg_sq, int groups, const int64_t *group_end,
                          const float *lr, const int64_t *act_offsets, int64_t act_total, double beta1, double beta2, double eps, int step,
-                         cudaStream_t s) {
+                         const float *mc_grad, float *mc_param, float *mc_act, cudaStream_t s) {
     if (world < 1 || world >= EX_MAX_WORLD) { set_error("exchange: world must be 1..%d", EX_MAX_WORLD - 1); return 1; }
     if (rank < 0 || rank >= world) { set_error("exchange: bad rank"); return 1; }
     if (groups != 5) { set_error("exchange: the block has 5 parameter groups (means3D, shs, opacity, scales, rotations)"); return 1; }
@@ -123,6 +154,9 @@ int launch_exchange_adam(int world, int rank, const float *const *grad_ptrs, flo
         if (!a.grad[r] || !a.param[r]) { set_error("exchange: NULL peer pointer"); return 1; }
     }
     a.param[world] = param_ptrs[rank];            // this rank's own block, for the local read
+    // all three or none: a block without a multicast mapping keeps the whole step on peer loads / stores
+    const bool mc = mc_grad && mc_param && (mc_act || !act_ptrs);
+    a.mc_grad = mc ? mc_grad : nullptr; a.mc_param = mc ? mc_param : nullptr; a.mc_act = mc ? mc_act : nullptr;
     a.lo4 = lo / 4; a.hi4 = hi / 4;
     a.groups = groups;
     int64_t start = 0;

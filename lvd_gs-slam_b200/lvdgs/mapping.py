@@ -74,6 +74,8 @@ class ShardedMapper:
         self.lrs = dict(lrs or {"means3D": 1.6e-4, "shs": 2.5e-3, "opacity": 5e-2, "scales": 1e-3, "rotations": 1e-3})
         self.betas, self.eps, self.t = betas, eps, 0
         self._p2p = None           # symmetric-memory handles of the peer-memory exchange (None: NCCL sequence)
+        self.exchange_mode = "nccl"     # "multicast" / "peer" once the peer-memory exchange has run
+        self.time_exchange, self._phase_log = False, []
         self._grad_block = None
         self._alloc(P)
         self.grad_norm_accum = torch.zeros(P, dtype=torch.float32, device=self.device)
@@ -282,25 +284,60 @@ class ShardedMapper:
         self.t += 1
         hp, ha, hg = self._p2p["param"], self._p2p["act"], self._p2p["grad"]
         if not hasattr(self, "_p2p_args") or self._p2p_args[0] is not hp:
+            import os
             W = self.world
-            arr = lambda h: (C.c_void_p * W)(*[int(x) for x in h.buffer_ptrs])
-            ends, lr = [], []
+            base = lambda h: [int(x) + int(getattr(h, "offset", 0)) for x in h.buffer_ptrs]
+            arr = lambda h: (C.c_void_p * W)(*base(h))
+            ends = []
             for n in GROUPS:
                 off, _ = self.layout[n]
                 ends.append(min((o for o, _ in self.layout.values() if o > off), default=self.total))
             ends[-1] = self.total
             act_off = (C.c_int64 * 3)(*[self.act_layout[n][0] for n in ACTIVATED])
-            self._p2p_args = (hp, arr(hg), arr(hp), arr(ha), (C.c_int64 * len(GROUPS))(*ends), act_off)
-        _, g_arr, p_arr, a_arr, ends, act_off = self._p2p_args
+            # NVSwitch multicast mappings of the three blocks (0 when the box has no multicast support): the sum over the
+            # ranks and the replication of the results then happen inside the switch (multimem.ld_reduce / multimem.st)
+            mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in (hg, hp, ha)]
+            if os.environ.get("LVDGS_MULTICAST", "1") == "0" or not all(mc):
+                mc = [0, 0, 0]
+            else:
+                mc = [m + int(getattr(h, "offset", 0)) for m, h in zip(mc, (hg, hp, ha))]
+            self.exchange_mode = "multicast" if mc[0] else "peer"
+            self._p2p_args = (hp, arr(hg), arr(hp), arr(ha), (C.c_int64 * len(GROUPS))(*ends), act_off,
+                              [C.c_void_p(m) if m else None for m in mc])
+        _, g_arr, p_arr, a_arr, ends, act_off, mc = self._p2p_args
         lr = (C.c_float * len(GROUPS))(*[float(self.lrs[n]) for n in GROUPS])
+        ev = self._phase_events(5) if self.time_exchange else None
+        if ev: ev[0].record()
         hg.barrier(channel=0)                                  # every rank's views have accumulated into its gradient block
+        if ev: ev[1].record()
         rc = L.lvdgs_exchange_adam(self.world, self.rank, g_arr, p_arr, a_arr, self.shard.start, self.shard.stop,
                                    _native.ptr(self.exp_avg), _native.ptr(self.exp_avg_sq), len(GROUPS), ends, lr, act_off,
-                                   self.act_flat.numel(), self.betas[0], self.betas[1], self.eps, self.t, self._stream())
+                                   self.act_flat.numel(), self.betas[0], self.betas[1], self.eps, self.t, mc[0], mc[1], mc[2],
+                                   self._stream())
         _native.check(rc, "lvdgs_exchange_adam")
         self.moments_sharded = True
+        if ev: ev[2].record()
         hg.barrier(channel=1)                                  # all stores have landed, all gradient slices have been read
+        if ev: ev[3].record()
         grad_flat.zero_()
+        if ev: ev[4].record()
+
+    def _phase_events(self, n):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        self._phase_log.append(evs)
+        return evs
+
+    def exchange_phase_ms(self):
+        """Median device time of the phases of the peer-memory exchange recorded since `time_exchange` was switched on:
+        barrier | exchange kernel | barrier | gradient-block memset."""
+        import statistics
+        torch.cuda.synchronize(self.device)
+        rows = [[a.elapsed_time(b) for a, b in zip(e[:-1], e[1:])] for e in self._phase_log]
+        self._phase_log = []
+        if not rows:
+            return None
+        names = ("barrier_before", "exchange_kernel", "barrier_after", "zero_gradients")
+        return {n: statistics.median(r[k] for r in rows) for k, n in enumerate(names)}
 
     def gather_moments(self):
         """Makes exp_avg / exp_avg_sq complete on every rank again (before prune / densify move rows around)."""

@@ -23,6 +23,7 @@ from .engine import RasterEngine
 # offsets (in floats) inside lvdgs_pose_state (include/lvdgs.h)
 _VIEW, _PROJ, _PRAW, _CAMPOS, _R, _T, _EXPO, _M, _V, _STEP, _CONV, _TAUN, _SIZE = 0, 16, 32, 48, 52, 61, 64, 68, 76, 84, 85, 86, 88
 LOSS_OPACITY_WEIGHT = 1
+LOSS_DEPTH_NEEDS_OPAQUE = 2
 
 
 class _StateCamera:
@@ -53,6 +54,7 @@ class PoseTracker:
         self.bg = torch.tensor(bg, **f32)
         self.cam = _StateCamera(self.state, W, H, tanfovx, tanfovy, self.bg)
         self.g_color = torch.empty(3, H, W, **f32)
+        self.g_depth = None                      # allocated by the first RGB-D frame
         self.loss_out = torch.zeros(4, **f32)
         self.loss_ws = torch.zeros(self.L.lvdgs_fused_loss_workspace_bytes(), dtype=torch.uint8, device=self.dev)
         self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -93,14 +95,28 @@ class PoseTracker:
 
     # ---- one frame ----
     def track(self, means3D, opacities, scales, rotations, shs, gt_image, grad_mask=None, iters=100,
-              stop_when_converged=True):
-        """Runs up to `iters` tracking iterations against `gt_image` [3,H,W] (tracking rgb loss of
-        utils/slam_utils.py:53-62 with the exposure model of :43) and returns a dict with the number of pose steps taken,
-        the last loss (device scalar), and the engine's render / depth / opacity of the last forward."""
+              stop_when_converged=True, gt_depth=None, alpha=0.95):
+        """Runs up to `iters` tracking iterations against `gt_image` [3,H,W] and returns a dict with the number of pose
+        steps taken, the last loss (device scalar), and the engine's render / depth / opacity of the last forward.
+        gt_depth None (the monocular configs LVD-GS ships: get_loss_tracking always returns get_loss_tracking_rgb for
+        them, utils/slam_utils.py:45-49): the rgb loss of utils/slam_utils.py:53-62 with the exposure model of :43.
+        gt_depth [H,W] or [1,H,W] (RGB-D configs): get_loss_tracking_rgbd (:65-83), alpha * rgb + (1 - alpha) * depth term
+        over the pixels with gt_depth > 0.01 and rendered opacity > 0.95; the depth gradient then enters the pose-only
+        backward (ten sums per (warp, Gaussian) instead of the six moments of the rgb-only loop).
+        Difference from the reference loop: when the step converges, the returned render is one forward at the UPDATED
+        pose (the reference returns the render_pkg from before the last pose update, utils/slam_frontend.py:1523-1533)."""
         L, eng, cam, p = self.L, self.eng, self.cam, _native.ptr
         stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
         gt = gt_image if (gt_image.dtype is torch.float32 and gt_image.is_contiguous()) else gt_image.contiguous().float()
         gm = None if grad_mask is None else grad_mask.contiguous().float()
+        gtd = None
+        w_rgb, w_depth, flags = 1.0, 0.0, LOSS_OPACITY_WEIGHT
+        if gt_depth is not None:
+            gtd = gt_depth.reshape(self.H, self.W).contiguous().float()
+            w_rgb, w_depth, flags = float(alpha), 1.0 - float(alpha), LOSS_OPACITY_WEIGHT | LOSS_DEPTH_NEEDS_OPAQUE
+            if self.g_depth is None:
+                self.g_depth = torch.empty(self.H, self.W, dtype=torch.float32, device=self.dev)
+        g_depth = self.g_depth if gtd is not None else None
         expo = self.state[_EXPO:_EXPO + 2]
         g_expo = self.loss_out[1:3] if self.optimise_exposure else None
         sl = eng.slots[0]
@@ -110,11 +126,11 @@ class PoseTracker:
             eng.forward(cam, means3D, opacities, scales, rotations, shs)        # host waits for R here ...
             if stop_when_converged and steps > 0 and int(self._flag_host[0]) != 0:
                 break                                                           # ... so the previous step's flag has landed
-            _native.check(L.lvdgs_fused_loss(self.W, self.H, p(sl.color), None, p(sl.opacity), p(gt), None, p(gm), p(expo),
-                                             self.rgb_thr, 1.0, 0.0, LOSS_OPACITY_WEIGHT, p(self.g_color), None, None,
-                                             p(self.loss_out), p(self.loss_ws), self.loss_ws.numel(), stream),
+            _native.check(L.lvdgs_fused_loss(self.W, self.H, p(sl.color), p(sl.depth) if gtd is not None else None, p(sl.opacity),
+                                             p(gt), p(gtd), p(gm), p(expo), self.rgb_thr, w_rgb, w_depth, flags, p(self.g_color),
+                                             p(g_depth), None, p(self.loss_out), p(self.loss_ws), self.loss_ws.numel(), stream),
                           "lvdgs_fused_loss")
-            eng.backward(cam, means3D, opacities, scales, rotations, shs, self.g_color, None, None, pose_only=True)
+            eng.backward(cam, means3D, opacities, scales, rotations, shs, self.g_color, g_depth, None, pose_only=True)
             _native.check(L.lvdgs_pose_step(p(self.state), p(sl.g_tau), p(g_expo), self.lr[0], self.lr[1], self.lr[2],
                                             self.betas[0], self.betas[1], self.eps, it, self.threshold, stream),
                           "lvdgs_pose_step")

@@ -124,3 +124,50 @@ def test_native_tracking_stops_on_convergence():
     tr.set_camera(true_cam.R, true_cam.T, true_cam.projection_matrix)
     out = tr.track(pc.get_xyz, pc.get_opacity, pc.get_scaling, pc.get_rotation, pc.get_features, target, iters=50)
     assert out["steps"] == 1
+
+
+def test_native_rgbd_tracking_iteration_matches_autograd_through_the_reference_loss():
+    """RGB-D configs: one PoseTracker iteration with gt_depth = get_loss_tracking_rgbd (utils/slam_utils.py:65-83; the
+    reference's function when /root/reference is mounted, else the restatement pinned against it) + autograd through the
+    plugin: same loss, same pose gradient (the depth gradient enters the pose-only backward)."""
+    import ref_conventions as rc
+    dev = "cuda"
+    c = synth.make_camera("mast3r_kitti")
+    sc = synth.make_scene(30_000, c, seed=8)
+    sc["opacities"] = np.clip(sc["opacities"] * 1.6, 0.4, 0.99).astype(np.float32)
+    pc = Gaussians(sc, dev)
+    bg = torch.zeros(3, device=dev)
+    true_cam = Cam(c, dev)
+    with torch.no_grad():
+        pkg0 = render(true_cam, pc, Pipe(), bg)
+        target, target_depth = pkg0["render"].clone(), pkg0["depth"].clone()
+    rng = np.random.default_rng(3)
+    target_depth = target_depth * torch.tensor(rng.uniform(0.9, 1.1, tuple(target_depth.shape)).astype(np.float32), device=dev)
+    target_depth[0, :7, :] = 0.0                                   # pixels without a depth measurement
+    tau0 = torch.tensor([0.02, -0.03, 0.03, math.radians(0.3), math.radians(-0.2), math.radians(0.25)], device=dev)
+    T0 = SE3_exp(tau0)
+    cam1 = Cam(c, dev)
+    cam1.update_RT(T0[:3, :3].contiguous(), T0[:3, 3].contiguous())
+    cam1.original_image = target
+    cam1.mono_depth = target_depth[0].cpu().numpy()
+    cam1.grad_mask = torch.ones(1, c.image_height, c.image_width, device=dev)
+    config = {"Training": {"monocular": False, "rgb_boundary_threshold": 0.01, "alpha": 0.9}, "Dataset": {"depth_loss": True}}
+    pkg = render(cam1, pc, Pipe(), bg)
+    _, su, _, _ = rc.load()
+    loss1 = su.get_loss_tracking_rgbd(config, pkg["render"], pkg["depth"], pkg["opacity"], cam1)
+    loss1.backward()
+    tr = trk.PoseTracker(30_000, c.image_width, c.image_height, c.tanfovx, c.tanfovy, device=dev, optimise_exposure=False,
+                         rgb_boundary_threshold=0.01)
+    tr.set_camera(T0[:3, :3], T0[:3, 3], true_cam.projection_matrix)
+    out = tr.track(pc.get_xyz, pc.get_opacity, pc.get_scaling, pc.get_rotation, pc.get_features, target, iters=1,
+                   stop_when_converged=False, gt_depth=target_depth, alpha=0.9)
+    loss_rgbd = float(out["loss"])                 # (out["loss"] is a view of the tracker's result buffer: read it now)
+    assert abs(loss_rgbd - float(loss1)) < 2e-5 * float(loss1)
+    g_nat = tr.eng.slots[0].g_tau.cpu().numpy()
+    g_ref = np.concatenate([cam1.cam_trans_delta.grad.cpu().numpy(), cam1.cam_rot_delta.grad.cpu().numpy()])
+    np.testing.assert_allclose(g_nat, g_ref, rtol=5e-4, atol=2e-6 * np.abs(g_ref).max())
+    # and the rgb-only iteration on the same frame differs (the depth term is live)
+    tr.set_camera(T0[:3, :3], T0[:3, 3], true_cam.projection_matrix)
+    out_rgb = tr.track(pc.get_xyz, pc.get_opacity, pc.get_scaling, pc.get_rotation, pc.get_features, target, iters=1,
+                       stop_when_converged=False)
+    assert abs(float(out_rgb["loss"]) - loss_rgbd) > 1e-3 * loss_rgbd
