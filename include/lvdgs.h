@@ -43,6 +43,10 @@ extern "C" {
 #define LVDGS_FLAG_ZEROED_OUTPUTS 32 /* backward: the caller has zero-filled every gradient output; rows of culled Gaussians are
                                       then left alone and the backward walks only the visible Gaussians */
 
+#define LVDGS_FLAG_ZEROED_SCRATCH 64 /* backward: the caller has zero-filled `scratch` (the first lvdgs_backward_scratch_bytes bytes) since
+                                      the last backward that used it; the backward then skips its own memset.  lvdgs.engine clears a
+                                      slot's scratch on the forward stream, off the backward stream's critical path */
+
 /* which buffer a resize callback is asked for */
 #define LVDGS_BUF_GEOM 0
 #define LVDGS_BUF_BINNING 1
@@ -148,6 +152,9 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
                             const float *campos, lvdgs_resize_fn resize, void *resize_user, int64_t capacity_hint,
                             float *out_color, int32_t *radii, float *out_depth, float *out_opacity,
                             int32_t *n_touched, int64_t *num_rendered, int64_t *binning_capacity, void *stream);
+
+/* cudaMemsetAsync(ptr, 0, bytes, stream) for callers without a CUDA runtime binding (used with LVDGS_FLAG_ZEROED_SCRATCH). */
+int lvdgs_zero_async(void *ptr, size_t bytes, void *stream);
 
 /* Device scratch needed by lvdgs_rasterize_backward for P Gaussians and R instances. */
 size_t lvdgs_backward_scratch_bytes(int32_t P, int64_t R);

@@ -337,6 +337,12 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     return 0;
 }
 
+int lvdgs_zero_async(void *ptr, size_t bytes, void *stream) {
+    if (!ptr && bytes) { set_error("zero_async: NULL pointer"); return 1; }
+    if (bytes) LVDGS_CHECK(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream));
+    return 0;
+}
+
 size_t lvdgs_backward_scratch_bytes(int32_t P, int64_t R) {
     (void)R;
     return align_up((size_t)(P > 0 ? P : 1) * ACC_STRIDE * sizeof(float));
@@ -374,7 +380,9 @@ int lvdgs_rasterize_backward(const lvdgs_raster_params *prm, const float *backgr
     GeomPtrs g = geom_ptrs(const_cast<void *>(geom_buffer), p.P);
     ImgPtrs im = img_ptrs(const_cast<void *>(img_buffer), W, H);
     BlendGradPtrs bg{(float *)scratch};
-    LVDGS_CHECK(cudaMemsetAsync(scratch, 0, (size_t)p.P * ACC_STRIDE * sizeof(float), s));
+    if (!(p.flags & LVDGS_FLAG_ZEROED_SCRATCH)) LVDGS_CHECK(cudaMemsetAsync(scratch, 0, (size_t)p.P * ACC_STRIDE * sizeof(float), s));
+    // dL_dtau_sum is zeroed by the blend backward (first thread of the launch) when there is one
+    bool tau_zeroed = false;
     if (R > 0) {
         BinPtrs b = bin_ptrs(const_cast<void *>(binning_buffer), binning_capacity);
         const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
@@ -384,12 +392,13 @@ int lvdgs_rasterize_backward(const lvdgs_raster_params *prm, const float *backgr
         // with precomputed colours) nor, without a depth loss, the depth sum -> the six geometric moments only
         const bool moments_only = (p.flags & LVDGS_FLAG_POSE_ONLY) && !dL_dout_depth && (p.sh_degree == 0 || colors_precomp);
         if (launch_blend_backward(p.P, W, H, R, im.ranges, b.vals[sel], im.tile_order, g, background, im.final_T, im.n_contrib,
-                                  dL_dout_color, dL_dout_depth, dL_dout_opacity, p.flags, moments_only, bg, s)) return 1;
+                                  dL_dout_color, dL_dout_depth, dL_dout_opacity, p.flags, moments_only, bg, dL_dtau_sum, s)) return 1;
+        tau_zeroed = true;
     }
     if (launch_preprocess_backward(p, means3D, radii, shs, scales, rotations, cov3D_precomp, viewmatrix, projmatrix,
                                    projmatrix_raw, campos, g, bg, colors_precomp != nullptr, dL_dmeans2D, dL_dcolors,
                                    dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drots, dL_dtau,
-                                   dL_dtau_sum, s)) return 1;
+                                   dL_dtau_sum, tau_zeroed, s)) return 1;
     return 0;
 }
 

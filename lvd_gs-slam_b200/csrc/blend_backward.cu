@@ -120,11 +120,13 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
     const float4 *__restrict__ means2D, const float4 *__restrict__ conic_opacity, const float4 *__restrict__ rgbd,
     const uint32_t *__restrict__ tile_order, const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
     const float *__restrict__ dL_dout_color, const float *__restrict__ dL_dout_depth,
-    const float *__restrict__ dL_dout_opacity, float *__restrict__ acc) {
+    const float *__restrict__ dL_dout_opacity, float *__restrict__ acc, float *__restrict__ zero6) {
     __shared__ BlendRec s_rec[BB_BATCH];
     __shared__ uint32_t s_mask[BB_BATCH / 32][BB_WARPS];     // [group of 32 staged entries][pixel block]
     __shared__ uint32_t s_top[BB_WARPS];
 
+    // the pose-gradient sum the preprocess backward adds into (it runs after this launch): cleared here, not by a memset
+    if (zero6 && blockIdx.x == 0 && threadIdx.x < 6) zero6[threadIdx.x] = 0.f;
     const int tile = tile_order ? (int)__ldg(tile_order + blockIdx.x) : (int)blockIdx.x;   // heaviest tiles first
     const int tile_x = tile % gx, tile_y = tile / gx;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
 int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, const uint32_t *point_list,
                           const uint32_t *tile_order, const GeomPtrs &g, const float *bg, const float *final_T, const uint32_t *n_contrib,
                           const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_opacity,
-                          int flags, bool moments_only, const BlendGradPtrs &o, cudaStream_t s) {
+                          int flags, bool moments_only, const BlendGradPtrs &o, float *zero6, cudaStream_t s) {
     (void)P;
     if (R <= 0) return 0;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
@@ -323,11 +325,11 @@ int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, c
     if (moments_only)
         blend_backward_kernel<true><<<gx * gy, BB_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
                                                                          g.rgbd, tile_order, bg, final_T, n_contrib, dL_dout_color,
-                                                                         nullptr, dop, o.acc);
+                                                                         nullptr, dop, o.acc, zero6);
     else
         blend_backward_kernel<false><<<gx * gy, BB_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
                                                                           g.rgbd, tile_order, bg, final_T, n_contrib, dL_dout_color,
-                                                                          dL_dout_depth, dop, o.acc);
+                                                                          dL_dout_depth, dop, o.acc, zero6);
     LVDGS_LAUNCHED(s, "blend_backward");
     return 0;
 }

@@ -223,7 +223,7 @@ struct BlendGradPtrs {
 int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, const uint32_t *point_list,
                           const uint32_t *tile_order, const GeomPtrs &g, const float *bg, const float *final_T, const uint32_t *n_contrib,
                           const float *dL_dout_color, const float *dL_dout_depth, const float *dL_dout_opacity,
-                          int flags, bool moments_only, const BlendGradPtrs &o, cudaStream_t s);
+                          int flags, bool moments_only, const BlendGradPtrs &o, float *zero6, cudaStream_t s);
 
 int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3D, const int32_t *radii,
                                const float *shs, const float *scales, const float *rotations,
@@ -232,7 +232,7 @@ int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3
                                const BlendGradPtrs &bgp, bool colors_are_precomp, float *dL_dmeans2D,
                                float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D, float *dL_dcov3D,
                                float *dL_dsh, float *dL_dscales, float *dL_drots, float *dL_dtau,
-                               float *dL_dtau_sum, cudaStream_t s);     // uses g.visible_list when no output needs the culled rows
+                               float *dL_dtau_sum, bool tau_sum_zeroed, cudaStream_t s);     // uses g.visible_list when no output needs the culled rows
 
 int launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t s);
 

@@ -31,12 +31,14 @@ struct PbArgs {
     const int32_t *radii;
     const uint8_t *clamped;
     const float4 *conic_opacity;
-    const float *acc;
+    const float *acc;          // accumulator rows of the blend backward
+    bool zero_culled_means2D;  // compact mode: clear dL_dmeans2D rows of culled Gaussians here (no memset launch)
     float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drots,
         *dL_dtau, *dL_dtau_sum;
     // compact mode (accumulate / pose-only / pre-zeroed outputs, no per-Gaussian tau): thread j handles Gaussian visible_list[j], j < *num_visible.
     // Only ~40-60 % of a map is in view, so the kernel runs that fraction of the warps, all lanes live; culled rows are
-    // never touched (accumulate mode leaves them as they are; dL_dmeans2D is zeroed by the launcher)
+    // never touched (accumulate mode leaves them as they are; their dL_dmeans2D rows are cleared by the block that owns
+    // their index range)
     const uint32_t *visible_list, *num_visible;
 };
 
@@ -61,6 +63,12 @@ __global__ void __launch_bounds__(PB_THREADS, LVDGS_PB_MINBLOCKS) preprocess_bac
     else if (threadIdx.x >= 64 && threadIdx.x < 80) s_praw[threadIdx.x - 64] = __ldg(a.proj_raw + threadIdx.x - 64);
     int i = blockIdx.x * PB_THREADS + threadIdx.x;
     if (a.visible_list) {
+        // the per-view screen-space gradient of a culled Gaussian is zero: every block clears the culled rows of its own
+        // index range (the listed, i.e. visible, rows are written by whichever block walks them -- disjoint sets)
+        if (a.zero_culled_means2D && i < a.P && a.radii[i] <= 0) {
+            float *row = a.dL_dmeans2D + 3 * (size_t)i;
+            row[0] = 0.f; row[1] = 0.f; row[2] = 0.f;
+        }
         const uint32_t nv = __ldg(a.num_visible);
         if ((uint32_t)(blockIdx.x * PB_THREADS) >= nv) return;               // block-uniform
         i = (uint32_t)i < nv ? (int)__ldg(a.visible_list + i) : a.P;          // a.P: out of range, the lane idles
@@ -71,7 +79,7 @@ __global__ void __launch_bounds__(PB_THREADS, LVDGS_PB_MINBLOCKS) preprocess_bac
     float dmean[3] = {0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, tau[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float dscale[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
-    const bool live = i < a.P && a.radii[i] > 0;
+    const bool live = i < a.P && (a.visible_list != nullptr || a.radii[i] > 0);     // a listed Gaussian is visible
     // tracking (utils/slam_frontend.py:1468-1521) optimises the camera only: no Gaussian parameter needs a gradient
     const bool pose_only = (a.flags & LVDGS_FLAG_POSE_ONLY) != 0;
     if (live) {
@@ -79,6 +87,7 @@ __global__ void __launch_bounds__(PB_THREADS, LVDGS_PB_MINBLOCKS) preprocess_bac
         const float4 *row = reinterpret_cast<const float4 *>(a.acc + (size_t)i * ACC_STRIDE);
         const float4 m0 = row[0], m1 = row[1];
         r2 = row[2];
+
         const float4 co = a.conic_opacity[i];
         const float o = co.w;
         r0.x = -0.5f * (float)a.W * o * (co.x * m0.x + co.y * m0.y);
@@ -362,7 +371,7 @@ int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3
                                const BlendGradPtrs &bgp, bool colors_are_precomp, float *dL_dmeans2D,
                                float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D, float *dL_dcov3D,
                                float *dL_dsh, float *dL_dscales, float *dL_drots, float *dL_dtau,
-                               float *dL_dtau_sum, cudaStream_t s) {
+                               float *dL_dtau_sum, bool tau_sum_zeroed, cudaStream_t s) {
     PbArgs a;
     a.P = p.P; a.D = p.sh_degree; a.M = p.sh_coeffs; a.W = p.width; a.H = p.height; a.flags = p.flags;
     a.tanfovx = p.tan_fovx; a.tanfovy = p.tan_fovy;
@@ -374,13 +383,14 @@ int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3
     a.dL_dmeans2D = dL_dmeans2D; a.dL_dcolors = dL_dcolors; a.dL_dopacity = dL_dopacity; a.dL_dmeans3D = dL_dmeans3D;
     a.dL_dcov3D = dL_dcov3D; a.dL_dsh = colors_are_precomp ? nullptr : dL_dsh; a.dL_dscales = dL_dscales;
     a.dL_drots = dL_drots; a.dL_dtau = dL_dtau; a.dL_dtau_sum = dL_dtau_sum;
-    if (dL_dtau_sum) LVDGS_CHECK(cudaMemsetAsync(dL_dtau_sum, 0, 6 * sizeof(float), s));
+    if (dL_dtau_sum && !tau_sum_zeroed) LVDGS_CHECK(cudaMemsetAsync(dL_dtau_sum, 0, 6 * sizeof(float), s));
     // the culled rows matter only when something dense is written for them: parameter gradients in store mode, dL_dtau
     const bool zeroed = (p.flags & LVDGS_FLAG_ZEROED_OUTPUTS) != 0;
     const bool compact = ((p.flags & LVDGS_FLAG_ACCUMULATE) || (p.flags & LVDGS_FLAG_POSE_ONLY) || zeroed) && !dL_dtau;
     a.visible_list = compact ? g.visible_list : nullptr;
     a.num_visible = g.num_instances + 2;
-    if (compact && dL_dmeans2D && !zeroed) LVDGS_CHECK(cudaMemsetAsync(dL_dmeans2D, 0, 3 * sizeof(float) * (size_t)p.P, s));
+    a.zero_culled_means2D = compact && dL_dmeans2D && !zeroed;
+
     LVDGS_PRE(s);
     preprocess_backward_kernel<<<ceil_div(p.P, PB_THREADS), PB_THREADS, 0, s>>>(a);
     LVDGS_LAUNCHED(s, "preprocess_backward");

@@ -119,7 +119,7 @@ EXPORTS = ["lvdgs_version", "lvdgs_last_error", "lvdgs_set_device", "lvdgs_launc
            "lvdgs_fused_loss_workspace_bytes", "lvdgs_fused_loss", "lvdgs_covis_counts", "lvdgs_n_obs",
            "lvdgs_compact_workspace_bytes", "lvdgs_compact_count", "lvdgs_compact_move", "lvdgs_pose_step", "lvdgs_gather_rows",
            "lvdgs_fp32_peak", "lvdgs_gaussian_activate", "lvdgs_gaussian_activation_backward",
-           "lvdgs_masked_ssim_loss_workspace_bytes", "lvdgs_masked_ssim_loss", "lvdgs_exchange_adam"]
+           "lvdgs_masked_ssim_loss_workspace_bytes", "lvdgs_masked_ssim_loss", "lvdgs_exchange_adam", "lvdgs_zero_async"]
 
 
 def lib():
@@ -158,6 +158,7 @@ def lib():
     L.lvdgs_adam_step.argtypes = [i64, vp, vp, vp, vp, i32, C.POINTER(i64), C.POINTER(f), C.c_double, C.c_double, C.c_double, i32, vp]
     L.lvdgs_exchange_adam.argtypes = [i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64, i64, vp, vp, i32, C.POINTER(i64),
                                       C.POINTER(f), C.POINTER(i64), i64, C.c_double, C.c_double, C.c_double, i32, vp, vp, vp, vp]
+    L.lvdgs_zero_async.argtypes = [vp, sz, vp]
     L.lvdgs_sort_workspace_bytes.argtypes = [i64]
     L.lvdgs_sort_workspace_bytes.restype = sz
     L.lvdgs_sort_pairs.argtypes = [i64, vp, vp, vp, vp, i32, vp, sz, C.POINTER(i32), vp]

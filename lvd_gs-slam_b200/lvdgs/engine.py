@@ -25,6 +25,7 @@ from . import _native
 from ._native import RasterParams, ptr
 
 FLAG_EXACT_PP, FLAG_OPACITY_GRAD, FLAG_ACCUMULATE, FLAG_POSE_ONLY = 1, 2, 4, 8
+FLAG_ZEROED_SCRATCH = 64
 
 # parameter groups of the contiguous parameter / gradient block, in block order
 GROUPS = ("means3D", "shs", "opacity", "scales", "rotations")
@@ -86,6 +87,7 @@ class _Slot:
         self.g_tau = torch.empty(6, **f32)
         self.streams = ()            # side streams that use this slot's tensors (set by the engine)
         self.R = 0
+        self.scratch_clean = False   # the forward cleared the backward's accumulator rows (LVDGS_FLAG_ZEROED_SCRATCH)
         self.capacity = 0            # instances the binning arena was last laid out for
         self.hint = 0                # speculative-launch capacity hint for the next forward
 
@@ -194,6 +196,10 @@ class RasterEngine:
                                             ptr(sl.radii), ptr(sl.depth), ptr(sl.opacity), ptr(sl.n_touched),
                                             C.byref(R), C.byref(cap), self._stream(stream))
         _native.check(rc, "lvdgs_rasterize_forward")
+        # the backward's accumulator rows are cleared here, behind the forward on ITS stream (LVDGS_FLAG_ZEROED_SCRATCH): in
+        # run_views that is off the backward stream, which carries the critical path
+        self.L.lvdgs_zero_async(ptr(sl.scratch), C.c_size_t(self.L.lvdgs_backward_scratch_bytes(self.P, 0)), self._stream(stream))
+        sl.scratch_clean = True
         sl.R = int(R.value)
         sl.capacity = int(cap.value)
         sl.hint = max(int(sl.R * 1.25) + 65536, int(sl.hint * 0.98))
@@ -204,6 +210,9 @@ class RasterEngine:
         """pose_only (tracking): only slot.g_tau is produced, no parameter gradients and no screen-space gradients."""
         sl = self.slots[slot]
         flags = self.flags | (FLAG_ACCUMULATE if accumulate and not pose_only else 0) | (FLAG_POSE_ONLY if pose_only else 0)
+        if sl.scratch_clean:            # one backward per forward consumes the cleared scratch
+            flags |= FLAG_ZEROED_SCRATCH
+            sl.scratch_clean = False
         prm = self._params(vc, flags)
         g = {k: None for k in self.grads} if pose_only else self.grads
         rc = self.L.lvdgs_rasterize_backward(
