@@ -37,6 +37,13 @@ constexpr int BB_BATCH = BB_THREADS * BB_SPT;
 #define LVDGS_BB_DIRECT_MAX 2
 #endif
 constexpr int BB_DIRECT_MAX = LVDGS_BB_DIRECT_MAX;   // up to this many contributing threads: skip the warp reduction
+// LVDGS_BB_PIPE: three staging buffers handed between the warps through mbarriers instead of two CTA barriers per batch: a
+// warp waits for another one only when that one is more than a batch behind (the per-block hit counts of a batch differ, and
+// with __syncthreads the busiest block of every batch sets the pace of all four)
+#ifndef LVDGS_BB_PIPE
+#define LVDGS_BB_PIPE 0
+#endif
+constexpr int BB_NBUF = LVDGS_BB_PIPE ? 3 : 1;
 
 // Transposing warp reduction of TEN values per lane: at every butterfly step a lane keeps half of its values and hands
 // the other half to its partner, so the value count halves while the lane span halves (5 + 3 + 2 + 1 + 1 = 12 shuffles
@@ -64,6 +71,22 @@ __device__ __forceinline__ float bsel(uint32_t m, float a, float b) {      // m 
     return d;
 }
 #define LVDGS_SHX(x, d) __shfl_xor_sync(0xffffffffu, (x), (d))
+
+// shared-memory mbarriers: arrive is non-blocking, waiting is on the phase parity -- the four warps of a tile hand staged
+// batches to each other without ever meeting at a CTA-wide barrier (LVDGS_BB_PIPE)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{ .reg .pred p;\n"
+                 "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra D;\n"
+                 "bra W;\n"
+                 "D: }" :: "r"(bar), "r"(parity) : "memory");
+}
 // returns MINUS the warp-wide sum (the visit's values are negated sums, see the hot loop)
 __device__ __forceinline__ float transpose_reduce10(const float (&v)[10], const LaneMasks &L) {
     float w[5], x[3], y[2];
@@ -121,9 +144,12 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
     const uint32_t *__restrict__ tile_order, const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
     const float *__restrict__ dL_dout_color, const float *__restrict__ dL_dout_depth,
     const float *__restrict__ dL_dout_opacity, float *__restrict__ acc, float *__restrict__ zero6) {
-    __shared__ BlendRec s_rec[BB_BATCH];
-    __shared__ uint32_t s_mask[BB_BATCH / 32][BB_WARPS];     // [group of 32 staged entries][pixel block]
+    __shared__ BlendRec s_rec[BB_NBUF][BB_BATCH];
+    __shared__ uint32_t s_mask[BB_NBUF][BB_BATCH / 32][BB_WARPS];     // [buffer][group of 32 staged entries][pixel block]
     __shared__ uint32_t s_top[BB_WARPS];
+#if LVDGS_BB_PIPE
+    __shared__ uint64_t s_bar[2 * BB_NBUF];                  // FULL[b] (every thread arrives), EMPTY[b] (one arrival per warp)
+#endif
 
     // the pose-gradient sum the preprocess backward adds into (it runs after this launch): cleared here, not by a memset
     if (zero6 && blockIdx.x == 0 && threadIdx.x < 6) zero6[threadIdx.x] = 0.f;
@@ -137,7 +163,7 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
     const float tx0 = (float)(tile_x * TILE), ty0 = (float)(tile_y * TILE);
     const size_t HW = (size_t)H * W;
     const uint2 range = ranges[tile];
-    const uint32_t a_rec = smem_u32(s_rec);
+    const uint32_t a_rec0 = smem_u32(s_rec);
 
     // per-pixel state, packed (lo = row py0, hi = row py0 + 4)
     uint32_t last[2];
@@ -188,8 +214,8 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
     // entries are visited in decreasing contributor index k = top-1 ... 0
     // entry j of a batch has contributor index k = remaining - 1 - j; "k < n_contrib" is tested as j >= thr
     int thr0 = (int)top - (int)last[0], thr1 = (int)top - (int)last[1];
-    for (int remaining = (int)top; remaining > 0; remaining -= BB_BATCH, thr0 -= BB_BATCH, thr1 -= BB_BATCH) {
-        __syncthreads();
+    // stage(): every thread loads BB_SPT instances of the batch whose first (rearmost) entry has contributor index remaining - 1
+    auto stage = [&](int remaining, BlendRec *rec, uint32_t (*msk)[BB_WARPS]) {
         const int nb = min(BB_BATCH, remaining);
 #pragma unroll
         for (int u = 0; u < BB_SPT; ++u) {
@@ -199,10 +225,10 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
                 const uint32_t id = __ldg(point_list + range.x + (uint32_t)(remaining - 1 - e));
                 const float4 m = __ldg(means2D + id);
                 const float4 co = __ldg(conic_opacity + id);
-                s_rec[e].xy = make_float2(m.x, m.y);
-                s_rec[e].id = id;
-                s_rec[e].co = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, -co.w);   // as forward
-                s_rec[e].cd = __ldg(rgbd + id);
+                rec[e].xy = make_float2(m.x, m.y);
+                rec[e].id = id;
+                rec[e].co = make_float4(-0.5f * LOG2E * co.x, -LOG2E * co.y, -0.5f * LOG2E * co.z, -co.w);   // as forward
+                rec[e].cd = __ldg(rgbd + id);
                 const float rx = m.x - tx0, ry = m.y - ty0;
                 uint32_t xb = 0, yb = 0;
                 if (!(rx + m.z < 0.f) && !(rx - m.z > 7.f)) xb |= 1u;
@@ -228,12 +254,14 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
 #pragma unroll
             for (int r = 0; r < BB_WARPS; ++r) {
                 const uint32_t m = __ballot_sync(0xffffffffu, (blocks >> r) & 1u);
-                if (lane == r) s_mask[u * BB_WARPS + warp][r] = m;
+                if (lane == r) msk[u * BB_WARPS + warp][r] = m;
             }
         }
-        __syncthreads();
+    };
+    // process(): this warp visits the staged instances that can reach its block
+    auto process = [&](int remaining, uint32_t a_rec, const uint32_t (*msk)[BB_WARPS]) {
         for (int wp = 0; wp < BB_BATCH / 32; ++wp) {
-            uint32_t mask = s_mask[wp][warp];
+            uint32_t mask = msk[wp][warp];
             {   // entries with contributor index >= wtop (j < remaining - wtop) contribute to no pixel of this warp
                 const int first_j = remaining - (int)wtop - wp * 32;
                 if (first_j >= 32) mask = 0; else if (first_j > 0) mask &= ~((1u << first_j) - 1u);
@@ -310,7 +338,43 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
                 }
             }
         }
+    };
+#if !LVDGS_BB_PIPE
+    for (int remaining = (int)top; remaining > 0; remaining -= BB_BATCH, thr0 -= BB_BATCH, thr1 -= BB_BATCH) {
+        __syncthreads();
+        stage(remaining, s_rec[0], s_mask[0]);
+        __syncthreads();
+        process(remaining, a_rec0, s_mask[0]);
     }
+#else
+    const int nbatch = ((int)top + BB_BATCH - 1) / BB_BATCH;
+    const uint32_t a_bar = smem_u32(s_bar);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < BB_NBUF; ++b) { mbar_init(a_bar + 8 * b, BB_THREADS); mbar_init(a_bar + 8 * (BB_NBUF + b), BB_WARPS); }
+    }
+    __syncthreads();
+    for (int k = 0; k < 2 && k < nbatch; ++k) {             // prologue: two batches in flight
+        stage((int)top - k * BB_BATCH, s_rec[k], s_mask[k]);
+        mbar_arrive(a_bar + 8 * k);
+    }
+    int b = 0, ph = 0;                                       // buffer and phase parity of batch k
+    for (int k = 0, remaining = (int)top; k < nbatch; ++k, remaining -= BB_BATCH, thr0 -= BB_BATCH, thr1 -= BB_BATCH) {
+        mbar_wait(a_bar + 8 * b, (uint32_t)ph);              // every thread's share of batch k has been staged
+        process(remaining, a_rec0 + (uint32_t)b * (uint32_t)(BB_BATCH * sizeof(BlendRec)), s_mask[b]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_bar + 8 * (BB_NBUF + b));      // this warp is done with buffer b
+        if (k + 2 < nbatch) {
+            // batch k + 2 goes where batch k - 1 was: wait until all four warps have left that one (they are at most a
+            // batch behind in the common case, so this rarely blocks)
+            const int b2 = b == 0 ? 2 : b - 1;
+            if (k >= 1) mbar_wait(a_bar + 8 * (BB_NBUF + b2), (uint32_t)(b == 0 ? ph ^ 1 : ph));
+            stage(remaining - 2 * BB_BATCH, s_rec[b2], s_mask[b2]);
+            mbar_arrive(a_bar + 8 * b2);
+        }
+        if (++b == BB_NBUF) { b = 0; ph ^= 1; }
+    }
+#endif
 }
 
 int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, const uint32_t *point_list,
