@@ -551,8 +551,13 @@ def main():
         kernels.sort(key=lambda e: -e["ms_per_view"])
         dom = next((e for e in kernels if "bound" in e), None)
         traffic, ncu = None, None
-        try:   # one `ncu --set full` capture of the same kernel, committed under profiles/ (per launch, like `achieved`)
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernel_metrics.json"))).get(dom["kernel"])
+        try:   # one `ncu --set full` capture per kernel, committed under profiles/ (per launch, like `achieved`)
+            ncu_all = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernel_metrics.json")))
+            for e in kernels:      # DRAM bytes of the captured launch (view 0) beside the algorithmic bytes of the mean view
+                if e["kernel"] in ncu_all and e.get("bound") == "hbm":
+                    e["ncu_dram_bytes_view0"] = ncu_all[e["kernel"]]["dram_bytes"]
+                    e["algorithmic_bytes_per_view"] = alg[e["kernel"]][1]
+            ncu = ncu_all.get(dom["kernel"])
             traffic = ncu["dram_bytes"]
         except Exception:
             pass
