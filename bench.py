@@ -237,10 +237,11 @@ def main():
         def step():
             args_ = [mp_.view(k) for k in ("means3D", "opacity", "scales", "rotations", "shs")]
             # forward of view k+1 overlaps the backward of view k (two streams, two buffer slots); gradients accumulate
-            eng_.run_views(my_vcs, *args_, fixed_upstream)
-            # chain rule to the raw parameters, SUM over the keyframe shards (NCCL reduce-scatter), Adam on this rank's
-            # slice, all-gather of the parameters, activations; leaves the gradient block zeroed
-            mp_.exchange_and_update(eng_.grad_flat)
+            eng_.run_views(my_vcs, *args_, fixed_upstream, bwd_wait=mp_.grad_ready)
+            # SUM over the keyframe shards, chain rule to the raw parameters, Adam on this rank's slice, new parameters to
+            # every rank, activations (one kernel over NVSwitch multicast / peer memory, or the NCCL sequence); the
+            # gradient block is cleared on a side stream, the next step's first backward waits for that (grad_ready)
+            mp_.exchange_and_update(eng_.grad_flat, defer_zero=True)
         return step
 
     def time_steps(step, steps, warmup):

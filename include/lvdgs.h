@@ -219,12 +219,16 @@ int lvdgs_adam_step(int64_t n, float *params, const float *grads, float *exp_avg
  * mc_grad / mc_param / mc_act: NVSwitch MULTICAST mappings of the three blocks (torch symmetric memory's multicast_ptr), or
  * NULL.  With all of them the sum over the ranks is one in-switch `multimem.ld_reduce` and every result is sent once and
  * replicated by the switch (`multimem.st`); without, the kernel loads from / stores to every peer itself.
+ * act_mode: 0 = the block holds no raw parameters (no chain rule, no activations; act_ptrs may be NULL); 1 = raw block, the
+ * kernel stores the activations of its slice into every rank's activated block; 2 = raw block, activations are NOT
+ * stored -- the caller runs lvdgs_gaussian_activate over the whole block after the closing barrier (8 of the 14 floats per
+ * Gaussian less over NVLink for one local pass over HBM).
  * The caller provides the two cross-rank barriers around the launch.
  */
 int lvdgs_exchange_adam(int32_t world, int32_t rank, const float *const *grad_ptrs, float *const *param_ptrs, float *const *act_ptrs,
                         int64_t lo, int64_t hi, float *exp_avg, float *exp_avg_sq, int32_t groups, const int64_t *group_end,
                         const float *lr, const int64_t *act_offsets, int64_t act_total, double beta1, double beta2, double eps,
-                        int32_t step, const float *mc_grad, float *mc_param, float *mc_act, void *stream);
+                        int32_t step, const float *mc_grad, float *mc_param, float *mc_act, int32_t act_mode, void *stream);
 
 /*
  * The binning sort on its own (stable LSD radix sort of u64 keys with u32 values over key bits

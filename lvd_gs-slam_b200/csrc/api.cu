@@ -430,11 +430,11 @@ int lvdgs_adam_step(int64_t n, float *params, const float *grads, float *exp_avg
 int lvdgs_exchange_adam(int32_t world, int32_t rank, const float *const *grad_ptrs, float *const *param_ptrs, float *const *act_ptrs,
                         int64_t lo, int64_t hi, float *exp_avg, float *exp_avg_sq, int32_t groups, const int64_t *group_end,
                         const float *lr, const int64_t *act_offsets, int64_t act_total, double beta1, double beta2, double eps,
-                        int32_t step, const float *mc_grad, float *mc_param, float *mc_act, void *stream) {
+                        int32_t step, const float *mc_grad, float *mc_param, float *mc_act, int32_t act_mode, void *stream) {
     if (!grad_ptrs || !param_ptrs || !exp_avg || !exp_avg_sq || !group_end || !lr || step < 1) { set_error("exchange: bad arguments"); return 1; }
     g_debug_sync = 0;
     return launch_exchange_adam(world, rank, grad_ptrs, param_ptrs, act_ptrs, lo, hi, exp_avg, exp_avg_sq, groups, group_end, lr,
-                                act_offsets, act_total, beta1, beta2, eps, step, mc_grad, mc_param, mc_act, (cudaStream_t)stream);
+                                act_offsets, act_total, beta1, beta2, eps, step, mc_grad, mc_param, mc_act, act_mode, (cudaStream_t)stream);
 }
 
 size_t lvdgs_fused_loss_workspace_bytes(void) { return fused_loss_workspace_bytes(); }

@@ -268,7 +268,7 @@ int launch_pose_step(lvdgs_pose_state *state, const float *g_tau, const float *g
 int launch_exchange_adam(int world, int rank, const float *const *grad_ptrs, float *const *param_ptrs, float *const *act_ptrs,
                          int64_t lo, int64_t hi, float *exp_avg, float *exp_avg_sq, int groups, const int64_t *group_end,
                          const float *lr, const int64_t *act_offsets, int64_t act_total, double beta1, double beta2, double eps,
-                         int step, const float *mc_grad, float *mc_param, float *mc_act, cudaStream_t s);
+                         int step, const float *mc_grad, float *mc_param, float *mc_act, int act_mode, cudaStream_t s);
 
 int launch_fp32_peak(int blocks, int iters, int mode, float *out, double *fmas, cudaStream_t s);
 

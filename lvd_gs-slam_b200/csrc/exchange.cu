@@ -36,6 +36,7 @@ struct ExchangeArgs {
     const float *mc_grad;                // NVSwitch multicast mappings of the same three blocks, or nullptr (peer loads / stores)
     float *mc_param, *mc_act;
     int world;
+    int raw, store_act;                  // block holds raw parameters (chain rule applies); activations are stored by this kernel
     int64_t lo4, hi4;                    // this rank's slice in float4 units
     int64_t group_end4[8];               // exclusive end of each parameter group in float4 units (means3D, shs, opacity, scales, rotations)
     float lr[8];
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) exchange_adam_kernel(float4 *__restrict__
         // every rank's parameter block is identical: read the local one (slot `world` = this rank's own block)
         float4 p = reinterpret_cast<const float4 *>(a.param[a.world])[i];
         // 2. chain rule through the activation of this group (act != nullptr: the block holds raw parameters)
-        const bool raw = a.act[0] != nullptr;
+        const bool raw = a.raw != 0;
         if (raw && grp == 2) {              // opacity = sigmoid(raw)
             const float o0 = 1.f / (1.f + expf(-p.x)), o1 = 1.f / (1.f + expf(-p.y)), o2 = 1.f / (1.f + expf(-p.z)), o3 = 1.f / (1.f + expf(-p.w));
             g.x *= o0 * (1.f - o0); g.y *= o1 * (1.f - o1); g.z *= o2 * (1.f - o2); g.w *= o3 * (1.f - o3);
@@ -113,7 +114,9 @@ __global__ void __launch_bounds__(256) exchange_adam_kernel(float4 *__restrict__
         // 4. all-gather + activate: the new raw values and their activations go to every rank
         float4 av = p;
         int64_t ai = -1;
-        if (raw && grp == 2) {
+        if (!a.store_act) {
+            // the caller activates the whole block locally after the closing barrier: 8 of the 14 floats per Gaussian less on the wire
+        } else if (raw && grp == 2) {
             av = make_float4(1.f / (1.f + expf(-p.x)), 1.f / (1.f + expf(-p.y)), 1.f / (1.f + expf(-p.z)), 1.f / (1.f + expf(-p.w)));
             ai = a.act_opacity4 + (i - a.off_opacity4);
         } else if (raw && grp == 3) {
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(256) exchange_adam_kernel(float4 *__restrict__
 int launch_exchange_adam(int world, int rank, const float *const *grad_ptrs, float *const *param_ptrs, float *const *act_ptrs,
                          int64_t lo, int64_t hi, float *exp_avg, float *exp_avg_sq, int groups, const int64_t *group_end,
                          const float *lr, const int64_t *act_offsets, int64_t act_total, double beta1, double beta2, double eps, int step,
-                         const float *mc_grad, float *mc_param, float *mc_act, cudaStream_t s) {
+                         const float *mc_grad, float *mc_param, float *mc_act, int act_mode, cudaStream_t s) {
     if (world < 1 || world >= EX_MAX_WORLD) { set_error("exchange: world must be 1..%d", EX_MAX_WORLD - 1); return 1; }
     if (rank < 0 || rank >= world) { set_error("exchange: bad rank"); return 1; }
     if (groups != 5) { set_error("exchange: the block has 5 parameter groups (means3D, shs, opacity, scales, rotations)"); return 1; }
@@ -149,13 +152,15 @@ int launch_exchange_adam(int world, int rank, const float *const *grad_ptrs, flo
     if (hi == lo) return 0;
     ExchangeArgs a{};
     a.world = world;
+    if (act_mode < 0 || act_mode > 2 || (act_mode == 1 && !act_ptrs)) { set_error("exchange: bad act_mode"); return 1; }
+    a.raw = act_mode != 0; a.store_act = act_mode == 1;
     for (int r = 0; r < world; ++r) {
         a.grad[r] = grad_ptrs[r]; a.param[r] = param_ptrs[r]; a.act[r] = act_ptrs ? act_ptrs[r] : nullptr;
         if (!a.grad[r] || !a.param[r]) { set_error("exchange: NULL peer pointer"); return 1; }
     }
     a.param[world] = param_ptrs[rank];            // this rank's own block, for the local read
     // all three or none: a block without a multicast mapping keeps the whole step on peer loads / stores
-    const bool mc = mc_grad && mc_param && (mc_act || !act_ptrs);
+    const bool mc = mc_grad && mc_param && (mc_act || act_mode != 1);
     a.mc_grad = mc ? mc_grad : nullptr; a.mc_param = mc ? mc_param : nullptr; a.mc_act = mc ? mc_act : nullptr;
     a.lo4 = lo / 4; a.hi4 = hi / 4;
     a.groups = groups;
@@ -169,7 +174,7 @@ int launch_exchange_adam(int world, int rank, const float *const *grad_ptrs, flo
         start = e;
     }
     a.off_opacity4 = starts[2] / 4; a.off_scales4 = starts[3] / 4; a.off_rot4 = starts[4] / 4;
-    if (act_ptrs) {
+    if (act_mode == 1) {
         if (!act_offsets) { set_error("exchange: act_offsets missing"); return 1; }
         for (int k = 0; k < 3; ++k)
             if (act_offsets[k] & 3) { set_error("exchange: activated groups must start on 16-byte boundaries"); return 1; }

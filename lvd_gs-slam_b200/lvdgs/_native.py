@@ -157,7 +157,7 @@ def lib():
     L.lvdgs_dist2.argtypes = [i32, vp, vp, vp, sz, vp]
     L.lvdgs_adam_step.argtypes = [i64, vp, vp, vp, vp, i32, C.POINTER(i64), C.POINTER(f), C.c_double, C.c_double, C.c_double, i32, vp]
     L.lvdgs_exchange_adam.argtypes = [i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64, i64, vp, vp, i32, C.POINTER(i64),
-                                      C.POINTER(f), C.POINTER(i64), i64, C.c_double, C.c_double, C.c_double, i32, vp, vp, vp, vp]
+                                      C.POINTER(f), C.POINTER(i64), i64, C.c_double, C.c_double, C.c_double, i32, vp, vp, vp, i32, vp]
     L.lvdgs_zero_async.argtypes = [vp, sz, vp]
     L.lvdgs_sort_workspace_bytes.argtypes = [i64]
     L.lvdgs_sort_workspace_bytes.restype = sz

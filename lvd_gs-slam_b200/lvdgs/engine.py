@@ -224,17 +224,20 @@ class RasterEngine:
             ptr(sl.g_tau), self._stream(stream))
         _native.check(rc, "lvdgs_rasterize_backward")
 
-    def run_views(self, vcs, means3D, opacities, scales, rotations, shs, upstream, on_view=None, before_view=None):
+    def run_views(self, vcs, means3D, opacities, scales, rotations, shs, upstream, on_view=None, before_view=None, bwd_wait=None):
         """Forward + backward of several views with gradients accumulated into `grad_flat`, software-pipelined over the
         forward / backward streams and the buffer slots.  `upstream(k, slot)` is called on the backward stream after
         view k's forward has finished and returns (dL_dcolor, dL_ddepth, dL_dopacity) for it -- the place where a caller
         computes its loss from `slot.color/depth/opacity`.  `on_view(k, slot)` (optional) runs on the backward stream
         after view k's backward (e.g. densification statistics from slot.g_means2D / slot.radii).  `before_view(k)`
-        (optional) runs on the host right before view k's forward is queued."""
+        (optional) runs on the host right before view k's forward is queued.  `bwd_wait` (optional): an event the first
+        backward has to wait for (the forwards do not)."""
         cur = torch.cuda.current_stream(self.dev)
         n = len(self.slots)
         start = torch.cuda.Event(); start.record(cur)
         self.s_fwd.wait_event(start); self.s_bwd.wait_event(start)
+        if bwd_wait is not None:       # e.g. the mapper's deferred clearing of the gradient block (ShardedMapper.grad_ready)
+            self.s_bwd.wait_event(bwd_wait)
         bwd_done = [None] * n
         for k, vc in enumerate(vcs):
             s = k % n

@@ -75,6 +75,11 @@ class ShardedMapper:
         self.betas, self.eps, self.t = betas, eps, 0
         self._p2p = None           # symmetric-memory handles of the peer-memory exchange (None: NCCL sequence)
         self.exchange_mode = "nccl"     # "multicast" / "peer" once the peer-memory exchange has run
+        import os
+        # activations of the updated parameters: recomputed locally after the exchange (default) or stored by the exchange
+        # kernel into every rank's activated block (LVDGS_EXCHANGE_LOCAL_ACT=0)
+        self.local_activation = os.environ.get("LVDGS_EXCHANGE_LOCAL_ACT", "1") != "0"
+        self.grad_ready = None          # with defer_zero: the event after which the gradient block is zero again
         self.time_exchange, self._phase_log = False, []
         self._grad_block = None
         self._alloc(P)
@@ -248,12 +253,12 @@ class ShardedMapper:
         self._adam_range(grad_flat, 0, self.total)
         self.activate()
 
-    def exchange_and_update(self, grad_flat: torch.Tensor):
+    def exchange_and_update(self, grad_flat: torch.Tensor, defer_zero: bool = False):
         """The exchange step of one iteration: raw-parameter chain rule, gradient SUM over the ranks, Adam, activations.
         NCCL: reduce-scatter -> Adam on this rank's slice -> all-gather of the parameters; the gradient block is zeroed
         for the next iteration on a side stream while the all-gather runs."""
         if self._p2p and grad_flat is self._grad_block:
-            return self._exchange_p2p(grad_flat)
+            return self._exchange_p2p(grad_flat, defer_zero)
         self.activation_backward(grad_flat)
         if not self._can_scatter():
             self.reduce_gradients(grad_flat)
@@ -278,7 +283,7 @@ class ShardedMapper:
         self.activate()
         cur.wait_event(self._zero_done)
 
-    def _exchange_p2p(self, grad_flat: torch.Tensor):
+    def _exchange_p2p(self, grad_flat: torch.Tensor, defer_zero: bool = False):
         """barrier | ONE kernel: peer reads of the gradient slice, chain rule, Adam, peer stores of parameters + activations | barrier."""
         C, _native, L = self._lib()
         self.t += 1
@@ -297,7 +302,8 @@ class ShardedMapper:
             # NVSwitch multicast mappings of the three blocks (0 when the box has no multicast support): the sum over the
             # ranks and the replication of the results then happen inside the switch (multimem.ld_reduce / multimem.st)
             mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in (hg, hp, ha)]
-            if os.environ.get("LVDGS_MULTICAST", "1") == "0" or not all(mc):
+            # (two ranks: every byte crosses the switch once either way, and peer loads / stores were measured faster)
+            if os.environ.get("LVDGS_MULTICAST", "1" if W > 2 else "0") == "0" or not all(mc):
                 mc = [0, 0, 0]
             else:
                 mc = [m + int(getattr(h, "offset", 0)) for m, h in zip(mc, (hg, hp, ha))]
@@ -313,13 +319,28 @@ class ShardedMapper:
         rc = L.lvdgs_exchange_adam(self.world, self.rank, g_arr, p_arr, a_arr, self.shard.start, self.shard.stop,
                                    _native.ptr(self.exp_avg), _native.ptr(self.exp_avg_sq), len(GROUPS), ends, lr, act_off,
                                    self.act_flat.numel(), self.betas[0], self.betas[1], self.eps, self.t, mc[0], mc[1], mc[2],
-                                   self._stream())
+                                   2 if self.local_activation else 1, self._stream())
         _native.check(rc, "lvdgs_exchange_adam")
         self.moments_sharded = True
         if ev: ev[2].record()
         hg.barrier(channel=1)                                  # all stores have landed, all gradient slices have been read
         if ev: ev[3].record()
-        grad_flat.zero_()
+        cur = torch.cuda.current_stream(self.device)
+        if defer_zero:
+            # the gradient block is cleared on a side stream; the caller makes its first backward wait for `grad_ready`
+            # (RasterEngine.run_views(..., bwd_wait=mapper.grad_ready)) instead of this stream
+            if self._zero_stream is None:
+                self._zero_stream = torch.cuda.Stream(self.device)
+            after = torch.cuda.Event(); after.record(cur)
+            self._zero_stream.wait_event(after)
+            with torch.cuda.stream(self._zero_stream):
+                grad_flat.zero_()
+                self.grad_ready = torch.cuda.Event(); self.grad_ready.record(self._zero_stream)
+        else:
+            grad_flat.zero_()
+            self.grad_ready = None
+        if self.local_activation:
+            self.activate()                                    # one local pass instead of 8 of 14 floats per Gaussian over NVLink
         if ev: ev[4].record()
 
     def _phase_events(self, n):
@@ -336,7 +357,7 @@ class ShardedMapper:
         self._phase_log = []
         if not rows:
             return None
-        names = ("barrier_before", "exchange_kernel", "barrier_after", "zero_gradients")
+        names = ("barrier_before", "exchange_kernel", "barrier_after", "zero_gradients_and_local_activation")
         return {n: statistics.median(r[k] for r in rows) for k, n in enumerate(names)}
 
     def gather_moments(self):

@@ -36,8 +36,8 @@ def _job(device, world, rank):
 
     for _ in range(ITERS):
         args = [mapper.view(k) for k in ("means3D", "opacity", "scales", "rotations", "shs")]
-        eng.run_views(vcs, *args, upstream)
-        mapper.exchange_and_update(eng.grad_flat)
+        eng.run_views(vcs, *args, upstream, bwd_wait=mapper.grad_ready)
+        mapper.exchange_and_update(eng.grad_flat, defer_zero=True)     # gradient block cleared on a side stream
     torch.cuda.synchronize(device)
     return mapper
 
