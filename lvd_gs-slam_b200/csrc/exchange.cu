@@ -66,21 +66,25 @@ __device__ __forceinline__ float adam_update(float p, float g, float &m, float &
     return p - lr * a.inv_bc1 * mi / denom;
 }
 
-__global__ void __launch_bounds__(256) exchange_adam_kernel(float4 *__restrict__ exp_avg, float4 *__restrict__ exp_avg_sq, const ExchangeArgs a) {
+// MAXW: compile-time bound of the world size (the peer-load path keeps one 128-bit load per rank in flight: the register
+// footprint follows MAXW -- 116 registers and 2 CTAs / SM for the generic 16, ~48 for the in-switch path); MC: the three
+// blocks have multicast mappings
+template <int MAXW, bool MC>
+__global__ void __launch_bounds__(256, MC ? 4 : (MAXW <= 4 ? 4 : 2)) exchange_adam_kernel(float4 *__restrict__ exp_avg, float4 *__restrict__ exp_avg_sq, const ExchangeArgs a) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = a.lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.hi4; i += stride) {
         // 1. reduce: this element's gradient from every rank -- in the switch, or summed here in rank order
         float4 g;
-        if (a.mc_grad) {
+        if (MC) {
             g = multimem_sum4(reinterpret_cast<const float4 *>(a.mc_grad) + i);
         } else {
-            float4 gr[EX_MAX_WORLD];
+            float4 gr[MAXW];
 #pragma unroll
-            for (int r = 0; r < EX_MAX_WORLD; ++r)
+            for (int r = 0; r < MAXW; ++r)
                 if (r < a.world) gr[r] = __ldcg(reinterpret_cast<const float4 *>(a.grad[r]) + i);      // L2 only: the line is remote and read once
             g = gr[0];
 #pragma unroll
-            for (int r = 1; r < EX_MAX_WORLD; ++r)
+            for (int r = 1; r < MAXW; ++r)
                 if (r < a.world) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }
         }
         int grp = 0;
@@ -127,12 +131,12 @@ __global__ void __launch_bounds__(256) exchange_adam_kernel(float4 *__restrict__
             av = make_float4(p.x / n, p.y / n, p.z / n, p.w / n);
             ai = a.act_rot4 + (i - a.off_rot4);
         }
-        if (a.mc_param) {
+        if (MC) {
             multimem_store4(reinterpret_cast<float4 *>(a.mc_param) + i, p);
             if (ai >= 0 && ai < a.act_total4) multimem_store4(reinterpret_cast<float4 *>(a.mc_act) + ai, av);
         } else {
 #pragma unroll
-            for (int r = 0; r < EX_MAX_WORLD; ++r)
+            for (int r = 0; r < MAXW; ++r)
                 if (r < a.world) {
                     __stcg(reinterpret_cast<float4 *>(a.param[r]) + i, p);
                     if (ai >= 0 && ai < a.act_total4) __stcg(reinterpret_cast<float4 *>(a.act[r]) + ai, av);
@@ -188,7 +192,12 @@ int launch_exchange_adam(int world, int rank, const float *const *grad_ptrs, flo
     const int64_t n4 = a.hi4 - a.lo4;
     const int blocks = (int)min((int64_t)148 * 8, (n4 + 255) / 256);
     LVDGS_PRE(s);
-    exchange_adam_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<float4 *>(exp_avg), reinterpret_cast<float4 *>(exp_avg_sq), a);
+    float4 *m4 = reinterpret_cast<float4 *>(exp_avg), *v4 = reinterpret_cast<float4 *>(exp_avg_sq);
+    if (mc) exchange_adam_kernel<1, true><<<blocks, 256, 0, s>>>(m4, v4, a);
+    else if (world <= 2) exchange_adam_kernel<2, false><<<blocks, 256, 0, s>>>(m4, v4, a);
+    else if (world <= 4) exchange_adam_kernel<4, false><<<blocks, 256, 0, s>>>(m4, v4, a);
+    else if (world <= 8) exchange_adam_kernel<8, false><<<blocks, 256, 0, s>>>(m4, v4, a);
+    else exchange_adam_kernel<EX_MAX_WORLD, false><<<blocks, 256, 0, s>>>(m4, v4, a);
     LVDGS_LAUNCHED(s, "exchange_adam");
     return 0;
 }
