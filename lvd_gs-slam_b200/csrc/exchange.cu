@@ -194,6 +194,7 @@ int launch_exchange_adam(int world, int rank, const float *const *grad_ptrs, flo
     LVDGS_PRE(s);
     float4 *m4 = reinterpret_cast<float4 *>(exp_avg), *v4 = reinterpret_cast<float4 *>(exp_avg_sq);
     if (mc) exchange_adam_kernel<1, true><<<blocks, 256, 0, s>>>(m4, v4, a);
+    else if (world == 1) exchange_adam_kernel<1, false><<<blocks, 256, 0, s>>>(m4, v4, a);
     else if (world <= 2) exchange_adam_kernel<2, false><<<blocks, 256, 0, s>>>(m4, v4, a);
     else if (world <= 4) exchange_adam_kernel<4, false><<<blocks, 256, 0, s>>>(m4, v4, a);
     else if (world <= 8) exchange_adam_kernel<8, false><<<blocks, 256, 0, s>>>(m4, v4, a);

@@ -259,6 +259,9 @@ class ShardedMapper:
         for the next iteration on a side stream while the all-gather runs."""
         if self._p2p and grad_flat is self._grad_block:
             return self._exchange_p2p(grad_flat, defer_zero)
+        if (self.world == 1 and self.raw and self.optimizer_fn is None and self.param_flat.is_cuda and grad_flat.is_cuda
+                and grad_flat.numel() >= self.total and not (grad_flat.data_ptr() & 15)):
+            return self._exchange_single(grad_flat)
         self.activation_backward(grad_flat)
         if not self._can_scatter():
             self.reduce_gradients(grad_flat)
@@ -283,6 +286,30 @@ class ShardedMapper:
         self.activate()
         cur.wait_event(self._zero_done)
 
+    def _group_ends(self):
+        ends = []
+        for n in GROUPS:
+            off, _ = self.layout[n]
+            ends.append(min((o for o, _ in self.layout.values() if o > off), default=self.total))
+        ends[-1] = self.total
+        return ends
+
+    def _exchange_single(self, grad_flat: torch.Tensor):
+        """One GPU: the same kernel with a world of one -- chain rule, Adam and activations in ONE launch instead of three
+        (lvdgs_gaussian_activation_backward, lvdgs_adam_step, lvdgs_gaussian_activate)."""
+        C, _native, L = self._lib()
+        self.t += 1
+        one = lambda t: (C.c_void_p * 1)(t.data_ptr())
+        ends = (C.c_int64 * len(GROUPS))(*self._group_ends())
+        lr = (C.c_float * len(GROUPS))(*[float(self.lrs[n]) for n in GROUPS])
+        act_off = (C.c_int64 * 3)(*[self.act_layout[n][0] for n in ACTIVATED])
+        rc = L.lvdgs_exchange_adam(1, 0, one(grad_flat), one(self.param_flat), one(self.act_flat), 0, self.total,
+                                   _native.ptr(self.exp_avg), _native.ptr(self.exp_avg_sq), len(GROUPS), ends, lr, act_off,
+                                   self.act_flat.numel(), self.betas[0], self.betas[1], self.eps, self.t, None, None, None, 1,
+                                   self._stream())
+        _native.check(rc, "lvdgs_exchange_adam")
+        grad_flat.zero_()
+
     def _exchange_p2p(self, grad_flat: torch.Tensor, defer_zero: bool = False):
         """barrier | ONE kernel: peer reads of the gradient slice, chain rule, Adam, peer stores of parameters + activations | barrier."""
         C, _native, L = self._lib()
@@ -293,11 +320,7 @@ class ShardedMapper:
             W = self.world
             base = lambda h: [int(x) + int(getattr(h, "offset", 0)) for x in h.buffer_ptrs]
             arr = lambda h: (C.c_void_p * W)(*base(h))
-            ends = []
-            for n in GROUPS:
-                off, _ = self.layout[n]
-                ends.append(min((o for o, _ in self.layout.values() if o > off), default=self.total))
-            ends[-1] = self.total
+            ends = self._group_ends()
             act_off = (C.c_int64 * 3)(*[self.act_layout[n][0] for n in ACTIVATED])
             # NVSwitch multicast mappings of the three blocks (0 when the box has no multicast support): the sum over the
             # ranks and the replication of the results then happen inside the switch (multimem.ld_reduce / multimem.st)

@@ -338,3 +338,34 @@ def test_masked_ssim_mapping_loss_matches_the_reference_expression(shape, with_d
                                          torch.tensor(bg, device=dev), depth=None if depth is None else depth.detach(),
                                          mono_depth=torch.tensor(mono_np, device=dev) if with_depth else None)
     assert float(again) == float(loss)
+
+
+def test_single_gpu_fused_update_equals_the_three_kernel_sequence():
+    """One GPU: ShardedMapper.exchange_and_update runs lvdgs_exchange_adam with a world of one (chain rule + Adam +
+    activations in one launch); it must reproduce lvdgs_gaussian_activation_backward -> lvdgs_adam_step ->
+    lvdgs_gaussian_activate (the expressions are the same; only fused-multiply-add contraction may differ)."""
+    from lvdgs.mapping import ShardedMapper, GROUPS
+    dev = torch.device("cuda")
+    P = 5003                                        # not a multiple of 4: exercises the padded group boundaries
+    g = torch.Generator(device="cpu").manual_seed(5)
+    init = {"means3D": torch.randn(P, 3, generator=g), "shs": torch.randn(P, 1, 3, generator=g),
+            "opacity": torch.rand(P, 1, generator=g) * 0.9 + 0.05, "scales": torch.rand(P, 3, generator=g) * 0.5 + 0.01,
+            "rotations": torch.randn(P, 4, generator=g)}
+    a, b = (ShardedMapper(P, sh_coeffs=1, device=dev) for _ in range(2))
+    for m in (a, b):
+        m.load(**{k: v.numpy() for k, v in init.items()})
+    ga, gb = a.new_grad_block(), b.new_grad_block()
+    for it in range(5):
+        grad = torch.randn(a.total, generator=g).to(dev) * 1e-3
+        for name, (off, ln) in a.layout.items():    # the padding between the groups carries no gradient
+            end = min((o for o, _ in a.layout.values() if o > off), default=a.total)
+            grad[off + ln:end] = 0
+        ga.copy_(grad); gb.copy_(grad)
+        a.exchange_and_update(ga)                   # fused
+        b.activation_backward(gb); b.adam_step(gb); gb.zero_()      # the sequence (adam_step activates)
+        assert float(ga.abs().max()) == 0.0
+    assert a.t == b.t == 5
+    for x, y, what in ((a.param_flat, b.param_flat, "params"), (a.exp_avg, b.exp_avg, "exp_avg"), (a.exp_avg_sq, b.exp_avg_sq, "exp_avg_sq")):
+        np.testing.assert_allclose(x.cpu().numpy(), y.cpu().numpy(), rtol=2e-6, atol=1e-9, err_msg=what)
+    for k in GROUPS:       # what the rasterizer reads (the float4 padding behind a group is never read by anyone)
+        np.testing.assert_allclose(a.view(k).cpu().numpy(), b.view(k).cpu().numpy(), rtol=2e-6, atol=1e-9, err_msg=k)
