@@ -472,8 +472,9 @@ def main():
         for j in range(NS):
             prefetch_c(j)
         # the forward stream waits for view j's camera right before the view is launched; the backward stream (loss) follows it
+        fwd_stream = eng.view_streams(NS)[0]
         eng.run_views(staged[0], *args_, upstream_c, on_view=after_view_c,
-                      before_view=lambda j: eng.s_fwd.wait_event(st_c[j]["ready"]))
+                      before_view=lambda j: fwd_stream.wait_event(st_c[j]["ready"]))
         mapper.exchange_and_update(eng.grad_flat)
         torch.cuda.current_stream().synchronize()                      # the step's results are on the host
 

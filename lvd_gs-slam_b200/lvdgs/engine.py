@@ -224,6 +224,14 @@ class RasterEngine:
             ptr(sl.g_tau), self._stream(stream))
         _native.check(rc, "lvdgs_rasterize_backward")
 
+    def view_streams(self, n_views: int):
+        """(forward stream, backward stream) run_views uses for a window of n_views: the two side streams, or the caller's
+        current stream for a single view (callbacks that queue waits on "the forward stream" ask here)."""
+        if n_views == 1:
+            cur = torch.cuda.current_stream(self.dev)
+            return cur, cur
+        return self.s_fwd, self.s_bwd
+
     def run_views(self, vcs, means3D, opacities, scales, rotations, shs, upstream, on_view=None, before_view=None, bwd_wait=None):
         """Forward + backward of several views with gradients accumulated into `grad_flat`, software-pipelined over the
         forward / backward streams and the buffer slots.  `upstream(k, slot)` is called on the backward stream after
@@ -233,6 +241,19 @@ class RasterEngine:
         (optional) runs on the host right before view k's forward is queued.  `bwd_wait` (optional): an event the first
         backward has to wait for (the forwards do not)."""
         cur = torch.cuda.current_stream(self.dev)
+        if len(vcs) == 1:
+            # one view (a rank of an 8-GPU window): nothing to overlap, so no stream hops -- forward, loss and backward run
+            # back to back on the caller's stream (three cross-stream dependencies less on the critical path)
+            if bwd_wait is not None:
+                cur.wait_event(bwd_wait)
+            if before_view is not None:
+                before_view(0)
+            self.forward(vcs[0], means3D, opacities, scales, rotations, shs, slot=0, stream=cur)
+            gc, gd, go = upstream(0, self.slots[0])
+            self.backward(vcs[0], means3D, opacities, scales, rotations, shs, gc, gd, go, accumulate=True, slot=0, stream=cur)
+            if on_view is not None:
+                on_view(0, self.slots[0])
+            return
         n = len(self.slots)
         start = torch.cuda.Event(); start.record(cur)
         self.s_fwd.wait_event(start); self.s_bwd.wait_event(start)

@@ -61,6 +61,32 @@ def test_pipelined_views_match_sequential_plugin():
             np.testing.assert_array_equal(seen[k][2].cpu().numpy(), out["n_touched"])
 
 
+def test_single_view_window_runs_on_the_callers_stream_and_matches_the_plugin():
+    """A window of ONE view (a rank of an 8-GPU mapping step) takes run_views' single-stream path: same gradient block,
+    same per-view outputs as the plugin surface."""
+    dev = torch.device("cuda")
+    cam = synth.make_camera("mast3r_kitti", 2)
+    P = 20_000
+    sc = synth.make_scene(P, cam, seed=12)
+    H, W = cam.image_height, cam.image_width
+    rng = np.random.default_rng(4)
+    gc, gd = rng.normal(0, 1, (3, H, W)).astype(np.float32), rng.normal(0, 1, (1, H, W)).astype(np.float32)
+    out, _, g = run_cuda(sc, cam, np.zeros(3, np.float32), grads=(gc, gd, None), debug=False)
+    t = lambda a: torch.tensor(a, device=dev)
+    args = [t(sc[k]) for k in ("means3D", "opacities", "scales", "rotations", "shs")]
+    eng = RasterEngine(P, W, H, device=dev)
+    assert eng.view_streams(1)[0] == torch.cuda.current_stream(dev) and eng.view_streams(2)[0] == eng.s_fwd
+    tg = (t(gc), t(gd))
+    for rep in range(3):
+        eng.zero_grads()
+        eng.run_views([ViewCamera(cam, dev)], *args, lambda k, slot: (tg[0], tg[1], None))
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(eng.color.cpu().numpy(), out["color"])
+        assert rel_err(eng.grads["means3D"].cpu().numpy().reshape(P, 3), g["means3D"]) < 1e-5
+        assert rel_err(eng.grads["rotations"].cpu().numpy().reshape(P, 4), g["rotations"]) < 1e-5
+        assert rel_err(eng.g_tau.cpu().numpy(), np.concatenate([g["rho"].reshape(-1), g["theta"].reshape(-1)])) < 1e-5
+
+
 def test_alternating_image_sizes_never_rerun_the_speculative_tail():
     """tracking renders 1241x376 and, per frame, one 512x144 depth image (utils/init_pose.py:145) on the
     same thread.  The long-list history is kept per (device, image size), so after warm-up neither shape disturbs the
