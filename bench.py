@@ -311,7 +311,8 @@ def main():
         exch_phases = mapper.exchange_phase_ms()
     step_split = {"views_ms": ms_views, "views_ms_by_rank": ms_views_ranks, "exchange_ms": ms_exch, "exchange_phases_ms_rank0": exch_phases,
                   "what": "timed apart, max over ranks: this rank's views through RasterEngine.run_views; "
-                          "ShardedMapper.exchange_and_update (activation chain rule, reduce-scatter, Adam, all-gather, activations)"}
+                          "ShardedMapper.exchange_and_update (gradient sum over the ranks, activation chain rule, Adam on the shard, "
+                          "parameters to every rank, activations; exchange_phases_ms_rank0 = its phases on rank 0 from CUDA events)"}
 
     # BASELINE configs[2] names 1 M Gaussians for the mapping window: the same step on that map (extra key; the headline
     # metric is quoted at 500 k)

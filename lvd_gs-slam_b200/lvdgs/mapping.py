@@ -13,11 +13,16 @@ backward kernel adds into it, there is no pack kernel).  The exchange step per i
 
 i.e. the optimiser state is sharded (ZeRO-1): the same bytes cross NVLink as in an all-reduce, but the Adam kernel
 touches 1/world of the block on every rank and the gradient block is re-zeroed off the critical path.
-On NVLink-connected GPUs of one node the three steps (plus the activation chain rule before and the activations after)
-are ONE kernel over peer memory (lvdgs_exchange_adam, csrc/exchange.cu): the parameter, activation and gradient blocks
-live in symmetric memory (torch.distributed._symmetric_memory), every rank reads its slice of all gradient blocks
-directly from its peers, updates it and stores the result into every peer's blocks; two device-side barriers bracket the
-launch.  LVDGS_P2P_EXCHANGE=0, or a failed rendezvous, selects the NCCL sequence above.  With a backend
+On NVLink-connected GPUs of one node the three steps (plus the activation chain rule before) are ONE kernel
+(lvdgs_exchange_adam, csrc/exchange.cu): the parameter, activation and gradient blocks live in symmetric memory
+(torch.distributed._symmetric_memory); every rank sums its slice of all gradient blocks inside the NVSwitch
+(multimem.ld_reduce on the multicast mapping; peer loads without multicast support or at two ranks), updates it and
+writes the new raw parameters once, replicated by the switch to every rank (multimem.st; peer stores otherwise); two
+device-side barriers bracket the launch, the activations are recomputed locally behind the second one
+(LVDGS_EXCHANGE_LOCAL_ACT=0: stored by the kernel instead), and the gradient block can be cleared on a side stream
+(`defer_zero`, `grad_ready`).  On ONE GPU the same kernel with a world of one replaces the three launches (chain rule,
+Adam, activations).  LVDGS_P2P_EXCHANGE=0, or a failed rendezvous, selects the NCCL sequence above; LVDGS_MULTICAST=0/1
+forces peer / multicast access.  With a backend
 that has no reduce-scatter (gloo, the CPU tests) the block is all-reduced and every rank runs the identical full update.
 Either way the replicas stay bit-identical without a broadcast.
 
