@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" entry points declared in include/lvdgs.h: buffer layouts, argument checks and the
 // launch sequence of the forward and backward passes.  No torch types, no allocation, one host sync (R).
 #include "common.cuh"
+#include <cstdlib>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -29,6 +30,11 @@ struct ProfEntry { const char *name; cudaEvent_t ev; cudaEvent_t pre; };
 static thread_local std::vector<ProfEntry> g_prof;
 static thread_local bool g_prof_on = false;
 static thread_local cudaEvent_t g_prof_pending_pre = nullptr;
+
+bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("LVDGS_PDL"); return !(e && e[0] == '0'); }();
+    return on && !g_prof_on;           // the profiler's events between launches serialise anyway
+}
 
 int profile_pre(cudaStream_t s) {
     if (!g_prof_on) return 0;

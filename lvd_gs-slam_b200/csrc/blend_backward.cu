@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(BB_THREADS, LVDGS_BB_MINBLOCKS) blend_backward
     __shared__ uint64_t s_bar[2 * BB_NBUF];                  // FULL[b] (every thread arrives), EMPTY[b] (one arrival per warp)
 #endif
 
+    pdl_wait();      // launched behind the loss kernel when the caller's stream has one right before (programmatic dependent launch)
     // the pose-gradient sum the preprocess backward adds into (it runs after this launch): cleared here, not by a memset
     if (zero6 && blockIdx.x == 0 && threadIdx.x < 6) zero6[threadIdx.x] = 0.f;
     const int tile = tile_order ? (int)__ldg(tile_order + blockIdx.x) : (int)blockIdx.x;   // heaviest tiles first
@@ -387,13 +388,11 @@ int launch_blend_backward(int P, int W, int H, int64_t R, const uint2 *ranges, c
     const float *dop = (flags & LVDGS_FLAG_OPACITY_GRAD) ? dL_dout_opacity : nullptr;
     LVDGS_PRE(s);
     if (moments_only)
-        blend_backward_kernel<true><<<gx * gy, BB_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
-                                                                         g.rgbd, tile_order, bg, final_T, n_contrib, dL_dout_color,
-                                                                         nullptr, dop, o.acc, zero6);
+        LVDGS_CHECK(launch_after_kernel(blend_backward_kernel<true>, dim3(gx * gy), dim3(BB_THREADS), 0, s, W, H, gx, ranges, point_list, g.means2D,
+                                        g.conic_opacity, g.rgbd, tile_order, bg, final_T, n_contrib, dL_dout_color, nullptr, dop, o.acc, zero6));
     else
-        blend_backward_kernel<false><<<gx * gy, BB_THREADS, 0, s>>>(W, H, gx, ranges, point_list, g.means2D, g.conic_opacity,
-                                                                          g.rgbd, tile_order, bg, final_T, n_contrib, dL_dout_color,
-                                                                          dL_dout_depth, dop, o.acc, zero6);
+        LVDGS_CHECK(launch_after_kernel(blend_backward_kernel<false>, dim3(gx * gy), dim3(BB_THREADS), 0, s, W, H, gx, ranges, point_list, g.means2D,
+                                        g.conic_opacity, g.rgbd, tile_order, bg, final_T, n_contrib, dL_dout_color, dL_dout_depth, dop, o.acc, zero6));
     LVDGS_LAUNCHED(s, "blend_backward");
     return 0;
 }

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(BF_THREADS, LVDGS_BF_MINBLOCKS) blend_forward_
 
     // a speculative launch whose capacity hint was too small has no valid sorted list (the sort retires, see
     // tile_sort.cu); its output is discarded and the tail re-run by the host, so do nothing here
+    pdl_wait();                                  // launched behind the tile sort (programmatic dependent launch)
     if (n_dev && __ldg(n_dev) > capacity) return;
     const uint2 range = ranges[tile];
     int todo = (int)(range.y - range.x);
@@ -174,9 +175,9 @@ int launch_blend_forward(int W, int H, int64_t capacity, const uint32_t *n_dev, 
                          uint32_t *n_contrib, int32_t *n_touched, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     LVDGS_PRE(s);
-    blend_forward_kernel<<<gx * gy, BF_THREADS, 0, s>>>(W, H, gx, (uint32_t)min(capacity, (int64_t)0xffffffffll), n_dev, ranges, point_list, g.means2D, g.conic_opacity,
-                                                                g.rgbd, tile_order, bg, out_color, out_depth, out_opacity, final_T,
-                                                                n_contrib, n_touched);
+    LVDGS_CHECK(launch_after_kernel(blend_forward_kernel, dim3(gx * gy), dim3(BF_THREADS), 0, s, W, H, gx, (uint32_t)min(capacity, (int64_t)0xffffffffll),
+                                    n_dev, ranges, point_list, g.means2D, g.conic_opacity, g.rgbd, tile_order, bg, out_color, out_depth, out_opacity,
+                                    final_T, n_contrib, n_touched));
     LVDGS_LAUNCHED(s, "blend_forward");
     return 0;
 }

@@ -41,6 +41,24 @@ extern thread_local int g_debug_sync;
         if (lvdgs::g_debug_sync) LVDGS_CHECK(cudaStreamSynchronize(stream));                     \
     } while (0)
 
+// ---- programmatic dependent launch (sm_90+): a kernel launched with launch_after_kernel() may be scheduled while the
+// kernel before it in the stream is still draining; it must execute pdl_wait() before it touches anything that kernel
+// wrote (everything older in the stream is complete by then).  No kernel here triggers its dependents early, so the only
+// effect is that launch latency and block scheduling overlap the predecessor's tail.  LVDGS_PDL=0 (environment) or an
+// active profiler (events between the launches) falls back to plain stream order.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();                                    // api.cu
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_after_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Per-device state: function attributes (opt-in shared memory sizes) and device properties belong to ONE device; a process
 // that drives several GPUs (one engine per device, or the tests' two-GPU runs) needs them once per device, not once per
 // process.  current_device() is the device the calling thread has selected (lvdgs_set_device / cudaSetDevice).

@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) binning_count_kernel(int P, int
     int32_t *s_grid = s_tab + 4 * SORT_BINS;
     for (int k = threadIdx.x; k < 4 * SORT_BINS + (in_smem ? cells : 0); k += COUNT_THREADS) s_tab[k] = 0;
     __syncthreads();
+    pdl_wait();                                  // launched behind preprocess_forward (programmatic dependent launch)
     int32_t *grid = in_smem ? s_grid : grid_g;
     for (int i = blockIdx.x * COUNT_THREADS + threadIdx.x; i < P; i += gridDim.x * COUNT_THREADS) {
         const uint32_t touched = __ldg(tiles_touched + i);
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
     const int gw = gx + 1, cells = gw * (gy + 1), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < WORK_BUCKETS) s_bucket[tid] = 0;
     if (tid == 0) s_longest = 0;
+    pdl_wait();                                  // launched behind binning_count
     const bool in_smem = cells <= PREP_GRID_SMEM;
     int32_t *grid = in_smem ? s_grid : grid_g;
     if (passes)      // the digit histograms exist only on the onesweep path
@@ -537,13 +539,13 @@ int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, con
         // ~2 k cells serialise in L2; these few CTAs with shared-memory tables cost 0.010 ms)
         const int blocks = min(148, ceil_div(P, COUNT_THREADS * 2));
         LVDGS_PRE(s);
-        binning_count_kernel<<<blocks, COUNT_THREADS, 4 * SORT_BINS * sizeof(uint32_t) + dyn, s>>>(
-            P, gx, gy, g.tiles_touched, g.rect, onesweep ? g.depths : nullptr, im.tile_grid, im.sort_hist);
+        LVDGS_CHECK(launch_after_kernel(binning_count_kernel, dim3(blocks), dim3(COUNT_THREADS), 4 * SORT_BINS * sizeof(uint32_t) + dyn, s,
+                                        P, gx, gy, g.tiles_touched, g.rect, onesweep ? g.depths : nullptr, im.tile_grid, im.sort_hist));
         LVDGS_LAUNCHED(s, "binning_count");
     }
     LVDGS_PRE(s);
-    binning_prep_kernel<<<1, PREP_THREADS, dyn, s>>>(gx, gy, passes, end_bit, ceil_div(P, PRE_THREADS), im.tile_grid, im.ranges,
-                                                     im.sort_hist, g.block_sums, g.num_instances, im.tile_order);
+    LVDGS_CHECK(launch_after_kernel(binning_prep_kernel, dim3(1), dim3(PREP_THREADS), dyn, s, gx, gy, passes, end_bit, ceil_div(P, PRE_THREADS),
+                                    im.tile_grid, im.ranges, im.sort_hist, g.block_sums, g.num_instances, im.tile_order));
     LVDGS_LAUNCHED(s, "binning_prep");
     return 0;
 }

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(PB_THREADS, LVDGS_PB_MINBLOCKS) preprocess_bac
     else if (threadIdx.x < 35) cam.campos[threadIdx.x - 32] = __ldg(a.campos + threadIdx.x - 32);
     else if (threadIdx.x >= 64 && threadIdx.x < 80) s_praw[threadIdx.x - 64] = __ldg(a.proj_raw + threadIdx.x - 64);
     int i = blockIdx.x * PB_THREADS + threadIdx.x;
+    pdl_wait();                                  // launched behind the blend backward (programmatic dependent launch)
     if (a.visible_list) {
         // the per-view screen-space gradient of a culled Gaussian is zero: every block clears the culled rows of its own
         // index range (the listed, i.e. visible, rows are written by whichever block walks them -- disjoint sets)
@@ -392,7 +393,7 @@ int launch_preprocess_backward(const lvdgs_raster_params &p, const float *means3
     a.zero_culled_means2D = compact && dL_dmeans2D && !zeroed;
 
     LVDGS_PRE(s);
-    preprocess_backward_kernel<<<ceil_div(p.P, PB_THREADS), PB_THREADS, 0, s>>>(a);
+    LVDGS_CHECK(launch_after_kernel(preprocess_backward_kernel, dim3(ceil_div(p.P, PB_THREADS)), dim3(PB_THREADS), 0, s, a));
     LVDGS_LAUNCHED(s, "preprocess_backward");
     return 0;
 }

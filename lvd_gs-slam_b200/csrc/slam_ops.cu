@@ -34,6 +34,7 @@ __device__ __forceinline__ float sgnf(float x) { return (float)(x > 0.f) - (floa
 __global__ void __launch_bounds__(LOSS_THREADS) fused_loss_kernel(const LossArgs a) {
     __shared__ float s_part[LOSS_THREADS / 32][4];
     __shared__ bool s_last;
+    pdl_wait();                                  // launched behind the blend forward (programmatic dependent launch)
     const float ea = a.exposure ? __expf(__ldg(a.exposure)) : 1.f;       // torch.exp in the reference; see tolerance in the tests
     const float eb = a.exposure ? __ldg(a.exposure + 1) : 0.f;
     const float k_rgb = a.w_rgb / (3.f * (float)a.HW), k_d = a.w_depth / (float)a.HW;
@@ -123,7 +124,7 @@ int launch_fused_loss(int W, int H, const float *color, const float *depth, cons
     a.ticket = (unsigned int *)((char *)ws + align_up(LOSS_MAX_BLOCKS * 4 * sizeof(float)));
     const int blocks = min(LOSS_MAX_BLOCKS, ceil_div(a.HW, LOSS_THREADS));
     LVDGS_PRE(s);
-    fused_loss_kernel<<<blocks, LOSS_THREADS, 0, s>>>(a);
+    LVDGS_CHECK(launch_after_kernel(fused_loss_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, s, a));
     LVDGS_LAUNCHED(s, "fused_loss");
     return 0;
 }
@@ -345,6 +346,7 @@ __global__ void pose_step_kernel(lvdgs_pose_state *st, const float *__restrict__
                                  float lr_rot, float lr_trans, float lr_exp, float beta1, float beta2, float eps,
                                  float bc1, float bc2_sqrt, float threshold) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    pdl_wait();                                  // launched behind the preprocess backward (programmatic dependent launch)
     // gradients in parameter order: rot_delta (theta), trans_delta (rho), exposure a, b
     float g[8];
 #pragma unroll
@@ -429,8 +431,8 @@ int launch_pose_step(lvdgs_pose_state *state, const float *g_tau, const float *g
     const float bc1 = (float)(1.0 - pow(beta1, (double)step));
     const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
     LVDGS_PRE(s);
-    pose_step_kernel<<<1, 32, 0, s>>>(state, g_tau, g_exposure, lr_rot, lr_trans, lr_exp, (float)beta1, (float)beta2,
-                                      (float)eps, bc1, bc2_sqrt, threshold);
+    LVDGS_CHECK(launch_after_kernel(pose_step_kernel, dim3(1), dim3(32), 0, s, state, g_tau, g_exposure, lr_rot, lr_trans, lr_exp, (float)beta1,
+                                    (float)beta2, (float)eps, bc1, bc2_sqrt, threshold));
     LVDGS_LAUNCHED(s, "pose_step");
     return 0;
 }

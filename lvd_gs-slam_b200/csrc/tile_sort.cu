@@ -459,6 +459,7 @@ __global__ void __launch_bounds__(THREADS) tile_sort_short_kernel(uint32_t n_hi,
     __shared__ uint64_t s_pairs[ts_phys(CAP / 2)];
     __shared__ uint32_t s_red[2 * (THREADS / 32) + 1];
 #endif
+    pdl_wait();                                  // launched behind the key emission (or the middle class): programmatic dependent launch
     const int tile = (int)__ldg(tile_order + blockIdx.x);
     const uint2 range = ranges[tile];
     const uint32_t n = range.y - range.x;
@@ -551,7 +552,8 @@ int launch_tile_sort(int tiles, int64_t capacity, const uint32_t *n_dev, const u
         LVDGS_LAUNCHED(s, "tile_sort_mid");
     }
     LVDGS_PRE(s);
-    tile_sort_short_kernel<TS_SHORT_THREADS, TS_SHORT_CAP><<<tiles, TS_SHORT_THREADS, 0, s>>>((uint32_t)TS_SHORT_CAP, long_lists ? 0 : 1, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out);
+    LVDGS_CHECK(launch_after_kernel(tile_sort_short_kernel<TS_SHORT_THREADS, TS_SHORT_CAP>, dim3(tiles), dim3(TS_SHORT_THREADS), 0, s, (uint32_t)TS_SHORT_CAP,
+                                    long_lists ? 0 : 1, cap, n_dev, ranges, tile_order, seg, keys_out, vals_out));
     LVDGS_LAUNCHED(s, "tile_sort");
     return 0;
 }

@@ -190,15 +190,16 @@ class RasterEngine:
         R = C.c_int64(0)
         cap = C.c_int64(0)
         prm = self._params(vc, self.flags)
+        # the backward's accumulator rows are cleared on the FORWARD's stream, ahead of its kernels (LVDGS_FLAG_ZEROED_SCRATCH):
+        # in run_views that is off the backward stream, which carries the critical path, and on a single stream (tracking) it
+        # keeps the kernel chain forward -> loss -> backward free of memsets (programmatic dependent launches)
+        self.L.lvdgs_zero_async(ptr(sl.scratch), C.c_size_t(self.L.lvdgs_backward_scratch_bytes(self.P, 0)), self._stream(stream))
         rc = self.L.lvdgs_rasterize_forward(C.byref(prm), ptr(vc.bg), ptr(means3D), None, ptr(opacities), ptr(scales),
                                             ptr(rotations), None, ptr(vc.view), ptr(vc.proj), ptr(vc.proj_raw), ptr(shs),
                                             ptr(vc.campos), sl.cb, None, C.c_int64(sl.hint), ptr(sl.color),
                                             ptr(sl.radii), ptr(sl.depth), ptr(sl.opacity), ptr(sl.n_touched),
                                             C.byref(R), C.byref(cap), self._stream(stream))
         _native.check(rc, "lvdgs_rasterize_forward")
-        # the backward's accumulator rows are cleared here, behind the forward on ITS stream (LVDGS_FLAG_ZEROED_SCRATCH): in
-        # run_views that is off the backward stream, which carries the critical path
-        self.L.lvdgs_zero_async(ptr(sl.scratch), C.c_size_t(self.L.lvdgs_backward_scratch_bytes(self.P, 0)), self._stream(stream))
         sl.scratch_clean = True
         sl.R = int(R.value)
         sl.capacity = int(cap.value)
