@@ -1,10 +1,14 @@
 """CPU oracle for the Gaussian-splatting rasterizer hot path -- TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the reference's CUDA rasterizer (`submodules/diff-gaussian-rasterization`, MonoGS
+PARITY PARTLY PINNED: the reference's CUDA rasterizer (`submodules/diff-gaussian-rasterization`, MonoGS
 "-w-pose" fork) and `simple-knn` are absent from /root/reference (`.MISSING_LARGE_BLOBS:1`), and the
-reference holds no tests or golden vectors.  The C files in this directory restate
-the published algorithm; `tests/test_oracle_autograd.py` checks the analytic
-backward against float64 autograd of the forward.
+reference holds no tests or golden vectors, so the rasterizer's internal arithmetic
+is UNPINNED: the C files in this directory restate the published algorithm;
+`tests/test_oracle_autograd.py` checks the analytic backward against float64 autograd of the forward.
+Pinned by RUNNING reference-held Python (utils/pose_utils.py, camera_utils.py, slam_utils.py ->
+tests/golden/reference_pin.npz): the pose-gradient conventions and the tracking chain around the rasterizer
+(tests/test_reference_pin.py).  `oracle/build_ref.py` builds the reference's own CUDA into oracle/_ref/ if its
+sources ever appear under /root/reference (today: absent).
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py` (cpu_baseline / `--impl reference`) may import
 this package.  The product (`lvd_gs-slam_b200/`) never does and has no CPU fallback.

@@ -5,10 +5,16 @@
  * that zwk0901/LVD_GS-SLAM calls through `diff_gaussian_rasterization` (the MonoGS "-w-pose"
  * fork: extra depth / opacity / n_touched outputs and camera-pose gradients).
  *
- * PARITY UNPINNED.  The CUDA source of that plugin is not in /root/reference (it shipped in
+ * PARITY PARTLY PINNED.  The CUDA source of that plugin is not in /root/reference (it shipped in
  * submodules.zip, listed in /root/reference/.MISSING_LARGE_BLOBS:1) and the reference has no
- * tests or golden vectors for it.  This file therefore restates the
- * published algorithm and anchors it on the in-tree call sites:
+ * tests or golden vectors for it: the rasterizer's INTERNAL arithmetic
+ * (EWA, 0.3 dilation, 3-sigma radius, 1/255 and 1e-4 cut-offs, key layout) is UNPINNED -- restated from the
+ * published algorithm.  What IS pinned by reference-held code (round 2): the pose
+ * gradient -- this file's analytic dL/dtau equals finite differences taken THROUGH the reference's own
+ * SE3_exp (utils/pose_utils.py:56-68), and the chain Camera -> render -> get_loss_tracking -> backward ->
+ * Adam -> update_pose with this oracle as the rasterizer reproduces the trajectory recorded by running
+ * the reference's Python (tests/golden/reference_pin.npz, tests/test_reference_pin.py).  oracle/build_ref.py
+ * compiles the reference's own CUDA into oracle/_ref/ if its sources ever appear.  Anchors on the in-tree call sites:
  *   - argument tuple / output dict keys : utils/slam_backend.py:98-117,184-194 ; utils/slam_frontend.py:1493-1500
  *   - matrix layout (transposed, i.e. column-major flat arrays) : utils/camera_utils.py:106-120
  *   - pose convention  T_new = Exp(tau) * T_w2c , tau = [rho ; theta]  : utils/pose_utils.py:56-87
