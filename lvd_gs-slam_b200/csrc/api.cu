@@ -298,8 +298,7 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     void *geom_base = resize(resize_user, LVDGS_BUF_GEOM, gl.total);
     if (!geom_base) { set_error("resize callback returned NULL (geom)"); return 1; }
     GeomPtrs g = geom_ptrs(geom_base, p.P);
-    // the tile grid + digit histograms are accumulated with atomics: one memset
-    LVDGS_CHECK(cudaMemsetAsync(im.tile_grid, 0, il.total - il.tile_grid, s));
+    // the tile grid + digit histograms + cursors are accumulated with atomics: preprocess_forward clears them (no memset launch)
     if (launch_preprocess_forward(p, means3D, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
                                   projmatrix, shs, campos, radii, n_touched, g, im, s)) return 1;
     // block offsets, R, tile ranges and all digit histograms of the sort, from the block sums and per-tile counts

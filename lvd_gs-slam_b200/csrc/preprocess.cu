@@ -149,6 +149,8 @@ struct PreArgs {
     const float *means3D, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp, *view, *proj, *shs, *campos;
     int32_t *radii;
     int32_t *n_touched;        // zeroed here (the blend forward counts into it)
+    uint32_t *zero_base;       // tile difference grid + digit histograms + tile cursors: cleared here, every block its share
+    int zero_words;            // (binning_count, the first kernel to add into them, runs after this launch has finished)
     GeomPtrs g;
 };
 
@@ -160,6 +162,12 @@ __global__ void __launch_bounds__(PRE_THREADS, LVDGS_PF_MINBLOCKS) preprocess_fo
     __shared__ CameraConst cam;
     __shared__ uint32_t s_warp[PRE_THREADS / 32];
     const int bid = blockIdx.x;
+    pdl_wait();                // may be launched behind the previous kernel of the stream (tracking: the pose step)
+    {
+        const int per_block = (a.zero_words + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int lo = bid * per_block, hi = min(a.zero_words, lo + per_block);
+        for (int k = lo + (int)threadIdx.x; k < hi; k += PRE_THREADS) a.zero_base[k] = 0u;
+    }
     if (threadIdx.x < 16) cam.view[threadIdx.x] = __ldg(a.view + threadIdx.x);
     else if (threadIdx.x < 32) cam.proj[threadIdx.x - 16] = __ldg(a.proj + threadIdx.x - 16);
     else if (threadIdx.x < 35) cam.campos[threadIdx.x - 32] = __ldg(a.campos + threadIdx.x - 32);
@@ -295,7 +303,12 @@ int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D
                               const float *cov3D_precomp, const float *view, const float *proj, const float *shs,
                               const float *campos, int32_t *radii, int32_t *n_touched, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s) {
     PreArgs a;
-    (void)im;
+    {
+        lvdgs_img_layout il;
+        lvdgs_get_img_layout(p.width, p.height, &il);
+        a.zero_base = reinterpret_cast<uint32_t *>(im.tile_grid);
+        a.zero_words = (int)((il.total - il.tile_grid) / sizeof(uint32_t));
+    }
     a.n_touched = n_touched;
     a.P = p.P; a.D = p.sh_degree; a.M = p.sh_coeffs; a.W = p.width; a.H = p.height;
     a.gx = (p.width + TILE - 1) / TILE; a.gy = (p.height + TILE - 1) / TILE;
@@ -306,7 +319,7 @@ int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D
     a.rotations = rotations; a.cov3D_precomp = cov3D_precomp; a.view = view; a.proj = proj; a.shs = shs;
     a.campos = campos; a.radii = radii; a.g = g;
     LVDGS_PRE(s);
-    preprocess_forward_kernel<<<ceil_div(p.P, PRE_THREADS), PRE_THREADS, 0, s>>>(a);
+    LVDGS_CHECK(launch_after_kernel(preprocess_forward_kernel, dim3(ceil_div(p.P, PRE_THREADS)), dim3(PRE_THREADS), 0, s, a));
     LVDGS_LAUNCHED(s, "preprocess_forward");
     return 0;
 }
