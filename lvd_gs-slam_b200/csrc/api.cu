@@ -31,10 +31,13 @@ static thread_local std::vector<ProfEntry> g_prof;
 static thread_local bool g_prof_on = false;
 static thread_local cudaEvent_t g_prof_pending_pre = nullptr;
 
+static bool pdl_profiling();
 bool pdl_enabled() {
     static const bool on = [] { const char *e = getenv("LVDGS_PDL"); return !(e && e[0] == '0'); }();
     return on && !g_prof_on;           // the profiler's events between launches serialise anyway
 }
+
+static bool pdl_profiling() { return g_prof_on; }
 
 int profile_pre(cudaStream_t s) {
     if (!g_prof_on) return 0;
@@ -184,7 +187,25 @@ int lvdgs_get_img_layout(int32_t W, int32_t H, lvdgs_img_layout *out) { if (!out
 
 // pinned slot + event for the asynchronous read-back of the instance count: one per host thread AND device (an event
 // belongs to the device it was created on)
-struct ReadBack { uint32_t *pinned = nullptr; cudaEvent_t event = nullptr; };
+struct ReadBack { uint32_t *pinned = nullptr; cudaEvent_t event = nullptr; uint32_t seq = 0; };
+// LVDGS_POLL_R=0: read (R, longest list) back with a copy + event instead of the kernel's direct write into pinned memory
+static bool poll_readback() {
+    static const bool on = [] { const char *e = getenv("LVDGS_POLL_R"); return !(e && e[0] == '0'); }();
+    return on;
+}
+// waits until binning_prep has published sequence number `seq` in the pinned slot (it wrote R and the longest list first)
+static int wait_readback(const uint32_t *pinned, uint32_t seq, cudaStream_t s) {
+    const volatile uint32_t *flag = pinned + 2;
+    for (uint64_t spins = 1; *flag != seq; ++spins) {
+        if ((spins & 0xfff) == 0) {              // every few thousand polls: has the stream died or drained without publishing?
+            const cudaError_t q = cudaStreamQuery(s);
+            if (q == cudaSuccess) { if (*flag == seq) break; set_error("forward: the instance count never arrived from the device"); return 1; }
+            if (q != cudaErrorNotReady) { set_error("forward: %s while waiting for the instance count", cudaGetErrorString(q)); return 1; }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);      // R and the longest list were written before the sequence number
+    return 0;
+}
 static thread_local ReadBack t_readback[MAX_DEVICES];
 // longest tile lists of this thread's last forwards (read back with R), per (device, image size): decide whether the next
 // forward launches tile_sort's long-list classes speculatively (a wrong guess costs time, never correctness).  The
@@ -288,7 +309,8 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     const int dev_id = current_device();
     ReadBack &rb = t_readback[dev_id];
     if (!rb.pinned) {
-        LVDGS_CHECK(cudaHostAlloc((void **)&rb.pinned, 64, cudaHostAllocDefault));
+        LVDGS_CHECK(cudaHostAlloc((void **)&rb.pinned, 64, cudaHostAllocDefault));      // UVA: the device can write it directly
+        memset(rb.pinned, 0, 64);
         LVDGS_CHECK(cudaEventCreateWithFlags(&rb.event, cudaEventDisableTiming));
     }
     uint32_t *const t_pinned_R = rb.pinned;
@@ -302,9 +324,16 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     if (launch_preprocess_forward(p, means3D, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
                                   projmatrix, shs, campos, radii, n_touched, g, im, s)) return 1;
     // block offsets, R, tile ranges and all digit histograms of the sort, from the block sums and per-tile counts
-    if (launch_binning_prep(p.P, W, H, (p.flags & LVDGS_FLAG_GLOBAL_SORT) ? 32 + tile_bits((uint32_t)(gx * gy)) : 0, g, im, s)) return 1;
-    LVDGS_CHECK(cudaMemcpyAsync(t_pinned_R, g.num_instances, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    LVDGS_CHECK(cudaEventRecord(t_R_event, s));
+    // (R, longest list) reach the host either by the kernel's own write into pinned memory + a sequence number the host
+    // polls (default: nothing sits between binning_prep and the key emission), or by a copy + event
+    const bool poll = poll_readback() && !pdl_profiling();
+    const uint32_t seq = poll ? ++rb.seq : 0u;
+    if (launch_binning_prep(p.P, W, H, (p.flags & LVDGS_FLAG_GLOBAL_SORT) ? 32 + tile_bits((uint32_t)(gx * gy)) : 0, g, im,
+                            poll ? t_pinned_R : nullptr, seq, s)) return 1;
+    if (!poll) {
+        LVDGS_CHECK(cudaMemcpyAsync(t_pinned_R, g.num_instances, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        LVDGS_CHECK(cudaEventRecord(t_R_event, s));
+    }
 
     // Speculative launch: with a capacity hint the whole rest of the forward is queued BEFORE the host waits for R,
     // so the device never idles across the read-back.  If R turns out larger than the hint, the tail is re-run with
@@ -321,7 +350,8 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
                                  out_opacity, n_touched, s)) return 1;
         launched = true;
     }
-    LVDGS_CHECK(cudaEventSynchronize(t_R_event));
+    if (poll) { if (wait_readback(t_pinned_R, seq, s)) return 1; }
+    else LVDGS_CHECK(cudaEventSynchronize(t_R_event));
     if (profile_mark("(host: R read-back)", s)) return 1;
     const int64_t R = t_pinned_R[0];
     const uint32_t longest = t_pinned_R[1];

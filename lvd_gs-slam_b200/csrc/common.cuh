@@ -207,7 +207,7 @@ int launch_preprocess_forward(const lvdgs_raster_params &p, const float *means3D
                               const float *opacities, const float *scales, const float *rotations,
                               const float *cov3D_precomp, const float *view, const float *proj, const float *shs,
                               const float *campos, int32_t *radii, int32_t *n_touched, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s);
-int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s);
+int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, const ImgPtrs &im, uint32_t *host_rb, uint32_t host_seq, cudaStream_t s);
 int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, int64_t capacity, uint64_t *keys, uint32_t *vals,
                      uint32_t *tile_cursor, const uint2 *ranges, int32_t *sel_out, cudaStream_t s);
 // tile-segment sort (tile_sort.cu): seg holds each tile's (depth bits << 32 | Gaussian) words in ranges[tile], unordered

@@ -412,7 +412,8 @@ __device__ __forceinline__ uint32_t prep_incl_scan(uint32_t c, uint32_t *s_ws) {
 __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int gy, int passes, int end_bit, int nblocks,
                                                                     int32_t *__restrict__ grid_g, uint2 *__restrict__ ranges,
                                                                     uint32_t *__restrict__ hist, uint32_t *__restrict__ block_sums,
-                                                                    uint32_t *__restrict__ R_out, uint32_t *__restrict__ tile_order) {
+                                                                    uint32_t *__restrict__ R_out, uint32_t *__restrict__ tile_order,
+                                                                    uint32_t *host_rb, uint32_t host_seq) {
     extern __shared__ int32_t s_grid[];
     __shared__ uint32_t s_h[SORT_MAX_PASSES * SORT_BINS];
     __shared__ uint32_t s_ws[32];
@@ -517,6 +518,15 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
         if (lane == 0) {
             R_out[1] = s_longest;            // longest tile list (0 if below 1024), read back together with R
             R_out[2] = 0u;                   // visible-Gaussian counter of the key emission that follows
+            if (host_rb) {
+                // the host's copy of (R, longest list), written straight into its pinned memory and published by a sequence
+                // number it polls: no copy or event between this kernel and the key emission, which can therefore be a
+                // programmatic dependent launch
+                volatile uint32_t *h = host_rb;
+                h[0] = *R_out; h[1] = s_longest;
+                __threadfence_system();
+                h[2] = host_seq;
+            }
         }
     }
     __syncthreads();
@@ -542,7 +552,7 @@ __global__ void __launch_bounds__(PREP_THREADS) binning_prep_kernel(int gx, int 
 }
 
 // end_bit > 0: global onesweep sort follows (digit histograms are prepared); end_bit == 0: tile-segment sort (cursors)
-int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, const ImgPtrs &im, cudaStream_t s) {
+int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, const ImgPtrs &im, uint32_t *host_rb, uint32_t host_seq, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const int passes = (end_bit + 7) / 8;
     const bool onesweep = end_bit > 0;
@@ -558,7 +568,7 @@ int launch_binning_prep(int P, int W, int H, int end_bit, const GeomPtrs &g, con
     }
     LVDGS_PRE(s);
     LVDGS_CHECK(launch_after_kernel(binning_prep_kernel, dim3(1), dim3(PREP_THREADS), dyn, s, gx, gy, passes, end_bit, ceil_div(P, PRE_THREADS),
-                                    im.tile_grid, im.ranges, im.sort_hist, g.block_sums, g.num_instances, im.tile_order));
+                                    im.tile_grid, im.ranges, im.sort_hist, g.block_sums, g.num_instances, im.tile_order, host_rb, host_seq));
     LVDGS_LAUNCHED(s, "binning_prep");
     return 0;
 }
@@ -592,6 +602,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_keys_kernel(int P, int gx, 
     __shared__ uint32_t s_wsum[EMIT_THREADS / 32];
     const int g0 = blockIdx.x * EMIT_THREADS;
     const int i = g0 + threadIdx.x;
+    pdl_wait();                                  // launched behind binning_prep when the host polls for R (no copy in between)
     if (BUCKET && sel_out && i == 0) *sel_out = 1;              // the tile-segment sort leaves its result in keys[1] / vals[1]
     const uint32_t span_begin = block_offsets[blockIdx.x];      // exclusive prefix over the preceding blocks (binning_prep)
     // K2, second half: inclusive scan of this block's tile counts
@@ -663,7 +674,8 @@ int launch_emit_keys(int P, int W, int H, const GeomPtrs &g, int64_t capacity, u
     const uint32_t cap = (uint32_t)min(capacity, (int64_t)0xffffffffll);
     LVDGS_PRE(s);
     if (tile_cursor)
-        emit_keys_kernel<true><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, tile_cursor, ranges, g.visible_list, g.num_instances + 2, sel_out);
+        LVDGS_CHECK(launch_after_kernel(emit_keys_kernel<true>, dim3(ceil_div(P, EMIT_THREADS)), dim3(EMIT_THREADS), 0, s, P, gx, cap, g.block_sums, g.tiles_touched,
+                                        g.point_offsets, g.rect, g.depths, keys, vals, tile_cursor, ranges, g.visible_list, g.num_instances + 2, sel_out));
     else
         emit_keys_kernel<false><<<ceil_div(P, EMIT_THREADS), EMIT_THREADS, 0, s>>>(P, gx, cap, g.block_sums, g.tiles_touched, g.point_offsets, g.rect, g.depths, keys, vals, nullptr, nullptr, g.visible_list, g.num_instances + 2, nullptr);
     LVDGS_LAUNCHED(s, "emit_keys");
