@@ -70,6 +70,20 @@ typedef struct lvdgs_raster_params {
  * from the calling thread; the latest pointer per buffer is the live one. */
 typedef void *(*lvdgs_resize_fn)(void *user, int32_t which, size_t bytes);
 
+/*
+ * A ready-made resize callback for hosts that know the buffer sizes in advance (lvdgs_get_*_layout) and want no call
+ * back into their own language per forward: pass lvdgs_static_resize as `resize` and a lvdgs_static_buffers as
+ * `resize_user`.  A request that fits capacity[which] is served from base[which]; a larger one goes to `fallback`
+ * (NULL: the request fails and the forward returns an error).
+ */
+typedef struct lvdgs_static_buffers {
+    void *base[3];              /* LVDGS_BUF_GEOM / _BINNING / _IMG, 256-byte aligned device pointers */
+    size_t capacity[3];         /* bytes available behind each */
+    lvdgs_resize_fn fallback;   /* e.g. the host's allocating callback */
+    void *fallback_user;
+} lvdgs_static_buffers;
+void *lvdgs_static_resize(void *user, int32_t which, size_t bytes);
+
 /* Byte offsets of the arrays inside the three opaque buffers (for parity tests and debuggers). */
 typedef struct lvdgs_geom_layout {
     size_t depths;         /* float  [P]    view-space z */

@@ -372,6 +372,13 @@ int lvdgs_rasterize_forward(const lvdgs_raster_params *prm, const float *backgro
     return 0;
 }
 
+void *lvdgs_static_resize(void *user, int32_t which, size_t bytes) {
+    lvdgs_static_buffers *b = (lvdgs_static_buffers *)user;
+    if (!b || which < 0 || which > 2) return nullptr;
+    if (b->base[which] && bytes <= b->capacity[which]) return b->base[which];
+    return b->fallback ? b->fallback(b->fallback_user, which, bytes) : nullptr;
+}
+
 int lvdgs_zero_async(void *ptr, size_t bytes, void *stream) {
     if (!ptr && bytes) { set_error("zero_async: NULL pointer"); return 1; }
     if (bytes) LVDGS_CHECK(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream));

@@ -85,6 +85,65 @@ def _resize(_user, which, nbytes):
 
 _RESIZE_CB = _native.RESIZE_FN(_resize)
 
+# Host-side cost of a render matters: the reference calls the plugin 100 times per tracked frame.  The three opaque
+# buffers are therefore carved out of ONE allocation whose sizes are known before the call (lvdgs_get_*_layout, cached
+# per shape) and handed to the library through its own C callback (lvdgs_static_resize) -- no call back into Python per
+# buffer; only a request that does not fit (a repeated speculative tail) reaches `_resize` above.
+_layout_cache = {}            # (P, W, H) -> (geom bytes, img bytes);  capacity -> binning bytes
+_static_cb = None
+
+
+def debug_buffers(node):
+    """{LVDGS_BUF_GEOM / _BINNING / _IMG: uint8 tensor} of a forward, from its autograd node (`color.grad_fn`): the three
+    opaque buffers as lvdgs._native.debug_views reads them (parity tests / debugging only)."""
+    arena, geom, binning, img, extra = node.arena
+    out = {}
+    for which, (off, n) in ((0, geom), (1, binning), (2, img)):
+        if which in extra:
+            out[which] = extra[which]
+        elif n:
+            out[which] = arena[off:off + n]
+    return out
+
+
+def _layout_sizes(L, P, W, H):
+    key = (P, W, H)
+    v = _layout_cache.get(key)
+    if v is None:
+        gl, il = _native.GeomLayout(), _native.ImgLayout()
+        L.lvdgs_get_geom_layout(P, C.byref(gl)); L.lvdgs_get_img_layout(W, H, C.byref(il))
+        if len(_layout_cache) > 256:
+            _layout_cache.clear()
+        v = _layout_cache[key] = (int(gl.total), int(il.total))
+    return v
+
+
+def _binning_size(L, capacity):
+    v = _layout_cache.get(capacity)
+    if v is None:
+        bl = _native.BinningLayout()
+        L.lvdgs_get_binning_layout(capacity, C.byref(bl))
+        if len(_layout_cache) > 256:
+            _layout_cache.clear()
+        v = _layout_cache[capacity] = int(bl.total)
+    return v
+
+
+def _align(n):
+    return (n + 511) & ~511
+
+
+try:                                       # raw cudaStream_t of the current stream without building a torch.cuda.Stream object
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:                     # older / newer torch: the public, slower route
+    _raw_stream = None
+
+
+def _current_stream(dev):
+    if _raw_stream is not None and dev.index is not None:
+        return _raw_stream(dev.index)
+    return torch.cuda.current_stream(dev).cuda_stream
+
 
 def _select_device(L, dev):
     # unconditionally: torch.cuda.set_device / another engine may have changed the thread's device since the last call,
@@ -134,11 +193,24 @@ class _RasterizeGaussians(torch.autograd.Function):
         cap = C.c_int64(0)
         hint = _capacity_hint.get(dev.index, 0) if SPECULATIVE else 0
         _select_device(L, dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _current_stream(dev)
         p = _ptr
+        # one allocation for the geometry / image / binning state (binning only when a capacity hint sizes it)
+        global _static_cb
+        if _static_cb is None:
+            _static_cb = C.cast(L.lvdgs_static_resize, _native.RESIZE_FN)
+        g_bytes, i_bytes = _layout_sizes(L, P, W, H) if P > 0 else (0, _layout_sizes(L, 0, W, H)[1])
+        b_bytes = _binning_size(L, hint) if (hint > 0 and P > 0) else 0
+        o_img, o_bin = _align(g_bytes), _align(g_bytes) + _align(i_bytes)
+        arena = torch.empty(o_bin + _align(b_bytes), dtype=torch.uint8, device=dev)
+        a0 = arena.data_ptr()
+        sb = _native.StaticBuffers()
+        sb.base[0], sb.base[1], sb.base[2] = a0 if g_bytes else None, (a0 + o_bin) if b_bytes else None, a0 + o_img
+        sb.capacity[0], sb.capacity[1], sb.capacity[2] = g_bytes, b_bytes, i_bytes
+        sb.fallback, sb.fallback_user = _RESIZE_CB, None
         try:
             rc = L.lvdgs_rasterize_forward(C.byref(prm), p(bg), p(m3), p(cp), p(op), p(sc), p(rot), p(cov), p(view),
-                                           p(proj), p(praw), p(shs), p(campos), _RESIZE_CB, None, hint, p(color),
+                                           p(proj), p(praw), p(shs), p(campos), _static_cb, C.addressof(sb), hint, p(color),
                                            p(radii), p(depth), p(opac_img), p(n_touched), C.byref(R), C.byref(cap), stream)
         finally:
             _tls.store = None
@@ -147,9 +219,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.flags = prm.flags          # the backward must see the forward's sort layout
         ctx.num_rendered = R.value
         ctx.capacity = cap.value
-        if SPECULATIVE:   # decay slowly, grow at once
-            _capacity_hint[dev.index] = max(int(R.value * 1.25) + 65536, int(hint * 0.98))
-        ctx.bufs = bufs
+        if SPECULATIVE:   # grow at once; shrink (slowly) only when the hint is far above what the views need, so that the
+            want = int(R.value * 1.25) + 65536          # binning size -- and with it the cached layout -- is stable frame to frame
+            _capacity_hint[dev.index] = want if want > hint else (int(hint * 0.98) if want * 2 < hint else hint)
+        # live pointers of the three buffers: the arena's parts, or what the fallback callback allocated for an oversized request
+        ctx.buf_ptrs = tuple(bufs[w].data_ptr() if w in bufs else sb.base[w] for w in (0, 1, 2))
+        ctx.arena = (arena, (0, g_bytes), (o_bin, b_bytes), (o_img, i_bytes), bufs)      # keeps the memory alive until the backward has run
+        ctx.prm = prm
         ctx.shapes = (P, M)
         ctx.aux = (bg, view, proj, praw, campos)
         ctx.in_shapes = (None if theta is None else theta.shape, None if rho is None else rho.shape)
@@ -189,20 +265,20 @@ class _RasterizeGaussians(torch.autograd.Function):
             off += pad4(w * P)
         flat_s = flat[off:off + nscratch]
         g_tau = flat[0:6]
-        prm = _params(rs, P, M)
+        prm = ctx.prm                                          # the forward's parameter block (same shapes, same camera)
         prm.flags = ctx.flags | (32 if ZEROED_OUTPUTS else 0)   # LVDGS_FLAG_ZEROED_OUTPUTS
         if pose_only:
             prm.flags |= 8          # LVDGS_FLAG_POSE_ONLY
         _select_device(L, dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _current_stream(dev)
         p = _ptr
         gc = _prep(grad_out_color)
         gd = _prep(grad_out_depth) if grad_out_depth is not None else None
         go = _prep(grad_out_opacity) if (grad_out_opacity is not None and (FLAGS & 2)) else None
-        b = ctx.bufs
+        b0, b1, b2 = ctx.buf_ptrs
         rc = L.lvdgs_rasterize_backward(C.byref(prm), p(bg), p(m3), p(radii), p(cp), p(op), p(sc), p(rot), p(cov), p(view),
-                                        p(proj), p(praw), p(gc), p(gd), p(go), p(shs), p(campos), p(b.get(0)),
-                                        ctx.num_rendered, ctx.capacity, p(b.get(1)), p(b.get(2)), p(flat_s),
+                                        p(proj), p(praw), p(gc), p(gd), p(go), p(shs), p(campos), b0,
+                                        ctx.num_rendered, ctx.capacity, b1, b2, p(flat_s),
                                         flat_s.numel() * 4, p(g["means2D"]), p(g.get("colors")), p(g.get("opac")),
                                         p(g.get("means3D")), p(g.get("cov")), p(g.get("sh")), p(g.get("sc")), p(g.get("rot")),
                                         None, p(g_tau), stream)

@@ -110,6 +110,10 @@ class ImgLayout(C.Structure):
 
 RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int32, C.c_size_t)
 
+
+class StaticBuffers(C.Structure):        # lvdgs_static_buffers (include/lvdgs.h)
+    _fields_ = [("base", C.c_void_p * 3), ("capacity", C.c_size_t * 3), ("fallback", RESIZE_FN), ("fallback_user", C.c_void_p)]
+
 EXPORTS = ["lvdgs_version", "lvdgs_last_error", "lvdgs_set_device", "lvdgs_launch_count", "lvdgs_reset_launch_count", "lvdgs_tail_rerun_count",
            "lvdgs_profile_begin", "lvdgs_profile_end",
            "lvdgs_get_geom_layout", "lvdgs_get_binning_layout", "lvdgs_get_img_layout", "lvdgs_rasterize_forward",
@@ -119,7 +123,7 @@ EXPORTS = ["lvdgs_version", "lvdgs_last_error", "lvdgs_set_device", "lvdgs_launc
            "lvdgs_fused_loss_workspace_bytes", "lvdgs_fused_loss", "lvdgs_covis_counts", "lvdgs_n_obs",
            "lvdgs_compact_workspace_bytes", "lvdgs_compact_count", "lvdgs_compact_move", "lvdgs_pose_step", "lvdgs_gather_rows",
            "lvdgs_fp32_peak", "lvdgs_gaussian_activate", "lvdgs_gaussian_activation_backward",
-           "lvdgs_masked_ssim_loss_workspace_bytes", "lvdgs_masked_ssim_loss", "lvdgs_exchange_adam", "lvdgs_zero_async"]
+           "lvdgs_masked_ssim_loss_workspace_bytes", "lvdgs_masked_ssim_loss", "lvdgs_exchange_adam", "lvdgs_zero_async", "lvdgs_static_resize"]
 
 
 def lib():
@@ -159,6 +163,8 @@ def lib():
     L.lvdgs_exchange_adam.argtypes = [i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64, i64, vp, vp, i32, C.POINTER(i64),
                                       C.POINTER(f), C.POINTER(i64), i64, C.c_double, C.c_double, C.c_double, i32, vp, vp, vp, i32, vp]
     L.lvdgs_zero_async.argtypes = [vp, sz, vp]
+    L.lvdgs_static_resize.argtypes = [vp, i32, sz]
+    L.lvdgs_static_resize.restype = vp
     L.lvdgs_sort_workspace_bytes.argtypes = [i64]
     L.lvdgs_sort_workspace_bytes.restype = sz
     L.lvdgs_sort_pairs.argtypes = [i64, vp, vp, vp, vp, i32, vp, sz, C.POINTER(i32), vp]

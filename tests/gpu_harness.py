@@ -44,7 +44,7 @@ def run_cuda(sc, cam, bg, grads=None, device="cuda", use_precomp_color=False, us
     torch.cuda.synchronize()
     out = dict(color=color.detach().cpu().numpy(), radii=radii.cpu().numpy(), depth=depth.detach().cpu().numpy(),
                opacity=opacity.detach().cpu().numpy(), n_touched=n_touched.cpu().numpy())
-    ctx_bufs = color.grad_fn.bufs if hasattr(color.grad_fn, "bufs") else None
+    ctx_bufs = dgr.debug_buffers(color.grad_fn) if hasattr(color.grad_fn, "arena") else None
     R = color.grad_fn.num_rendered if hasattr(color.grad_fn, "num_rendered") else None
     internals = None
     if ctx_bufs is not None:
